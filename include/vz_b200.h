@@ -1,0 +1,294 @@
+/*
+ * vz_b200.h -- C ABI of the B200-native image -> LLM-embedding path of Vision-Zephyr.
+ *
+ * The reference (baohuyvanba/Vision-Zephyr) is pure Python: it has no FFI of its own.  The
+ * drop-in boundary is therefore the four Python callables listed in SURVEY.md section 8(b); the
+ * Python shim in vision-zephyr_b200/ keeps their signatures and calls the entry points below
+ * through ctypes.  Every entry point names the reference code it replaces (file:line, relative
+ * to the reference checkout).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - every pointer is a DEVICE pointer unless its name ends in _h (host).
+ *   - every launch goes to the cudaStream_t passed last (as void*); no entry point allocates,
+ *     synchronises or keeps mutable global state, so the library is re-entrant
+ *     (reference threading note: vis_zephyr/serve/api.py:161-177).
+ *   - return value: 0 = ok, <0 = vz_status; vz_status_string() names it.
+ *   - bf16 tensors are row-major; "ld" arguments are leading dimensions in ELEMENTS.
+ */
+#ifndef VZ_B200_H
+#define VZ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  VZ_OK = 0,
+  VZ_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, misaligned pointer/stride        */
+  VZ_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels were written for                   */
+  VZ_ERR_CUDA = -3,         /* a CUDA runtime/driver call failed (see vz_last_cuda_error)         */
+  VZ_ERR_NO_DEVICE = -4,    /* no sm_100 device                                                   */
+  VZ_ERR_WORKSPACE = -5     /* workspace too small                                                */
+} vz_status;
+
+/* constants.py:12-14 */
+#define VZ_IGNORE_INDEX (-100)
+#define VZ_IMAGE_TOKEN_INDEX (-200)
+
+const char* vz_status_string(int status);
+/* last cudaError_t seen by the calling thread inside this library (0 if none) */
+int vz_last_cuda_error(void);
+/* library/ABI version: major*100+minor */
+int vz_version(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* GEMM core (tcgen05 / TMEM / TMA).  out[M,N] = epilogue(A[M,K] * W[N,K]^T)                   */
+/* Replaces every torch.nn.Linear / F.linear / conv-as-GEMM call on the path                   */
+/* (SURVEY.md 2.2 rows K4, K5, K7, K8).                                                        */
+/* ------------------------------------------------------------------------------------------ */
+enum { VZ_ACT_NONE = 0, VZ_ACT_QUICK_GELU = 1, VZ_ACT_GELU_ERF = 2 };
+enum {
+  VZ_ROWS_PLAIN = 0,       /* out row = m, residual row = m                                       */
+  VZ_ROWS_PATCH_EMBED = 1, /* out row = m + m/rows_per + 1, residual row = 1 + m % rows_per
+                              (CLIP patch embedding + position embedding, rows_per = 576)         */
+  VZ_ROWS_RES_MOD = 2      /* out row = m, residual row = m % rows_per (broadcast residual)       */
+};
+
+typedef struct {
+  const void* A;        /* bf16 [M, lda]                       */
+  const void* W;        /* bf16 [N, ldw]                       */
+  void* out;            /* bf16 [*, ldo]                       */
+  const float* bias;    /* f32 [N] or NULL                     */
+  const void* residual; /* bf16 [*, ldr] or NULL (may alias out) */
+  int M, N, K;
+  int lda, ldw, ldo, ldr;
+  int act;              /* VZ_ACT_*                            */
+  int row_mode;         /* VZ_ROWS_*                           */
+  int rows_per;         /* see row_mode                        */
+  int force_simple;     /* 1 = debug path: plain CUDA-core GEMM (no tcgen05); for bring-up only */
+} vz_gemm_args;
+
+int vz_gemm_bf16(const vz_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Row kernels                                                                                 */
+/* ------------------------------------------------------------------------------------------ */
+/* LayerNorm over rows of width D (D % 8 == 0, D <= 8192), fp32 statistics, eps inside sqrt.
+ * Replaces nn.LayerNorm in HF CLIP (pre_layrnorm, layer_norm1/2) and QFormer
+ * (multimodal_projector/builder.py:15,18,27,68,70).                                           */
+int vz_layernorm_bf16(const void* x, int ldx, const float* gamma, const float* beta, void* out,
+                      int ldo, int M, int D, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (1) Preprocess: visual-prompt alpha blend + anyres resize/pad/tile + normalise + patchify    */
+/* Replaces vip_processor/conversation_generator.py:143-146 (alpha_composite),                  */
+/* multi_scale_process.py:71-114,136-183 (LANCZOS resize, pad, tile cut, global view) and      */
+/* CLIPImageProcessor.preprocess (rescale + normalise).                                        */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const uint8_t* src;  /* RGB u8 [H, W, 3] (PIL / numpy HWC)                                      */
+  const uint8_t* layers; /* RGBA u8 [n_layers, H, W, 4] host-rasterised overlays, or NULL         */
+  int W, H;
+  int prim_begin, prim_count; /* range into the primitive array, applied in order              */
+} vz_image_desc;
+
+enum { VZ_PRIM_LAYER = 0, VZ_PRIM_RECT = 1 };
+typedef struct {
+  int type;            /* VZ_PRIM_LAYER: composite layers[layer]; VZ_PRIM_RECT: PIL rectangle outline */
+  int layer;
+  int x0, y0, x1, y1;  /* rectangle corners (inclusive), already int()-truncated like PIL        */
+  int width;           /* outline width                                                          */
+  uint32_t rgba;       /* r | g<<8 | b<<16 | a<<24                                               */
+} vz_prim;
+
+typedef struct {
+  int image;           /* index into the image array                                              */
+  int out_w, out_h;    /* LANCZOS target size of the source image for this view                   */
+  int off_x, off_y;    /* where the resized image is pasted on the (black) canvas                 */
+  int tile_x, tile_y;  /* origin of this 336x336 tile on the canvas                               */
+  int tab_h, tab_v;    /* offsets (in int32 words) of the axis tables inside `tables`             */
+} vz_tile_desc;
+
+/* Axis table layout (int32 words), built on the host exactly like Pillow's precompute_coeffs
+ * (Resample.c) for (in_size -> out_size):  [0]=ksize, [1]=out_size, then out_size words xmin,
+ * then out_size words count, then out_size*ksize fixed-point (22-bit) coefficients.            */
+enum { VZ_OUT_PATCHES_BF16 = 0, VZ_OUT_CHW_F32 = 1 };
+
+/* out: VZ_OUT_PATCHES_BF16 -> bf16 [T*576, 592] (im2col rows in (c,ky,kx) order, K padded
+ *      588->592 with zeros);  VZ_OUT_CHW_F32 -> f32 [T,3,336,336] (the reference layout).
+ * lut768: f32 [3][256] normalisation table (generated by the oracle processor on a 0..255 ramp).
+ * images / prims / tiles / tables / lut768 are DEVICE arrays; max_src_w = widest source image and
+ * max_ksize = largest ksize among the tables (they size the kernel's shared-memory staging).    */
+int vz_preprocess(const vz_image_desc* images, int n_images, const vz_prim* prims, int n_prims,
+                  const vz_tile_desc* tiles, int n_tiles, const int32_t* tables,
+                  const float* lut768, int out_mode, void* out, int max_src_w, int max_ksize,
+                  void* stream);
+
+/* f32/bf16 pixel_values [T,3,336,336] -> bf16 patches [T*576,592]; the API-compatible entry of
+ * CLIPVisionTower.forward (vision_encoder/vision_encoder.py:80-117) when the caller already holds
+ * reference-style pixel tensors.  src_is_f32: 1 = float32, 0 = bf16.                            */
+int vz_patchify(const void* pixel_values, int src_is_f32, int T, void* patches, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (2) CLIP ViT-L/14-336 encoder + multi-layer fusion                                           */
+/* Replaces CLIPVisionTower.forward / feature_select (vision_encoder/vision_encoder.py:58-117)  */
+/* and DenseChannelIntegrationFusion.forward (gating_fusion/gating_fusion.py:22-50).            */
+/* ------------------------------------------------------------------------------------------ */
+#define VZ_VIT_LAYERS 24
+#define VZ_VIT_WIDTH 1024
+#define VZ_VIT_TOKENS 577
+#define VZ_VIT_PATCHES 576
+#define VZ_VIT_HEADS 16
+#define VZ_VIT_MLP 4096
+#define VZ_PATCH_K 592
+#define VZ_FUSED_WIDTH 5120
+
+typedef struct {
+  const float *ln1_g, *ln1_b;
+  const void* w_qkv;   /* bf16 [3072,1024] = cat(q_proj, k_proj, v_proj) */
+  const float* b_qkv;  /* f32 [3072] */
+  const void* w_o;     /* bf16 [1024,1024] */
+  const float* b_o;
+  const float *ln2_g, *ln2_b;
+  const void* w_fc1;   /* bf16 [4096,1024] */
+  const float* b_fc1;
+  const void* w_fc2;   /* bf16 [1024,4096] */
+  const float* b_fc2;
+} vz_vit_layer;
+
+typedef struct {
+  const void* patch_w;    /* bf16 [1024,592]  conv weight flattened (c,ky,kx), zero padded */
+  const void* class_emb;  /* bf16 [1024] */
+  const void* pos_emb;    /* bf16 [577,1024] */
+  const float *pre_ln_g, *pre_ln_b;
+  vz_vit_layer layers[VZ_VIT_LAYERS];
+} vz_vit_weights;
+
+size_t vz_vit_workspace_bytes(int T);
+
+/* patches: bf16 [T*576,592].  fused_out: bf16 [T*576,5120] =
+ * cat(mean(h4..h8), mean(h9..h13), mean(h14..h18), mean(h19..h23), h24)[:,1:].
+ * If norm_g/norm_b are non-NULL the QFormer.pre_norm LayerNorm(5120)
+ * (multimodal_projector/builder.py:68,74) is applied in the same kernel.
+ * hidden_out (optional, may be NULL): bf16 [25][T*577,1024] copy-out of all hidden states
+ * (tests only).                                                                                */
+int vz_vit_forward(const vz_vit_weights* w, const void* patches, int T, void* fused_out,
+                   const float* norm_g, const float* norm_b, void* hidden_out, void* workspace,
+                   size_t workspace_bytes, int force_simple_gemm, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (3) Q-Former projector                                                                      */
+/* Replaces QFormer.forward / QFormerBlock.forward (multimodal_projector/builder.py:34-92).     */
+/* ------------------------------------------------------------------------------------------ */
+#define VZ_QF_BLOCKS 8
+#define VZ_QF_QUERIES 32
+#define VZ_QF_WIDTH 4096
+#define VZ_QF_HEADS 8
+#define VZ_QF_HEAD_DIM 512
+#define VZ_QF_FFN 8192
+
+typedef struct {
+  const float *n1_g, *n1_b, *n2_g, *n2_b, *n3_g, *n3_b;
+  const void* sa_in_w;   /* bf16 [12288,4096] */
+  const float* sa_in_b;  /* f32 [12288] */
+  const void* sa_out_w;  /* bf16 [4096,4096] */
+  const float* sa_out_b;
+  const void* ca_q_w;    /* bf16 [4096,4096] */
+  const float* ca_in_b;  /* f32 [12288] (q,k,v biases) */
+  const void* ca_out_w;  /* bf16 [4096,4096] */
+  const float* ca_out_b;
+  const void* ffn1_w;    /* bf16 [8192,4096] */
+  const float* ffn1_b;
+  const void* ffn2_w;    /* bf16 [4096,8192] */
+  const float* ffn2_b;
+} vz_qf_block;
+
+typedef struct {
+  const void* learned_queries; /* bf16 [32,4096] */
+  const float *pre_g, *pre_b;  /* LayerNorm(5120) */
+  const float *norm_g, *norm_b;/* LayerNorm(4096) */
+  const void* kv_w;            /* bf16 [8*2*4096, 5120]: blocks' (k_proj_weight, v_proj_weight) stacked */
+  const float* kv_b;           /* f32 [65536]: matching slices of cross_attn.in_proj_bias        */
+  vz_qf_block blocks[VZ_QF_BLOCKS];
+} vz_qf_weights;
+
+size_t vz_qformer_workspace_bytes(int T, int n_samples, int text_rows);
+
+/* feats: bf16 [T*576,5120] (already pre_norm'ed if feats_normed, else pre_norm is applied here).
+ * Text conditioning (vis_zephyr_arch.py:157-195 + builder.py:76-87), dead rows removed:
+ *   text_emb  bf16 [text_rows+1, 4096]: the non-image token embeddings of all samples packed
+ *             back to back, followed by ONE all-zero row (the zero padding row of :181-186);
+ *   text_off  int32 [n_samples+1] prefix offsets of each sample's rows in text_emb;
+ *   L         batch-global max text length (quirk Q3: zero-pad rows take part in the softmax);
+ *   tile_sample int32 [T] sample index of each tile.
+ * text_emb == NULL reproduces QFormer.forward(features, text_embeddings=None).
+ * out: bf16 [T*32, ldo] (ldo >= 4096; may point into the all-gather buffer).                   */
+int vz_qformer_forward(const vz_qf_weights* w, const void* feats, int feats_normed, int T,
+                       const void* text_emb, const int32_t* text_off, int text_rows,
+                       int n_samples, int L, const int32_t* tile_sample, void* out, int ldo,
+                       void* workspace, size_t workspace_bytes, int force_simple_gemm,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (4) merge (anyres unpad / image_newline) + splice                                           */
+/* Replaces vis_zephyr_arch.py:157-195 (text rows), :214-333 (splice), :396-473 (merge),        */
+/* :476-530 (pad + collate).                                                                   */
+/* ------------------------------------------------------------------------------------------ */
+enum { VZ_MERGE_FLAT = 0, VZ_MERGE_SPATIAL = 1, VZ_MERGE_SPATIAL_UNPAD = 2, VZ_MERGE_SINGLE_NEWLINE = 3 };
+
+/* One entry per image slot (one projected image = one slot, vis_zephyr_arch.py:283-296).      */
+typedef struct {
+  int row_base;   /* first row of this image in the projector output [sum T_i * hw, D]           */
+  int n_rows;     /* rows this slot contributes after merging (host-computed, exact)             */
+  int merge;      /* VZ_MERGE_*                                                                  */
+  int hw;         /* rows per tile (h*w)                                                         */
+  int h, w;       /* feature-map side lengths per tile                                           */
+  int n_w, n_h;   /* anyres grid (calculate_grid_shape)                                          */
+  int y0, y1, x0, x1; /* unpad_image crop on the [n_h*h, n_w*w] map (as written, quirk Q4)       */
+} vz_slot_desc;
+
+/* Plan pass: one CTA, warp-level prefix sums.  Outputs (all int32):
+ *   tok_dest [B,S]   destination row of each kept non-image token inside its sample, -1 else
+ *   slot_dest [n_slots*2] (sample, first destination row) of each consumed slot, -1 if unused
+ *   lengths  [B]     spliced length per sample (after optional truncation)
+ *   text_len [B]     count of ids != IMAGE_TOKEN_INDEX over the whole row (vis_zephyr_arch.py:168)
+ *   totals   [4]     {Lmax, max text_len, slots consumed, sum text_len}
+ * mask: uint8 [B,S] (attention_mask.bool()) or NULL (all ones).                               */
+int vz_splice_plan(const int64_t* input_ids, const uint8_t* mask, int B, int S,
+                   const vz_slot_desc* slots, int n_slots, int max_len, int32_t* tok_dest,
+                   int32_t* slot_dest, int32_t* lengths, int32_t* text_len, int32_t* totals,
+                   void* stream);
+
+/* Gather pass for text conditioning: text_emb[text_off[b] + j] = embed[id] for the j-th
+ * non-image token of sample b; row `sum text_len` is set to zero.  text_off int32 [B+1] is
+ * written too.  elem_bytes = 2 (bf16/fp16) or 4 (f32); D*elem_bytes % 16 == 0.                 */
+int vz_text_gather(const int64_t* input_ids, int B, int S, const void* embed_table, int D,
+                   int elem_bytes, const int32_t* text_len, void* text_emb, int32_t* text_off,
+                   void* stream);
+
+/* Scatter pass.  vis: projector output rows [*, D] (ldv elements per row), image_newline [D] or
+ * NULL, labels int64 [B,S] or NULL (=> IGNORE_INDEX everywhere).  Outputs: out_embeds [B,Lout,D],
+ * out_labels int64 [B,Lout], out_mask uint8 [B,Lout], out_pos int64 [B,Lout]. Every output
+ * element is written exactly once (padding included), so the buffers need no memset.
+ * slot_prefix int32 [n_slots+1]: exclusive prefix sum of slots[].n_rows (host-known, uploaded with
+ * the slot table); total_vis_rows = slot_prefix[n_slots].                                       */
+int vz_splice_scatter(const int64_t* input_ids, const int64_t* labels, int B, int S,
+                      const void* embed_table, const void* vis, int ldv, const void* image_newline,
+                      int D, int elem_bytes, const vz_slot_desc* slots, int n_slots,
+                      const int32_t* slot_prefix, int total_vis_rows, const int32_t* tok_dest, const int32_t* slot_dest, const int32_t* lengths,
+                      int Lout, int pad_left, void* out_embeds, int64_t* out_labels,
+                      uint8_t* out_mask, int64_t* out_pos, void* stream);
+
+/* Merge only (vis_zephyr_arch.py:396-473) for one slot list: out rows [sum n_rows, D].          */
+int vz_merge_rows(const void* vis, int ldv, const void* image_newline, int D, int elem_bytes,
+                  const vz_slot_desc* slots, int n_slots, const int32_t* out_row_base, void* out,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VZ_B200_H */

@@ -1,0 +1,121 @@
+"""Host-side integer logic of the product package (no GPU): resolution choice, grid shapes, LANCZOS
+tables, unpad bounds / merged row counts, image sharding and the gloo exchange."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import vision_zephyr_b200 as vz
+from vision_zephyr_b200 import anyres
+from vision_zephyr_b200.dist import gather_visual_tokens, shard_images
+from helpers import PINPOINTS_C3, PINPOINTS_SHIPPED
+from oracle import pil_ops as P
+
+
+def test_shipped_pinpoints_known_answers():
+    """SURVEY.md 8(c) known-answer vectors."""
+    pins = "'[[336, 672], [672, 336], [336, 1008], [1008, 336]]'"  # doubly quoted, as in config.json:16
+    assert anyres.select_best_fit_resolution((637, 336), PINPOINTS_SHIPPED) == (672, 336)
+    assert anyres.select_best_fit_resolution((681, 336), PINPOINTS_SHIPPED) == (1008, 336)
+    assert anyres.select_best_fit_resolution((1920, 804), PINPOINTS_SHIPPED) == (1008, 336)
+    assert anyres.select_best_fit_resolution((336, 336), PINPOINTS_SHIPPED) == (336, 672)
+    assert anyres.calculate_grid_shape((637, 336), pins, 336) == (2, 1)
+    assert anyres.calculate_grid_shape((1000, 900), str(PINPOINTS_C3), 336) == (2, 2)
+    assert len(anyres.anyres_views((1000, 900), PINPOINTS_C3)[0]) == 5
+    with pytest.raises(ValueError):
+        anyres.calculate_grid_shape((10, 10), "7", 336)
+
+
+@pytest.mark.parametrize("n_in,n_out", [(1000, 672), (900, 604), (336, 336), (200, 336), (1920, 336), (17, 336), (804, 140)])
+def test_lanczos_table_equals_oracle_matrix(n_in, n_out):
+    t = anyres.lanczos_table(n_in, n_out)
+    ks, n = int(t[0]), int(t[1])
+    assert n == n_out
+    xmin, cnt, kk = t[2:2 + n], t[2 + n:2 + 2 * n], t[2 + 2 * n:].reshape(n, ks)
+    K = np.zeros((n_out, n_in), np.int64)
+    for x in range(n):
+        K[x, xmin[x]:xmin[x] + cnt[x]] = kk[x, :cnt[x]]
+        assert not kk[x, cnt[x]:].any()
+    ref = P.coeff_matrix(n_in, n_out) if n_in != n_out else np.eye(n_in, dtype=np.int64) * (1 << 22)
+    assert np.array_equal(K, ref)
+
+
+def test_merged_row_counts_match_reference(golden_dir):
+    g = np.load(f"{golden_dir}/golden_merge.npz")
+    for c in range(10):
+        W, H, n_w, n_h, T, unpad = (int(v) for v in g[f"case{c}_meta"])
+        d = anyres.slot_descriptor(0, T, 576, "spatial_unpad" if unpad else "spatial", "anyres", (W, H),
+                                   str(PINPOINTS_C3), 336, 24)
+        assert d["n_rows"] == g[f"case{c}_rows"].shape[0], c
+        assert (d["n_w"], d["n_h"]) == (n_w, n_h)
+        s = anyres.slot_descriptor(0, 1, 576, "spatial_unpad" if unpad else "spatial")
+        assert s["n_rows"] == g[f"case{c}_single_rows"].shape[0]
+    assert anyres.slot_descriptor(64, 5, 32, "flat")["n_rows"] == 160
+    with pytest.raises(ValueError):
+        anyres.slot_descriptor(0, 1, 32, "bogus")
+    with pytest.raises(NotImplementedError):
+        anyres.slot_descriptor(0, 5, 576, "spatial", "square", (10, 10), str(PINPOINTS_C3), 336, 24)
+
+
+def test_builders_keep_reference_errors():
+    from types import SimpleNamespace
+    with pytest.raises(ValueError, match="Unknown vision tower path"):
+        vz.build_vision_tower(SimpleNamespace(mm_vision_tower="/no/such/dir", mm_vision_select_layer="-2"))
+    t = vz.build_vision_tower(SimpleNamespace(mm_vision_tower="openai/clip-vit-large-patch14-336",
+                                              mm_vision_select_layer="-2,-5,-8,-11,6"), delay_load=True)
+    assert (t.hidden_size, t.num_patches, t.is_loaded, t.select_layers) == (5120, 576, False, [-2, -5, -8, -11, 6])
+    with pytest.raises(ValueError, match="Invalid format"):
+        vz.build_vision_tower(SimpleNamespace(mm_vision_tower="openai/x", mm_vision_select_layer="a,b"), delay_load=True)
+    assert vz.build_vision_projector is vz.build_multimodal_projector
+
+
+def test_projector_state_dict_keys_match_reference():
+    from types import SimpleNamespace
+    with torch.device("meta"):
+        p = vz.build_multimodal_projector(SimpleNamespace(hidden_size=4096))
+    keys = set(p.state_dict().keys())
+    assert len(keys) == 1 + 8 * 20 + 4
+    for k in ["learned_queries", "blocks.0.self_attn.in_proj_weight", "blocks.7.cross_attn.k_proj_weight",
+              "blocks.3.cross_attn.in_proj_bias", "blocks.3.cross_attn.out_proj.bias", "blocks.5.ffn.0.weight",
+              "blocks.5.ffn.2.bias", "blocks.1.norm3.weight", "pre_norm.bias", "norm.weight"]:
+        assert k in keys, k
+    assert sum(v.numel() for v in p.state_dict().values()) == 1678428160
+    with pytest.raises(ValueError):
+        vz.build_multimodal_projector(SimpleNamespace(hidden_size=1024))
+
+
+def test_shard_images_is_a_contiguous_partition():
+    for tiles, world in [([5] * 8, 2), ([5] * 64, 8), ([3, 4, 5, 1, 2], 3), ([5] * 3, 8), ([1], 4)]:
+        b = shard_images(tiles, world)
+        assert len(b) == world and b[0][0] == 0 and b[-1][1] == len(tiles)
+        assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+    assert shard_images([5] * 64, 8) == [(8 * r, 8 * r + 8) for r in range(8)]
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tiles = [5, 3, 4, 5]
+    bounds = shard_images(tiles, world)
+    rows = [sum(tiles[a:b]) * 32 for a, b in bounds]
+    start = sum(rows[:rank])
+    local = (torch.arange(rows[rank] * 8, dtype=torch.float32).reshape(rows[rank], 8) + start * 8).to(torch.bfloat16)
+    full = gather_visual_tokens(local, rows)
+    ref = torch.arange(sum(rows) * 8, dtype=torch.float32).reshape(-1, 8).to(torch.bfloat16)
+    q.put((rank, bool(torch.equal(full, ref)), tuple(full.shape)))
+    dist.destroy_process_group()
+
+
+def test_gather_visual_tokens_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 500
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(60) for p in procs]
+    assert res == [(0, True, (17 * 32, 8)), (1, True, (17 * 32, 8))]

@@ -1,0 +1,148 @@
+"""ctypes binding of libvz_b200.so (the C ABI declared in include/vz_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvz_b200.so")
+
+VIT_LAYERS = 24
+QF_BLOCKS = 8
+
+
+class VzError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("W", C.c_void_p), ("out", C.c_void_p), ("bias", C.c_void_p),
+        ("residual", C.c_void_p),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("lda", C.c_int), ("ldw", C.c_int), ("ldo", C.c_int), ("ldr", C.c_int),
+        ("act", C.c_int), ("row_mode", C.c_int), ("rows_per", C.c_int), ("force_simple", C.c_int),
+    ]
+
+
+class ImageDesc(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("layers", C.c_void_p), ("W", C.c_int), ("H", C.c_int),
+                ("prim_begin", C.c_int), ("prim_count", C.c_int)]
+
+
+class Prim(C.Structure):
+    _fields_ = [("type", C.c_int), ("layer", C.c_int), ("x0", C.c_int), ("y0", C.c_int),
+                ("x1", C.c_int), ("y1", C.c_int), ("width", C.c_int), ("rgba", C.c_uint32)]
+
+
+class TileDesc(C.Structure):
+    _fields_ = [("image", C.c_int), ("out_w", C.c_int), ("out_h", C.c_int), ("off_x", C.c_int),
+                ("off_y", C.c_int), ("tile_x", C.c_int), ("tile_y", C.c_int), ("tab_h", C.c_int),
+                ("tab_v", C.c_int)]
+
+
+class VitLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_g", "ln2_b", "w_fc1", "b_fc1",
+        "w_fc2", "b_fc2")]
+
+
+class VitWeights(C.Structure):
+    _fields_ = [("patch_w", C.c_void_p), ("class_emb", C.c_void_p), ("pos_emb", C.c_void_p),
+                ("pre_ln_g", C.c_void_p), ("pre_ln_b", C.c_void_p),
+                ("layers", VitLayer * VIT_LAYERS)]
+
+
+class QfBlock(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "n1_g", "n1_b", "n2_g", "n2_b", "n3_g", "n3_b", "sa_in_w", "sa_in_b", "sa_out_w", "sa_out_b",
+        "ca_q_w", "ca_in_b", "ca_out_w", "ca_out_b", "ffn1_w", "ffn1_b", "ffn2_w", "ffn2_b")]
+
+
+class QfWeights(C.Structure):
+    _fields_ = [("learned_queries", C.c_void_p), ("pre_g", C.c_void_p), ("pre_b", C.c_void_p),
+                ("norm_g", C.c_void_p), ("norm_b", C.c_void_p), ("kv_w", C.c_void_p),
+                ("kv_b", C.c_void_p), ("blocks", QfBlock * QF_BLOCKS)]
+
+
+class SlotDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "row_base", "n_rows", "merge", "hw", "h", "w", "n_w", "n_h", "y0", "y1", "x0", "x1")]
+
+
+# enums of include/vz_b200.h
+ACT_NONE, ACT_QUICK_GELU, ACT_GELU_ERF = 0, 1, 2
+ROWS_PLAIN, ROWS_PATCH_EMBED, ROWS_RES_MOD = 0, 1, 2
+PRIM_LAYER, PRIM_RECT = 0, 1
+OUT_PATCHES_BF16, OUT_CHW_F32 = 0, 1
+MERGE_FLAT, MERGE_SPATIAL, MERGE_SPATIAL_UNPAD, MERGE_SINGLE_NEWLINE = 0, 1, 2, 3
+
+# every symbol include/vz_b200.h declares: name -> (restype, argtypes)
+_vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
+SYMBOLS = {
+    "vz_status_string": (C.c_char_p, [_i]),
+    "vz_last_cuda_error": (_i, []),
+    "vz_version": (_i, []),
+    "vz_gemm_bf16": (_i, [C.POINTER(GemmArgs), _vp]),
+    "vz_layernorm_bf16": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, C.c_float, _vp]),
+    "vz_preprocess": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp]),
+    "vz_patchify": (_i, [_vp, _i, _i, _vp, _vp]),
+    "vz_vit_workspace_bytes": (_sz, [_i]),
+    "vz_vit_forward": (_i, [C.POINTER(VitWeights), _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "vz_qformer_workspace_bytes": (_sz, [_i, _i, _i]),
+    "vz_qformer_forward": (_i, [C.POINTER(QfWeights), _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i,
+                                _vp, _sz, _i, _vp]),
+    "vz_splice_plan": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vz_text_gather": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "vz_splice_scatter": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp,
+                               _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "vz_merge_rows": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise VzError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise VzError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C vision-zephyr_b200/csrc`). There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        lib = load()
+        msg = lib.vz_status_string(status).decode()
+        extra = ""
+        if status == -3:
+            extra = f" (cuda error {lib.vz_last_cuda_error()})"
+        raise VzError(f"{what}: {msg}{extra}")
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

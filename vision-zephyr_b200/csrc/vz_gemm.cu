@@ -1,0 +1,375 @@
+// vz_gemm.cu -- persistent, warp-specialised bf16 GEMM for sm_100a:
+//   out[M,N] = epilogue( A[M,K] * W[N,K]^T )          (both operands K-major, fp32 accumulate)
+// TMA (cp.async.bulk.tensor, 128B swizzle) -> shared-memory ring -> tcgen05.mma (one issuing
+// thread, 128xBN accumulator in TMEM, double buffered) -> tcgen05.ld epilogue with fused
+// bias / quick-GELU / erf-GELU / residual / row remapping.
+//
+// This one kernel serves every Linear on the path (K4 patch embedding, K5 CLIP
+// q/k/v/out/fc1/fc2, K7 the stacked cross-attention K/V projection, K8 the Q-Former linears).
+#include "vz_common.cuh"
+
+namespace vz {
+
+thread_local int g_last_cuda_error = 0;
+
+namespace {
+
+constexpr int BM = 128;       // UMMA M (cta_group::1)
+constexpr int BK = 64;        // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int UMMA_K = 16;    // fixed for 16-bit inputs
+constexpr int kThreads = 256; // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int GROUP_N = 8;    // n-blocks per rasterisation band (keeps the W band + A strip in L2)
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + align slack
+};
+
+struct GemmDev {
+  __nv_bfloat16* out;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  int M, N, K;
+  int ldo, ldr;
+  int act, row_mode, rows_per;
+  int num_m, num_n, num_k;
+};
+
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
+  const int per_band = num_m * GROUP_N;
+  const int band = tile / per_band;
+  const int within = tile - band * per_band;
+  const int n0 = band * GROUP_N;
+  const int gsz = min(GROUP_N, num_n - n0);
+  m_blk = within / gsz;
+  n_blk = n0 + (within - m_blk * gsz);
+}
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == VZ_ACT_QUICK_GELU) {
+    return x / (1.0f + __expf(-1.702f * x));
+  } else if (act == VZ_ACT_GELU_ERF) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  }
+  return x;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                         const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + C::STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * C::STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.num_m * p.num_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk);
+        for (int kb = 0; kb < p.num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          tma_load_2d(&tmA, &full_bar[stage], sA + stage * C::A_BYTES, kb * BK, m_blk * BM);
+          tma_load_2d(&tmB, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK, n_blk * BN);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 300 + stage);
+          tc_fence_after();
+          const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(sA + stage * C::A_BYTES));
+          const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(sB + stage * C::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 B (16 bf16) along K inside the swizzle atom: +2 in the (addr>>4) field
+            umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================ epilogue ================================
+    const int q = warp - 4;  // TMEM lane quarter == warp % 4
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk);
+      mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+      tc_fence_after();
+      const int m = m_blk * BM + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      int out_row = m, res_row = m;
+      if (p.row_mode == VZ_ROWS_PATCH_EMBED) {
+        const int img = m / p.rows_per;
+        out_row = m + img + 1;
+        res_row = 1 + (m - img * p.rows_per);
+      } else if (p.row_mode == VZ_ROWS_RES_MOD) {
+        res_row = m % p.rows_per;
+      }
+      __nv_bfloat16* out_ptr = p.out + (size_t)out_row * p.ldo;
+      const __nv_bfloat16* res_ptr =
+          p.residual ? p.residual + (size_t)res_row * p.ldr : nullptr;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (p.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(b4 + i);
+            v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+          }
+        }
+        if (p.act != VZ_ACT_NONE) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], p.act);
+        }
+        if (row_ok) {
+          if (res_ptr) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(res_ptr + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 w = r4[i];
+              v[8 * i + 0] += bf16_lo(w.x); v[8 * i + 1] += bf16_hi(w.x);
+              v[8 * i + 2] += bf16_lo(w.y); v[8 * i + 3] += bf16_hi(w.y);
+              v[8 * i + 4] += bf16_lo(w.z); v[8 * i + 5] += bf16_hi(w.z);
+              v[8 * i + 6] += bf16_lo(w.w); v[8 * i + 7] += bf16_hi(w.w);
+            }
+          }
+          uint4* o4 = reinterpret_cast<uint4*>(out_ptr + col0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 w;
+            w.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+            w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+            w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+            w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+            o4[i] = w;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Bring-up / cross-check path: plain CUDA-core tiled GEMM with the same epilogue semantics.
+// Selected only by force_simple (tests use it to tell a tcgen05 bug from a model-graph bug).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gemm_bf16_simple_kernel(const __nv_bfloat16* __restrict__ A, int lda,
+                        const __nv_bfloat16* __restrict__ W, int ldw, const GemmDev p) {
+  __shared__ float sa[16][17];
+  __shared__ float sw[16][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m = blockIdx.y * 16 + ty;
+  const int n = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < p.K; k0 += 16) {
+    const int ka = k0 + tx;
+    sa[ty][tx] = (m < p.M && ka < p.K) ? __bfloat162float(A[(size_t)m * lda + ka]) : 0.f;
+    const int wn = blockIdx.x * 16 + ty;
+    sw[ty][tx] = (wn < p.N && ka < p.K) ? __bfloat162float(W[(size_t)wn * ldw + ka]) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += sa[ty][k] * sw[tx][k];
+    __syncthreads();
+  }
+  if (m >= p.M || n >= p.N) return;
+  int out_row = m, res_row = m;
+  if (p.row_mode == VZ_ROWS_PATCH_EMBED) {
+    const int img = m / p.rows_per;
+    out_row = m + img + 1;
+    res_row = 1 + (m - img * p.rows_per);
+  } else if (p.row_mode == VZ_ROWS_RES_MOD) {
+    res_row = m % p.rows_per;
+  }
+  float v = acc;
+  if (p.bias) v += p.bias[n];
+  v = act_apply(v, p.act);
+  if (p.residual) v += __bfloat162float(p.residual[(size_t)res_row * p.ldr + n]);
+  p.out[(size_t)out_row * p.ldo + n] = __float2bfloat16_rn(v);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(ptr);
+  }();
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner dim = K (contiguous), outer dim = rows; box = {64, box_rows}.
+int make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return VZ_ERR_CUDA;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_last_cuda_error = 100000 + (int)r;
+    return VZ_ERR_CUDA;
+  }
+  return VZ_OK;
+}
+
+template <int BN>
+int launch_tc(const vz_gemm_args& a, const GemmDev& p, int num_sms, cudaStream_t st) {
+  using C = Cfg<BN>;
+  CUtensorMap tmA, tmB;
+  VZ_TRY(make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM));
+  VZ_TRY(make_tmap(&tmB, a.W, a.N, a.K, a.ldw, BN));
+  static bool attr_done = false;  // idempotent attribute; benign race
+  if (!attr_done) {
+    VZ_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int tiles = p.num_m * p.num_n;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_bf16_tcgen05_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+  VZ_LAUNCH_CHECK();
+  return VZ_OK;
+}
+
+}  // namespace
+
+int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
+  if (!a.A || !a.W || !a.out) return VZ_ERR_BAD_ARG;
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) return VZ_ERR_BAD_ARG;
+  if ((a.lda & 7) || (a.ldw & 7) || (a.ldo & 7) || (a.residual && (a.ldr & 7))) return VZ_ERR_BAD_ARG;
+  if (!aligned16(a.A) || !aligned16(a.W) || !aligned16(a.out) || (a.residual && !aligned16(a.residual)) ||
+      (a.bias && !aligned16(a.bias)))
+    return VZ_ERR_BAD_ARG;
+  if (a.N % 32 != 0 || a.K % 8 != 0) return VZ_ERR_UNSUPPORTED;
+  if (a.row_mode != VZ_ROWS_PLAIN && a.rows_per <= 0) return VZ_ERR_BAD_ARG;
+
+  GemmDev p;
+  p.out = reinterpret_cast<__nv_bfloat16*>(a.out);
+  p.bias = a.bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual);
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.ldo = a.ldo; p.ldr = a.ldr;
+  p.act = a.act; p.row_mode = a.row_mode; p.rows_per = a.rows_per;
+  p.num_m = (a.M + BM - 1) / BM;
+  p.num_k = (a.K + BK - 1) / BK;
+
+  if (a.force_simple) {
+    p.num_n = 0;
+    dim3 grid((a.N + 15) / 16, (a.M + 15) / 16);
+    gemm_bf16_simple_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a.A), a.lda,
+                                                  reinterpret_cast<const __nv_bfloat16*>(a.W), a.ldw, p);
+    VZ_LAUNCH_CHECK();
+    return VZ_OK;
+  }
+
+  int dev = 0, num_sms = 0;
+  VZ_CUDA_CHECK(cudaGetDevice(&dev));
+  VZ_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  // 128x256 tiles when they still fill the machine, otherwise 128x128 for more CTAs
+  const long tiles256 = (long)p.num_m * ((a.N + 255) / 256);
+  if (a.N % 256 == 0 && tiles256 >= num_sms) {
+    p.num_n = a.N / 256;
+    return launch_tc<256>(a, p, num_sms, st);
+  }
+  p.num_n = (a.N + 127) / 128;
+  return launch_tc<128>(a, p, num_sms, st);
+}
+
+}  // namespace vz
+
+extern "C" int vz_gemm_bf16(const vz_gemm_args* args, void* stream) {
+  if (!args) return VZ_ERR_BAD_ARG;
+  return vz::gemm_launch(*args, reinterpret_cast<cudaStream_t>(stream));
+}

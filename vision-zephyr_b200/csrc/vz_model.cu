@@ -1,0 +1,232 @@
+// vz_model.cu -- host-side orchestration (C++) of the two tensor-core subsystems:
+//   vz_vit_forward      CLIP ViT-L/14-336 + multi-layer fusion (+ optional QFormer.pre_norm)
+//   vz_qformer_forward  8-block Q-Former projector with dead-row elimination in block 0
+// Everything is enqueued on the caller's stream; no allocation, no synchronisation.
+#include "vz_common.cuh"
+
+namespace vz {
+namespace {
+
+struct Bump {
+  uint8_t* base; size_t off, cap;
+  void* take(size_t bytes) {
+    const size_t a = (off + 255) & ~(size_t)255;
+    off = a + bytes;
+    return base ? base + a : nullptr;
+  }
+};
+
+constexpr size_t kB16 = 2;
+
+int gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act,
+         const void* residual, int ldr, void* out, int ldo, int row_mode, int rows_per, int simple,
+         cudaStream_t st) {
+  vz_gemm_args g;
+  g.A = A; g.W = W; g.out = out; g.bias = bias; g.residual = residual;
+  g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldo = ldo; g.ldr = ldr;
+  g.act = act; g.row_mode = row_mode; g.rows_per = rows_per; g.force_simple = simple;
+  return gemm_launch(g, st);
+}
+
+struct VitWs {
+  void* hs[VZ_VIT_LAYERS + 1];
+  void *xn, *qkv, *attn, *mid, *h;
+  size_t total;
+};
+
+VitWs vit_layout(void* base, int T) {
+  Bump b{reinterpret_cast<uint8_t*>(base), 0, 0};
+  const size_t M = (size_t)T * VZ_VIT_TOKENS;
+  VitWs w;
+  // hidden states are contiguous so tests can copy them out in one go
+  uint8_t* hs0 = reinterpret_cast<uint8_t*>(b.take((VZ_VIT_LAYERS + 1) * M * VZ_VIT_WIDTH * kB16));
+  for (int i = 0; i <= VZ_VIT_LAYERS; ++i) w.hs[i] = base ? hs0 + (size_t)i * M * VZ_VIT_WIDTH * kB16 : nullptr;
+  w.xn = b.take(M * VZ_VIT_WIDTH * kB16);
+  w.qkv = b.take(M * 3 * VZ_VIT_WIDTH * kB16);
+  w.attn = b.take(M * VZ_VIT_WIDTH * kB16);
+  w.mid = b.take(M * VZ_VIT_WIDTH * kB16);
+  w.h = b.take(M * VZ_VIT_MLP * kB16);
+  w.total = b.off + 256;
+  return w;
+}
+
+struct QfWs {
+  void *featsN, *KV, *x, *xn, *qkv, *attn, *q, *hbuf, *q0n, *qkv0, *tn, *kv_text, *attn0, *x1;
+  size_t total;
+};
+
+QfWs qf_layout(void* base, int T, int n_samples, int text_rows) {
+  Bump b{reinterpret_cast<uint8_t*>(base), 0, 0};
+  const size_t P = (size_t)T * VZ_VIT_PATCHES, M = (size_t)T * VZ_QF_QUERIES;
+  const size_t R1 = (size_t)text_rows + 1, Bs = (size_t)(n_samples > 0 ? n_samples : 1) * VZ_QF_QUERIES;
+  QfWs w;
+  w.featsN = b.take(P * VZ_FUSED_WIDTH * kB16);
+  w.KV = b.take(P * (size_t)(VZ_QF_BLOCKS * 2 * VZ_QF_WIDTH) * kB16);
+  w.x = b.take(M * VZ_QF_WIDTH * kB16);
+  w.xn = b.take(M * VZ_QF_WIDTH * kB16);
+  w.qkv = b.take(M * 3 * VZ_QF_WIDTH * kB16);
+  w.attn = b.take(M * VZ_QF_WIDTH * kB16);
+  w.q = b.take(M * VZ_QF_WIDTH * kB16);
+  w.hbuf = b.take(M * VZ_QF_FFN * kB16);
+  w.q0n = b.take((size_t)VZ_QF_QUERIES * VZ_QF_WIDTH * kB16);
+  w.qkv0 = b.take((size_t)VZ_QF_QUERIES * 3 * VZ_QF_WIDTH * kB16);
+  w.tn = b.take(R1 * VZ_QF_WIDTH * kB16);
+  w.kv_text = b.take(R1 * 2 * VZ_QF_WIDTH * kB16);
+  w.attn0 = b.take(Bs * VZ_QF_WIDTH * kB16);
+  w.x1 = b.take(Bs * VZ_QF_WIDTH * kB16);
+  w.total = b.off + 256;
+  return w;
+}
+
+}  // namespace
+}  // namespace vz
+
+using namespace vz;
+
+extern "C" size_t vz_vit_workspace_bytes(int T) { return T > 0 ? vit_layout(nullptr, T).total : 0; }
+
+extern "C" size_t vz_qformer_workspace_bytes(int T, int n_samples, int text_rows) {
+  return T > 0 ? qf_layout(nullptr, T, n_samples, text_rows < 0 ? 0 : text_rows).total : 0;
+}
+
+extern "C" int vz_vit_forward(const vz_vit_weights* w, const void* patches, int T, void* fused_out,
+                              const float* norm_g, const float* norm_b, void* hidden_out, void* workspace,
+                              size_t workspace_bytes, int simple, void* stream) {
+  if (!w || !patches || !fused_out || !workspace || T <= 0) return VZ_ERR_BAD_ARG;
+  if ((norm_g == nullptr) != (norm_b == nullptr)) return VZ_ERR_BAD_ARG;
+  if (!aligned16(workspace) || !aligned16(patches) || !aligned16(fused_out)) return VZ_ERR_BAD_ARG;
+  const VitWs ws = vit_layout(workspace, T);
+  if (ws.total > workspace_bytes) return VZ_ERR_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int M = T * VZ_VIT_TOKENS, MP = T * VZ_VIT_PATCHES, D = VZ_VIT_WIDTH;
+
+  // embeddings: class token rows, then conv-as-GEMM (+ position embedding in the epilogue)
+  VZ_TRY(cls_rows_launch(w->class_emb, w->pos_emb, ws.mid, T, st));
+  VZ_TRY(gemm(patches, VZ_PATCH_K, w->patch_w, VZ_PATCH_K, MP, D, VZ_PATCH_K, nullptr, VZ_ACT_NONE,
+              w->pos_emb, D, ws.mid, D, VZ_ROWS_PATCH_EMBED, VZ_VIT_PATCHES, simple, st));
+  VZ_TRY(layernorm_launch(ws.mid, D, w->pre_ln_g, w->pre_ln_b, ws.hs[0], D, M, D, 1e-5f, nullptr, 1, st));
+
+  for (int l = 0; l < VZ_VIT_LAYERS; ++l) {
+    const vz_vit_layer& L = w->layers[l];
+    const void* x = ws.hs[l];
+    VZ_TRY(layernorm_launch(x, D, L.ln1_g, L.ln1_b, ws.xn, D, M, D, 1e-5f, nullptr, 1, st));
+    VZ_TRY(gemm(ws.xn, D, L.w_qkv, D, M, 3 * D, D, L.b_qkv, VZ_ACT_NONE, nullptr, 0, ws.qkv, 3 * D,
+                VZ_ROWS_PLAIN, 0, simple, st));
+    VZ_TRY(vit_attn_launch(ws.qkv, ws.attn, T, st));
+    VZ_TRY(gemm(ws.attn, D, L.w_o, D, M, D, D, L.b_o, VZ_ACT_NONE, x, D, ws.mid, D, VZ_ROWS_PLAIN, 0,
+                simple, st));
+    VZ_TRY(layernorm_launch(ws.mid, D, L.ln2_g, L.ln2_b, ws.xn, D, M, D, 1e-5f, nullptr, 1, st));
+    VZ_TRY(gemm(ws.xn, D, L.w_fc1, D, M, VZ_VIT_MLP, D, L.b_fc1, VZ_ACT_QUICK_GELU, nullptr, 0, ws.h,
+                VZ_VIT_MLP, VZ_ROWS_PLAIN, 0, simple, st));
+    VZ_TRY(gemm(ws.h, VZ_VIT_MLP, L.w_fc2, VZ_VIT_MLP, M, D, VZ_VIT_MLP, L.b_fc2, VZ_ACT_NONE, ws.mid, D,
+                ws.hs[l + 1], D, VZ_ROWS_PLAIN, 0, simple, st));
+  }
+  // hidden_states[-21:], CLS dropped, 4 x mean-of-5 + last (+ pre_norm)
+  VZ_TRY(fuse_launch(&ws.hs[4], T, norm_g, norm_b, fused_out, st));
+  if (hidden_out) {
+    VZ_CUDA_CHECK(cudaMemcpyAsync(hidden_out, ws.hs[0], (size_t)(VZ_VIT_LAYERS + 1) * M * D * kB16,
+                                  cudaMemcpyDeviceToDevice, st));
+  }
+  return VZ_OK;
+}
+
+extern "C" int vz_qformer_forward(const vz_qf_weights* w, const void* feats, int feats_normed, int T,
+                                  const void* text_emb, const int32_t* text_off, int text_rows, int n_samples,
+                                  int L, const int32_t* tile_sample, void* out, int ldo, void* workspace,
+                                  size_t workspace_bytes, int simple, void* stream) {
+  if (!w || !feats || !out || !workspace || T <= 0 || ldo < VZ_QF_WIDTH || (ldo & 7)) return VZ_ERR_BAD_ARG;
+  const bool has_text = text_emb != nullptr;
+  if (has_text && (!text_off || !tile_sample || n_samples <= 0 || text_rows < 0 || L < 0)) return VZ_ERR_BAD_ARG;
+  if (!aligned16(workspace) || !aligned16(feats) || !aligned16(out)) return VZ_ERR_BAD_ARG;
+  const QfWs ws = qf_layout(workspace, T, has_text ? n_samples : 1, has_text ? text_rows : 0);
+  if (ws.total > workspace_bytes) return VZ_ERR_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int P = T * VZ_VIT_PATCHES, M = T * VZ_QF_QUERIES, D = VZ_QF_WIDTH, D3 = 3 * VZ_QF_WIDTH;
+  const int KVW = VZ_QF_BLOCKS * 2 * VZ_QF_WIDTH;
+  const __nv_bfloat16* qkv0 = reinterpret_cast<const __nv_bfloat16*>(ws.qkv0);
+  const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(ws.qkv);
+  const __nv_bfloat16* KV = reinterpret_cast<const __nv_bfloat16*>(ws.KV);
+
+  // pre_norm (builder.py:74) unless the fusion kernel already applied it
+  const void* fn = feats;
+  if (!feats_normed) {
+    VZ_TRY(layernorm_launch(feats, VZ_FUSED_WIDTH, w->pre_g, w->pre_b, ws.featsN, VZ_FUSED_WIDTH, P,
+                            VZ_FUSED_WIDTH, 1e-5f, nullptr, 1, st));
+    fn = ws.featsN;
+  }
+  // K/V projections of all 8 cross-attention blocks in ONE GEMM (features are block-invariant,
+  // builder.py:84-90): [P,5120] x [65536,5120]^T
+  VZ_TRY(gemm(fn, VZ_FUSED_WIDTH, w->kv_w, VZ_FUSED_WIDTH, P, KVW, VZ_FUSED_WIDTH, w->kv_b, VZ_ACT_NONE,
+              nullptr, 0, ws.KV, KVW, VZ_ROWS_PLAIN, 0, simple, st));
+
+  // ---- block 0 self-attention: queries are tile-invariant, text K/V are per sample --------------
+  const vz_qf_block& B0 = w->blocks[0];
+  VZ_TRY(layernorm_launch(w->learned_queries, D, B0.n1_g, B0.n1_b, ws.q0n, D, VZ_QF_QUERIES, D, 1e-5f,
+                          nullptr, 1, st));
+  VZ_TRY(gemm(ws.q0n, D, B0.sa_in_w, D, VZ_QF_QUERIES, D3, D, B0.sa_in_b, VZ_ACT_NONE, nullptr, 0, ws.qkv0, D3,
+              VZ_ROWS_PLAIN, 0, simple, st));
+  if (has_text) {
+    const int R1 = text_rows + 1;  // + the zero row standing for every padded position
+    VZ_TRY(layernorm_launch(text_emb, D, B0.n1_g, B0.n1_b, ws.tn, D, R1, D, 1e-5f, nullptr, 1, st));
+    const __nv_bfloat16* w_kv = reinterpret_cast<const __nv_bfloat16*>(B0.sa_in_w) + (size_t)D * D;
+    VZ_TRY(gemm(ws.tn, D, w_kv, D, R1, 2 * D, D, B0.sa_in_b + D, VZ_ACT_NONE, nullptr, 0, ws.kv_text, 2 * D,
+                VZ_ROWS_PLAIN, 0, simple, st));
+    const __nv_bfloat16* kvt = reinterpret_cast<const __nv_bfloat16*>(ws.kv_text);
+    VZ_TRY(qattn_launch(0, qkv0, D3, 0, qkv0 + D, qkv0 + 2 * D, D3, 0, VZ_QF_QUERIES, kvt, kvt + D, 2 * D,
+                        text_off, kvt + (size_t)text_rows * 2 * D, kvt + (size_t)text_rows * 2 * D + D, L,
+                        ws.attn0, D, n_samples, st));
+    VZ_TRY(gemm(ws.attn0, D, B0.sa_out_w, D, n_samples * VZ_QF_QUERIES, D, D, B0.sa_out_b, VZ_ACT_NONE,
+                w->learned_queries, D, ws.x1, D, VZ_ROWS_RES_MOD, VZ_QF_QUERIES, simple, st));
+    VZ_TRY(gather_rows_launch(ws.x1, ws.x, M, D * (int)kB16, tile_sample, VZ_QF_QUERIES, st));
+  } else {
+    VZ_TRY(qattn_launch(1, qkv0, D3, 0, qkv0 + D, qkv0 + 2 * D, D3, 0, VZ_QF_QUERIES, nullptr, nullptr, D3,
+                        nullptr, nullptr, nullptr, 0, ws.attn0, D, 1, st));
+    VZ_TRY(gemm(ws.attn0, D, B0.sa_out_w, D, VZ_QF_QUERIES, D, D, B0.sa_out_b, VZ_ACT_NONE, w->learned_queries,
+                D, ws.x1, D, VZ_ROWS_PLAIN, 0, simple, st));
+    VZ_TRY(gather_rows_launch(ws.x1, ws.x, M, D * (int)kB16, nullptr, VZ_QF_QUERIES, st));
+  }
+
+  for (int i = 0; i < VZ_QF_BLOCKS; ++i) {
+    const vz_qf_block& Bk = w->blocks[i];
+    if (i > 0) {
+      VZ_TRY(layernorm_launch(ws.x, D, Bk.n1_g, Bk.n1_b, ws.xn, D, M, D, 1e-5f, nullptr, 1, st));
+      VZ_TRY(gemm(ws.xn, D, Bk.sa_in_w, D, M, D3, D, Bk.sa_in_b, VZ_ACT_NONE, nullptr, 0, ws.qkv, D3,
+                  VZ_ROWS_PLAIN, 0, simple, st));
+      VZ_TRY(qattn_launch(1, qkv, D3, VZ_QF_QUERIES, qkv + D, qkv + 2 * D, D3, VZ_QF_QUERIES, VZ_QF_QUERIES,
+                          nullptr, nullptr, D3, nullptr, nullptr, nullptr, 0, ws.attn, D, T, st));
+      VZ_TRY(gemm(ws.attn, D, Bk.sa_out_w, D, M, D, D, Bk.sa_out_b, VZ_ACT_NONE, ws.x, D, ws.x, D,
+                  VZ_ROWS_PLAIN, 0, simple, st));
+    }
+    // cross-attention over the tile's 576 patch rows
+    VZ_TRY(layernorm_launch(ws.x, D, Bk.n2_g, Bk.n2_b, ws.xn, D, M, D, 1e-5f, nullptr, 1, st));
+    VZ_TRY(gemm(ws.xn, D, Bk.ca_q_w, D, M, D, D, Bk.ca_in_b, VZ_ACT_NONE, nullptr, 0, ws.q, D, VZ_ROWS_PLAIN,
+                0, simple, st));
+    VZ_TRY(qattn_launch(2, ws.q, D, VZ_QF_QUERIES, KV + (size_t)(2 * i) * D, KV + (size_t)(2 * i + 1) * D, KVW,
+                        VZ_VIT_PATCHES, VZ_VIT_PATCHES, nullptr, nullptr, KVW, nullptr, nullptr, nullptr, 0,
+                        ws.attn, D, T, st));
+    VZ_TRY(gemm(ws.attn, D, Bk.ca_out_w, D, M, D, D, Bk.ca_out_b, VZ_ACT_NONE, ws.x, D, ws.x, D, VZ_ROWS_PLAIN,
+                0, simple, st));
+    // FFN, exact (erf) GELU
+    VZ_TRY(layernorm_launch(ws.x, D, Bk.n3_g, Bk.n3_b, ws.xn, D, M, D, 1e-5f, nullptr, 1, st));
+    VZ_TRY(gemm(ws.xn, D, Bk.ffn1_w, D, M, VZ_QF_FFN, D, Bk.ffn1_b, VZ_ACT_GELU_ERF, nullptr, 0, ws.hbuf,
+                VZ_QF_FFN, VZ_ROWS_PLAIN, 0, simple, st));
+    VZ_TRY(gemm(ws.hbuf, VZ_QF_FFN, Bk.ffn2_w, VZ_QF_FFN, M, D, VZ_QF_FFN, Bk.ffn2_b, VZ_ACT_NONE, ws.x, D,
+                ws.x, D, VZ_ROWS_PLAIN, 0, simple, st));
+  }
+  VZ_TRY(layernorm_launch(ws.x, D, w->norm_g, w->norm_b, out, ldo, M, D, 1e-5f, nullptr, 1, st));
+  return VZ_OK;
+}
+
+extern "C" const char* vz_status_string(int status) {
+  switch (status) {
+    case VZ_OK: return "ok";
+    case VZ_ERR_BAD_ARG: return "bad argument (null / size / alignment)";
+    case VZ_ERR_UNSUPPORTED: return "unsupported shape";
+    case VZ_ERR_CUDA: return "CUDA call failed (see vz_last_cuda_error)";
+    case VZ_ERR_NO_DEVICE: return "no sm_100 device";
+    case VZ_ERR_WORKSPACE: return "workspace too small";
+    default: return "unknown status";
+  }
+}
+extern "C" int vz_last_cuda_error(void) { return vz::g_last_cuda_error; }
+extern "C" int vz_version(void) { return 100; }

@@ -1,0 +1,244 @@
+"""GPU image preprocessing: visual-prompt blend + anyres tiling + normalise (+ patchify).
+
+Host-facing mirror of
+  process_any_resolution_image   vis_zephyr/model/multi_scale_process.py:136-183
+  process_images (fixed 336)     vis_zephyr/model/mm_utils.py:38-87
+  image_blending (pixel part)    vis_zephyr/model/vip_processor/conversation_generator.py:13-148
+All pixel arithmetic runs in the CUDA kernel `vz_preprocess`; this module only builds the small
+descriptor tables (tile geometry, LANCZOS coefficients) and moves them to the device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .anyres import TILE, TablePool, anyres_views, single_view
+
+OPENAI_CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+OPENAI_CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def clip_lut(mean=OPENAI_CLIP_MEAN, std=OPENAI_CLIP_STD, style: str = "hf-numpy") -> np.ndarray:
+    """f32 [3,256] table of CLIPImageProcessor's rescale+normalise on every u8 value.
+    'hf-numpy'  : transformers 4.52.4 slow processor (the reference's pin, environment.yaml:108):
+                  f32(f64(u8) * (1/255)) then (x - f32 mean) / f32 std in float32.
+    'hf-fused'  : torchvision fast path of newer transformers: (f32(u8) - 255 m) / (255 s)."""
+    v = np.arange(256, dtype=np.float64)
+    out = np.empty((3, 256), np.float32)
+    for c in range(3):
+        m, s = np.float32(mean[c]), np.float32(std[c])
+        if style == "hf-numpy":
+            x = (v * (1 / 255)).astype(np.float32)
+            out[c] = (x - m) / s
+        elif style == "hf-fused":
+            mm = np.float32(mean[c]) * np.float32(255.0)
+            sd = np.float32(std[c]) * np.float32(255.0)
+            out[c] = (v.astype(np.float32) - mm) / sd
+        else:
+            raise ValueError(style)
+    return out
+
+
+def lut_from_processor(processor) -> np.ndarray:
+    """Run ANY HF-style image processor on a 0..255 ramp and read the 768 values back: the LUT is
+    then bit-identical to that installation's processor."""
+    from PIL import Image
+    size = processor.crop_size["height"]
+    ramp = np.zeros((size, size, 3), np.uint8)
+    ramp[0, :256, :] = np.arange(256, dtype=np.uint8)[:, None]
+    px = processor.preprocess(Image.fromarray(ramp), return_tensors="pt")["pixel_values"][0]
+    return px[:, 0, :256].contiguous().numpy().astype(np.float32)
+
+
+@dataclass
+class VisualPrompt:
+    """One visual-prompt instance applied to an image, in drawing order.
+    kind 'layer': a host-rasterised RGBA overlay [H,W,4] (any PIL ImageDraw shape);
+    kind 'rectangle': ImageDraw.rectangle(outline=rgba, width) rasterised in the kernel
+    (vip_processor/shape_draw.py:68-71)."""
+    kind: str
+    rgba: Tuple[int, int, int, int] = (0, 0, 0, 0)
+    bbox: Optional[Tuple[float, float, float, float]] = None
+    width: int = 1
+    layer: Optional[np.ndarray] = None
+
+
+@dataclass
+class PreprocessPlan:
+    """Device-resident descriptors for one batch (built once per batch on the host)."""
+    n_tiles: int
+    tiles_per_image: List[int]
+    image_sizes: List[Tuple[int, int]]
+    images_dev: torch.Tensor
+    prims_dev: Optional[torch.Tensor]
+    tiles_dev: torch.Tensor
+    tables_dev: torch.Tensor
+    lut_dev: torch.Tensor
+    n_images: int
+    n_prims: int
+    max_src_w: int
+    max_ksize: int
+    keep: list = field(default_factory=list)  # tensors that must outlive the launch
+    h2d_bytes: int = 0
+    algorithmic_bytes: int = 0
+
+
+def _struct_array_to_dev(arr, device) -> torch.Tensor:
+    raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+    return torch.from_numpy(raw).to(device, non_blocking=True)
+
+
+def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut: np.ndarray,
+               prompts: Optional[Sequence[Sequence[VisualPrompt]]] = None) -> PreprocessPlan:
+    """images: u8 CUDA tensors [H,W,3]; views[i]: list of view dicts (see anyres.anyres_views)."""
+    device = images[0].device
+    pool = TablePool()
+    n_img = len(images)
+    img_arr = (_lib.ImageDesc * n_img)()
+    prim_list, tile_list, keep = [], [], []
+    tiles_per_image, sizes = [], []
+    max_w, algo = 1, 0
+    for i, im in enumerate(images):
+        if im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3 or not im.is_cuda:
+            raise ValueError("images must be uint8 CUDA tensors of shape [H, W, 3]")
+        im = im.contiguous()
+        keep.append(im)
+        H, W = int(im.shape[0]), int(im.shape[1])
+        sizes.append((W, H))
+        max_w = max(max_w, W)
+        algo += 3 * W * H
+        layers = []
+        begin = len(prim_list)
+        for p in (prompts[i] if prompts is not None else ()):
+            pr = _lib.Prim()
+            if p.kind == "layer":
+                lay = np.ascontiguousarray(p.layer, dtype=np.uint8)
+                if lay.shape != (H, W, 4):
+                    raise ValueError("overlay layer must be [H, W, 4] uint8")
+                pr.type, pr.layer = _lib.PRIM_LAYER, len(layers)
+                layers.append(lay)
+                algo += 4 * W * H
+            elif p.kind == "rectangle":
+                if int(p.width) == 0:
+                    continue  # ImageDraw.rectangle draws nothing for width == 0
+                x0, y0, x1, y1 = (int(v) for v in p.bbox)  # PIL truncates the float corners
+                if x1 < x0 or y1 < y0:
+                    raise ValueError("x1 must be greater than or equal to x0 (PIL semantics)")
+                pr.type = _lib.PRIM_RECT
+                pr.x0, pr.y0, pr.x1, pr.y1, pr.width = x0, y0, x1, y1, int(p.width)
+                r, g, b, a = p.rgba
+                pr.rgba = (r & 255) | ((g & 255) << 8) | ((b & 255) << 16) | ((a & 255) << 24)
+            else:
+                raise ValueError(f"unsupported visual prompt kind {p.kind!r}")
+            prim_list.append(pr)
+        lay_dev = None
+        if layers:
+            lay_dev = torch.from_numpy(np.stack(layers)).to(device, non_blocking=True)
+            keep.append(lay_dev)
+        d = img_arr[i]
+        d.src = im.data_ptr()
+        d.layers = lay_dev.data_ptr() if lay_dev is not None else None
+        d.W, d.H = W, H
+        d.prim_begin, d.prim_count = begin, len(prim_list) - begin
+        tiles_per_image.append(len(views[i]))
+        for v in views[i]:
+            t = _lib.TileDesc()
+            t.image = i
+            t.out_w, t.out_h = v["out_w"], v["out_h"]
+            t.off_x, t.off_y = v["off_x"], v["off_y"]
+            t.tile_x, t.tile_y = v["tile_x"], v["tile_y"]
+            t.tab_h = pool.offset(W, v["out_w"])
+            t.tab_v = pool.offset(H, v["out_h"])
+            tile_list.append(t)
+    n_tiles = len(tile_list)
+    tile_arr = (_lib.TileDesc * n_tiles)(*tile_list)
+    prim_arr = (_lib.Prim * max(1, len(prim_list)))(*prim_list)
+    tables = pool.pack()
+    plan = PreprocessPlan(
+        n_tiles=n_tiles, tiles_per_image=tiles_per_image, image_sizes=sizes,
+        images_dev=_struct_array_to_dev(img_arr, device),
+        prims_dev=_struct_array_to_dev(prim_arr, device) if prim_list else None,
+        tiles_dev=_struct_array_to_dev(tile_arr, device),
+        tables_dev=torch.from_numpy(tables).to(device, non_blocking=True),
+        lut_dev=torch.from_numpy(np.ascontiguousarray(lut, np.float32)).to(device, non_blocking=True),
+        n_images=n_img, n_prims=len(prim_list), max_src_w=max_w, max_ksize=pool.max_ksize, keep=keep)
+    plan.h2d_bytes = (plan.images_dev.numel() + plan.tiles_dev.numel() + plan.tables_dev.numel() * 4 +
+                      (plan.prims_dev.numel() if plan.prims_dev is not None else 0) + 768 * 4)
+    plan.algorithmic_bytes = algo
+    return plan
+
+
+def run_plan(plan: PreprocessPlan, out_mode: str = "patches", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Launch vz_preprocess.  out_mode 'patches' -> bf16 [T*576, 592]; 'chw' -> f32 [T,3,336,336]."""
+    lib = _lib.load()
+    dev = plan.tiles_dev.device
+    T = plan.n_tiles
+    if out_mode == "patches":
+        if out is None:
+            out = torch.empty((T * 576, 592), dtype=torch.bfloat16, device=dev)
+        mode = _lib.OUT_PATCHES_BF16
+    elif out_mode == "chw":
+        if out is None:
+            out = torch.empty((T, 3, TILE, TILE), dtype=torch.float32, device=dev)
+        mode = _lib.OUT_CHW_F32
+    else:
+        raise ValueError(out_mode)
+    st = lib.vz_preprocess(_lib.ptr(plan.images_dev), plan.n_images, _lib.ptr(plan.prims_dev), plan.n_prims,
+                           _lib.ptr(plan.tiles_dev), T, _lib.ptr(plan.tables_dev), _lib.ptr(plan.lut_dev),
+                           mode, _lib.ptr(out), plan.max_src_w, plan.max_ksize, _lib.stream_ptr())
+    _lib.check(st, "vz_preprocess")
+    return out
+
+
+class PatchBatch:
+    """bf16 im2col patch rows [T*576, 592] produced by the fused preprocess kernel; accepted by
+    CLIPVisionTowerB200.forward in place of reference-style pixel tensors."""
+
+    def __init__(self, patches: torch.Tensor, tiles_per_image: List[int], image_sizes: List[Tuple[int, int]]):
+        self.patches = patches
+        self.tiles_per_image = list(tiles_per_image)
+        self.image_sizes = list(image_sizes)
+
+    @property
+    def n_tiles(self) -> int:
+        return self.patches.shape[0] // 576
+
+    @property
+    def device(self):
+        return self.patches.device
+
+    @property
+    def dtype(self):
+        return self.patches.dtype
+
+
+def process_any_resolution_images(images: Sequence[torch.Tensor], grid_pinpoints, lut: np.ndarray,
+                                  prompts=None, out_mode: str = "patches"):
+    """Batch version of process_any_resolution_image (multi_scale_process.py:136-183) on u8 CUDA
+    images [H,W,3].  Returns PatchBatch (out_mode='patches') or a list of f32 [T_i,3,336,336]
+    tensors in the reference layout (out_mode='chw')."""
+    views = []
+    for im in images:
+        v, _ = anyres_views((int(im.shape[1]), int(im.shape[0])), grid_pinpoints)
+        views.append(v)
+    plan = build_plan(images, views, lut, prompts)
+    out = run_plan(plan, out_mode)
+    if out_mode == "patches":
+        return PatchBatch(out, plan.tiles_per_image, plan.image_sizes)
+    return list(torch.split(out, plan.tiles_per_image, dim=0))
+
+
+def process_fixed_images(images: Sequence[torch.Tensor], lut: np.ndarray, prompts=None,
+                         out_mode: str = "patches", mode: str = "identity"):
+    """Fixed-336 path (config 2): blend visual prompts onto 336x336 images, normalise, patchify."""
+    views = [single_view((int(im.shape[1]), int(im.shape[0])), mode) for im in images]
+    plan = build_plan(images, views, lut, prompts)
+    out = run_plan(plan, out_mode)
+    if out_mode == "patches":
+        return PatchBatch(out, plan.tiles_per_image, plan.image_sizes)
+    return list(torch.split(out, plan.tiles_per_image, dim=0))

@@ -1,0 +1,241 @@
+"""CLIP ViT-L/14-336 vision tower with multi-layer feature fusion, running on the B200 kernels.
+
+Drop-in for the reference's
+  build_vision_tower            vis_zephyr/model/vision_encoder/builder.py:8-24
+  CLIPVisionTower               vis_zephyr/model/vision_encoder/vision_encoder.py:13-151
+  DenseChannelIntegrationFusion vis_zephyr/model/gating_fusion/gating_fusion.py:22-50
+Same constructor arguments, same attributes/properties, same forward() input forms (list, 4-D,
+3-D tensors) plus PatchBatch from the fused preprocess kernel.  The arithmetic is
+`vz_vit_forward` (csrc/vz_model.cu); there is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from types import SimpleNamespace
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .preprocess import PatchBatch
+
+WIDTH, LAYERS, TOKENS, PATCHES, MLP, PATCH_K = 1024, 24, 577, 576, 4096, 592
+
+
+def default_clip_config():
+    """CLIP ViT-L/14-336 geometry (what CLIPVisionConfig.from_pretrained would return)."""
+    return SimpleNamespace(hidden_size=WIDTH, intermediate_size=MLP, num_hidden_layers=LAYERS,
+                           num_attention_heads=16, image_size=336, patch_size=14, projection_dim=768,
+                           hidden_act="quick_gelu", layer_norm_eps=1e-5)
+
+
+class Workspace:
+    """Grow-only device scratch shared by the tower and the projector of one process/stream."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != torch.device(device):
+            self.buf = None
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+class CLIPVisionTowerB200(nn.Module):
+    def __init__(self, vision_tower_path, args, delay_load: bool = False):
+        super().__init__()
+        self.is_loaded = False
+        self.vision_tower_path = ("openai/clip-vit-large-patch14-336" if vision_tower_path is None
+                                  else vision_tower_path)
+        self.select_feature = getattr(args, "mm_vision_select_feature", "patch")
+        raw = getattr(args, "mm_vision_select_layer", None)
+        if isinstance(raw, str):
+            try:
+                self.select_layers = [int(x.strip()) for x in raw.split(",")]
+            except ValueError:
+                raise ValueError("Invalid format for mm_vision_select_layer. Expected a comma-separated "
+                                 f"string of integers, but got: {raw}")
+        else:
+            self.select_layers = [-2]  # parsed but unused by feature_select, like the reference (quirk Q5)
+        self.cfg_only = default_clip_config()
+        self.image_processor = None
+        self.force_simple_gemm = False
+        self._w: Optional[_lib.VitWeights] = None
+        self._packed: Dict[str, torch.Tensor] = {}
+        self._ws = Workspace()
+        self._dtype = torch.bfloat16
+        # a zero-size parameter-free anchor so .to(device) / .device work before loading
+        self.register_buffer("_anchor", torch.zeros(1), persistent=False)
+        if not delay_load:
+            self.load_model()
+
+    # -- loading ---------------------------------------------------------------------------
+    def load_model(self, state_dict: Optional[Dict[str, torch.Tensor]] = None, device=None):
+        """Load CLIP weights.  `state_dict` uses HF CLIPVisionModel names ('vision_model.*');
+        if omitted they are read from `vision_tower_path` with transformers."""
+        from transformers import CLIPImageProcessor
+        if state_dict is None:
+            from transformers import CLIPVisionModel
+            hf = CLIPVisionModel.from_pretrained(self.vision_tower_path)
+            state_dict = hf.state_dict()
+            self.cfg_only = hf.config
+        try:
+            self.image_processor = CLIPImageProcessor.from_pretrained(self.vision_tower_path)
+        except Exception:
+            from .preprocess import OPENAI_CLIP_MEAN, OPENAI_CLIP_STD
+            self.image_processor = CLIPImageProcessor(
+                size={"shortest_edge": 336}, crop_size={"height": 336, "width": 336},
+                image_mean=list(OPENAI_CLIP_MEAN), image_std=list(OPENAI_CLIP_STD), resample=3)
+        dev = torch.device(device) if device is not None else self._anchor.device
+        self._pack(state_dict, dev)
+        self.is_loaded = True
+        return self
+
+    def _pack(self, sd: Dict[str, torch.Tensor], dev):
+        """HF layout -> kernel layout: bf16 weights ([N,K] row-major, q/k/v stacked, conv weight
+        flattened (c,ky,kx) and K-padded 588->592), fp32 biases and LayerNorm parameters."""
+        sd = {k[len("vision_tower."):] if k.startswith("vision_tower.") else k: v for k, v in sd.items()}
+        p = "vision_model."
+        bf = lambda t: t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        P: Dict[str, torch.Tensor] = {}
+        conv = sd[p + "embeddings.patch_embedding.weight"].detach().reshape(WIDTH, 588)
+        pw = torch.zeros((WIDTH, PATCH_K), dtype=torch.bfloat16, device=dev)
+        pw[:, :588] = conv.to(device=dev, dtype=torch.bfloat16)
+        P["patch_w"] = pw
+        P["class_emb"] = bf(sd[p + "embeddings.class_embedding"])
+        P["pos_emb"] = bf(sd[p + "embeddings.position_embedding.weight"])
+        P["pre_ln_g"] = f32(sd[p + "pre_layrnorm.weight"])
+        P["pre_ln_b"] = f32(sd[p + "pre_layrnorm.bias"])
+        for l in range(LAYERS):
+            q = f"{p}encoder.layers.{l}."
+            P[f"{l}.w_qkv"] = bf(torch.cat([sd[q + "self_attn.q_proj.weight"], sd[q + "self_attn.k_proj.weight"],
+                                            sd[q + "self_attn.v_proj.weight"]], 0))
+            P[f"{l}.b_qkv"] = f32(torch.cat([sd[q + "self_attn.q_proj.bias"], sd[q + "self_attn.k_proj.bias"],
+                                             sd[q + "self_attn.v_proj.bias"]], 0))
+            P[f"{l}.w_o"], P[f"{l}.b_o"] = bf(sd[q + "self_attn.out_proj.weight"]), f32(sd[q + "self_attn.out_proj.bias"])
+            P[f"{l}.ln1_g"], P[f"{l}.ln1_b"] = f32(sd[q + "layer_norm1.weight"]), f32(sd[q + "layer_norm1.bias"])
+            P[f"{l}.ln2_g"], P[f"{l}.ln2_b"] = f32(sd[q + "layer_norm2.weight"]), f32(sd[q + "layer_norm2.bias"])
+            P[f"{l}.w_fc1"], P[f"{l}.b_fc1"] = bf(sd[q + "mlp.fc1.weight"]), f32(sd[q + "mlp.fc1.bias"])
+            P[f"{l}.w_fc2"], P[f"{l}.b_fc2"] = bf(sd[q + "mlp.fc2.weight"]), f32(sd[q + "mlp.fc2.bias"])
+        self._packed = P
+        self._rebuild_pointers()
+
+    def _apply(self, fn, *a, **k):
+        """nn.Module.to()/cuda(): follow the device move (dtypes of the packed buffers are fixed:
+        bf16 weights, f32 biases / LayerNorm parameters) and refresh the pointer table."""
+        out = super()._apply(fn, *a, **k)
+        dev = self._anchor.device
+        if self._packed and self._packed["patch_w"].device != dev:
+            self._packed = {key: t.to(dev) for key, t in self._packed.items()}
+            self._rebuild_pointers()
+        return out
+
+    def _rebuild_pointers(self):
+        P, w = self._packed, _lib.VitWeights()
+        w.patch_w, w.class_emb, w.pos_emb = P["patch_w"].data_ptr(), P["class_emb"].data_ptr(), P["pos_emb"].data_ptr()
+        w.pre_ln_g, w.pre_ln_b = P["pre_ln_g"].data_ptr(), P["pre_ln_b"].data_ptr()
+        for l in range(LAYERS):
+            for name in ("ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_g", "ln2_b", "w_fc1", "b_fc1",
+                         "w_fc2", "b_fc2"):
+                setattr(w.layers[l], name, P[f"{l}.{name}"].data_ptr())
+        self._w = w
+
+    # -- compute ----------------------------------------------------------------------------
+    def _patches_of(self, images) -> torch.Tensor:
+        """pixel tensor [T,3,336,336] (f32/bf16) -> bf16 patch rows via vz_patchify."""
+        lib = _lib.load()
+        if images.shape[-3:] != (3, 336, 336):
+            raise ValueError(f"Input image size ({images.shape[-2]}*{images.shape[-1]}) doesn't match model (336*336).")
+        x = images.to(self.device)
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.to(torch.float32)
+        x = x.contiguous()
+        T = x.shape[0]
+        patches = torch.empty((T * PATCHES, PATCH_K), dtype=torch.bfloat16, device=x.device)
+        _lib.check(lib.vz_patchify(_lib.ptr(x), 1 if x.dtype == torch.float32 else 0, T, _lib.ptr(patches),
+                                   _lib.stream_ptr()), "vz_patchify")
+        return patches
+
+    def encode_patches(self, patches: torch.Tensor, pre_norm=None, return_hidden: bool = False):
+        """patches bf16 [T*576,592] -> fused features bf16 [T,576,5120] (QFormer.pre_norm applied in
+        the fusion kernel when pre_norm=(gamma_f32, beta_f32))."""
+        if not self.is_loaded:
+            raise RuntimeError("vision tower weights are not loaded (call load_model())")
+        if self.select_feature != "patch":
+            if self.select_feature == "cls_patch":
+                raise NotImplementedError("select_feature='cls_patch' is not on the B200 path")
+            raise ValueError(f"Unknown feature selection strategy: {self.select_feature}")
+        lib = _lib.load()
+        T = patches.shape[0] // PATCHES
+        dev = patches.device
+        fused = torch.empty((T, PATCHES, 5 * WIDTH), dtype=torch.bfloat16, device=dev)
+        nbytes = lib.vz_vit_workspace_bytes(T)
+        ws = self._ws.get(nbytes, dev)
+        hidden = torch.empty((LAYERS + 1, T, TOKENS, WIDTH), dtype=torch.bfloat16, device=dev) if return_hidden else None
+        g = b = None
+        if pre_norm is not None:
+            g, b = pre_norm
+        _lib.check(lib.vz_vit_forward(C.byref(self._w), _lib.ptr(patches), T, _lib.ptr(fused), _lib.ptr(g),
+                                      _lib.ptr(b), _lib.ptr(hidden), _lib.ptr(ws), ws.numel(),
+                                      1 if self.force_simple_gemm else 0, _lib.stream_ptr()), "vz_vit_forward")
+        return (fused, hidden) if return_hidden else fused
+
+    @torch.no_grad()
+    def forward(self, images):
+        """vision_encoder.py:80-117: list -> list of features; 4-D / 3-D tensor -> features cast back
+        to the input dtype (quirk Q7)."""
+        if isinstance(images, PatchBatch):
+            return self.encode_patches(images.patches)
+        if isinstance(images, list):
+            feats = []
+            for image in images:
+                x = image if image.ndim == 4 else image.unsqueeze(0)
+                feats.append(self.encode_patches(self._patches_of(x)).to(image.dtype))
+            return feats
+        if images.ndim == 3:
+            images = images.unsqueeze(0)
+        return self.encode_patches(self._patches_of(images)).to(images.dtype)
+
+    # -- reference properties -------------------------------------------------------------------
+    @property
+    def dummy_feature(self):
+        return torch.zeros(1, self.hidden_size, device=self.device, dtype=self.dtype)
+
+    @property
+    def dtype(self):
+        return self._dtype
+
+    @property
+    def device(self):
+        if self._packed:
+            return self._packed["patch_w"].device
+        return self._anchor.device
+
+    @property
+    def config(self):
+        return self.cfg_only
+
+    @property
+    def hidden_size(self):
+        return self.config.hidden_size * 5
+
+    @property
+    def num_patches(self):
+        return (self.config.image_size // self.config.patch_size) ** 2
+
+    @property
+    def num_patches_per_side(self):
+        return self.config.image_size // self.config.patch_size
+
+
+def build_vision_tower(vision_tower_cfg, **kwargs):
+    """vision_encoder/builder.py:8-24 (same acceptance rule and error)."""
+    path = getattr(vision_tower_cfg, "mm_vision_tower", getattr(vision_tower_cfg, "vision_tower", None))
+    exists = os.path.exists(path) if path is not None else False
+    if path is not None and (exists or path.startswith("openai") or path.startswith("laion")):
+        return CLIPVisionTowerB200(vision_tower_path=path, args=vision_tower_cfg, **kwargs)
+    raise ValueError(f"Unknown vision tower path: {path}")
