@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- anyres images/s through the image -> LLM-embedding path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+Workload (config.workload = "c3_anyres_b8"): per GPU, 8 synthetic RGB images (sizes that all select
+the 672x672 pinpoint -> 1 global + 2x2 tiles = 5 tiles each, 40 tiles), 64-token prompts with one
+<image> placeholder, random-init CLIP ViT-L/14-336 + Q-Former + 32000x4096 embedding table, 'flat'
+merge.  N GPUs = N such shards (weak scaling, BASELINE config 4 at N=8): every rank encodes its 8
+images, ONE all-gather moves the projected visual tokens, rank 0 splices the global batch.
+
+A step = preprocess kernel -> ViT -> fusion -> Q-Former -> (all-gather) -> plan/gather/scatter.
+`value`   : device-resident inputs (u8 images + ids already in HBM), CUDA-event timed, max over ranks.
+`e2e`     : same metric through the public API with HOST buffers: pinned u8 images + ids copied H2D,
+            descriptor tables rebuilt, outputs copied D2H, all inside the timed region.
+`roofline`: the tcgen05 GEMM kernel (dominant), FLOPs = 2MNK per launch, CUDA events on its stream.
+`cpu_baseline`: the fp32 oracle port of the reference algorithm on the host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PINPOINTS = [[336, 672], [672, 336], [672, 672], [336, 1008], [1008, 336]]
+IMAGE_SIZES = [(1000, 900), (900, 1000), (1344, 1344), (700, 650), (1000, 900), (800, 760), (1200, 1100), (672, 672)]
+IMAGES_PER_GPU, TILES_PER_IMAGE, SEQ = 8, 5, 64
+GFLOP_PER_TILE = 856.9  # ViT 381.918 + projector 474.997 (L-independent part)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(rank, n_local=IMAGES_PER_GPU):
+    imgs = []
+    for i in range(n_local):
+        W, H = IMAGE_SIZES[i % len(IMAGE_SIZES)]
+        imgs.append(np.random.default_rng(1000 + rank * 64 + i).integers(0, 256, (H, W, 3), dtype=np.uint8))
+    return imgs
+
+
+def make_ids(n_samples):
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(3, 32000, (n_samples, SEQ), generator=g)
+    ids[:, 10] = -200
+    return ids
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference_arm(args):
+    """The reference's algorithm on the box's host cores: the pinned fp32 oracle port (the reference
+    is pure Python/PyTorch and cannot travel to the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import model as M, pil_ops as P, splice as S, weights
+    torch.set_num_threads(os.cpu_count())
+    cores = torch.get_num_threads()
+    w_clip, w_qf, embed = weights.clip_state_dict(0), weights.qformer_state_dict(1), weights.embed_table(2)
+    import vision_zephyr_b200 as vz
+    lut = vz.clip_lut()
+    ids = make_ids(1)
+
+    def one_image(img):
+        px = torch.from_numpy(P.process_any_resolution(img, PINPOINTS, lut))
+        with torch.no_grad():
+            text = M.text_embeddings_for(ids, [px.shape[0]], embed)
+            vis = M.encode_images(w_clip, w_qf, px, text)
+        feats = S.process_image_patches([vis.numpy()], [(img.shape[1], img.shape[0])], "flat", [(2, 2)])
+        return S.splice(ids.numpy(), None, None, False, embed.numpy(), feats)[0]
+
+    imgs = make_inputs(0)
+    t0 = time.perf_counter()
+    one_image(imgs[0])
+    t_first = time.perf_counter() - t0
+    steps, warm = args.steps, max(args.warmup - 1, 0)
+    # bound the run to a few minutes: shrink the number of timed steps if one image is slow
+    budget = 240.0
+    if t_first * (steps + warm) > budget:
+        steps = max(1, int(budget / t_first) - warm)
+    for i in range(warm):
+        one_image(imgs[(i + 1) % len(imgs)])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one_image(imgs[i % len(imgs)])
+    dt = time.perf_counter() - t0
+    value = steps / dt
+    line = {"impl": "reference", "metric": "anyres images/sec (ViT-L/14-336 + Q-Former)", "value": value,
+            "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": 1000 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "c3_anyres_b8", "sample": "1 image (5 tiles) per step", "seq_len": SEQ},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": f"{steps} timed steps x 1 anyres image (5 tiles, 63 text tokens), fp32 torch oracle"},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    import vision_zephyr_b200 as vz
+    from vision_zephyr_b200 import _lib
+    from vision_zephyr_b200.dist import shard_images
+    from vision_zephyr_b200.runtime import VisionEmbeddingPath, random_init_
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    path = random_init_(VisionEmbeddingPath(device=dev), seed=0)
+    lut = vz.clip_lut()
+    n_global = IMAGES_PER_GPU * world
+    tiles_global = [TILES_PER_IMAGE] * n_global
+    sizes_global = [IMAGE_SIZES[i % len(IMAGE_SIZES)] for r in range(world) for i in range(IMAGES_PER_GPU)]
+    lo, hi = shard_images(tiles_global, world)[rank]
+    assert (lo, hi) == (rank * IMAGES_PER_GPU, (rank + 1) * IMAGES_PER_GPU)
+    host_imgs = [torch.from_numpy(x).pin_memory() for x in make_inputs(rank)]
+    ids_host = make_ids(n_global).pin_memory()
+    dev_imgs = [x.to(dev) for x in host_imgs]
+    ids_dev = ids_host.to(dev)
+    from vision_zephyr_b200.anyres import anyres_views
+    from vision_zephyr_b200.preprocess import PatchBatch, build_plan, run_plan
+    views = [anyres_views((int(im.shape[1]), int(im.shape[0])), PINPOINTS)[0] for im in dev_imgs]
+    pre_plan = build_plan(dev_imgs, views, lut)
+    assert pre_plan.tiles_per_image == [TILES_PER_IMAGE] * IMAGES_PER_GPU, pre_plan.tiles_per_image
+
+    def step_device():
+        """inputs resident in HBM; preprocess descriptors (pure geometry) prebuilt"""
+        patches = run_plan(pre_plan, "patches")
+        pb = PatchBatch(patches, pre_plan.tiles_per_image, pre_plan.image_sizes)
+        if world > 1:
+            return path.prepare_inputs_labels_for_multimodal_sharded(ids_dev, None, None, None, None, pb, tiles_global,
+                                                                     sizes_global)
+        return path.prepare_inputs_labels_for_multimodal(ids_dev, None, None, None, None, pb, sizes_global)
+
+    out_host = {}
+
+    def step_e2e():
+        """public API from HOST buffers: H2D of images + ids, descriptor build, kernels, D2H of the result"""
+        imgs = [x.to(dev, non_blocking=True) for x in host_imgs]
+        ids = ids_host.to(dev, non_blocking=True)
+        pb = vz.process_any_resolution_images(imgs, PINPOINTS, lut, out_mode="patches")
+        if world > 1:
+            r = path.prepare_inputs_labels_for_multimodal_sharded(ids, None, None, None, None, pb, tiles_global, sizes_global)
+        else:
+            r = path.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, pb, sizes_global)
+        if r[4] is not None:
+            if "emb" not in out_host:
+                out_host["emb"] = torch.empty(r[4].shape, dtype=r[4].dtype).pin_memory()
+            out_host["emb"].copy_(r[4], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return r
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- warm-up ------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        out = step_device()
+    barrier()
+    if rank == 0:
+        assert out[4].shape == (n_global, SEQ - 1 + TILES_PER_IMAGE * 32, 4096), out[4].shape
+        assert torch.isfinite(out[4].float()).all()
+
+    # ---- timed region: device-resident inputs -------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.vz_gemm_profile(1)
+    l0 = lib.vz_kernel_launches()
+    ms_total = timed(step_device, args.steps)
+    launches = int(lib.vz_kernel_launches() - l0)
+    import ctypes as C
+    n_g, g_ms, g_fl = C.c_longlong(0), C.c_double(0), C.c_double(0)
+    _lib.check(lib.vz_gemm_profile_read(C.byref(n_g), C.byref(g_ms), C.byref(g_fl)), "gemm profile")
+    lib.vz_gemm_profile(0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host buffers --------------------------------------------------------------------
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_kind = peaks()
+    ms_step = ms_total / args.steps
+    value = n_global / (ms_step / 1000.0)
+    e2e_value = n_global / (ms_e2e / args.steps / 1000.0)
+    h2d = sum(x.numel() for x in host_imgs) + ids_host.numel() * 8 + pre_plan.h2d_bytes
+    d2h = out_host["emb"].numel() * 2 + (2 * n_global + 4) * 4
+    gemm_tflops = (g_fl.value / 1e12) / (g_ms.value / 1e3) if g_ms.value > 0 else 0.0
+    peak_tf = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    line = {
+        "metric": "anyres images/sec (ViT-L/14-336 + Q-Former)", "value": value, "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "c3_anyres_b8", "images_per_gpu": IMAGES_PER_GPU, "tiles_per_image": TILES_PER_IMAGE,
+                   "global_images": n_global, "seq_len": SEQ, "merge": "flat", "parallelism": f"dp{world}",
+                   "l2_policy": "per-step working set (3.0 GB K/V + 1.2 GB hidden states + 4.0 GB weights) exceeds the 126 MB L2",
+                   "tiles_per_s": value * TILES_PER_IMAGE,
+                   "path_tflops_algorithmic": value * TILES_PER_IMAGE * GFLOP_PER_TILE / 1000.0 / world},
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "gemm_bf16_tcgen05_kernel", "bound": "tensor", "achieved": gemm_tflops, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf if peak_tf else None, "traffic": None,
+                     "peak_source": f"{pk_kind} bf16_tflops_sustained", "launches": int(n_g.value),
+                     "gemm_ms_per_step": g_ms.value / args.steps,
+                     "gemm_share_of_step": (g_ms.value / args.steps) / ms_step if ms_step else None},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_sample():
+    """oracle port on the host cores, rank 0 at N=1: ONE anyres image (5 tiles, 63 text tokens)."""
+    from oracle import model as M, pil_ops as P, splice as S, weights
+    import vision_zephyr_b200 as vz
+    torch.set_num_threads(os.cpu_count())
+    w_clip, w_qf, embed = weights.clip_state_dict(0), weights.qformer_state_dict(1), weights.embed_table(2)
+    lut = vz.clip_lut()
+    ids = make_ids(1)
+    img = make_inputs(0, 1)[0]
+    t0 = time.perf_counter()
+    px = torch.from_numpy(P.process_any_resolution(img, PINPOINTS, lut))
+    with torch.no_grad():
+        text = M.text_embeddings_for(ids, [px.shape[0]], embed)
+        vis = M.encode_images(w_clip, w_qf, px, text)
+    feats = S.process_image_patches([vis.numpy()], [(img.shape[1], img.shape[0])], "flat", [(2, 2)])
+    S.splice(ids.numpy(), None, None, False, embed.numpy(), feats)
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "1 anyres image (1000x900 -> 5 tiles, 63 text tokens), fp32 torch oracle, cold run"}
+
+
+if __name__ == "__main__":
+    main()

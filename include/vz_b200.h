@@ -74,6 +74,14 @@ typedef struct {
 
 int vz_gemm_bf16(const vz_gemm_args* args, void* stream);
 
+/* Measurement hooks (bench.py / tests; no effect on results).
+ * vz_kernel_launches: number of CUDA kernels this library has launched in the process.
+ * vz_gemm_profile(1): record CUDA events around every tcgen05 GEMM launch (on its own stream);
+ * vz_gemm_profile_read: synchronise them and return launches, summed ms and summed 2*M*N*K.     */
+long long vz_kernel_launches(void);
+int vz_gemm_profile(int enable);
+int vz_gemm_profile_read(long long* launches, double* total_ms, double* total_flops);
+
 /* ------------------------------------------------------------------------------------------ */
 /* Row kernels                                                                                 */
 /* ------------------------------------------------------------------------------------------ */

@@ -1,0 +1,93 @@
+"""End-to-end parity through the reference-shaped public API (prepare_inputs_labels_for_multimodal)
+against tensors produced by the reference itself (golden_model.npz) and the fp32 oracle.
+Tolerance (north_star): bf16 CUDA path vs fp32: cosine >= 0.999 per visual-token row, max-abs <= 0.1
+on the LayerNorm-ed (unit-scale) outputs; integer outputs bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import PINPOINTS_C3, cos_rows, synth_image
+
+pytestmark = pytest.mark.gpu
+COS_MIN, MAX_ABS = 0.999, 0.1
+
+
+def _lut(golden_dir):
+    return np.load(f"{golden_dir}/golden_pixels.npz")["lut"]
+
+
+def test_config1_single_image_matches_reference(vision_path, golden_dir):
+    import vision_zephyr_b200 as vz
+    g = np.load(f"{golden_dir}/golden_model.npz")
+    lut = _lut(golden_dir)
+    img = synth_image(0, 336, 336)
+    px = vz.process_fixed_images([torch.from_numpy(img).cuda()], lut, out_mode="chw")   # list of [1,3,336,336] f32
+    ids = torch.from_numpy(g["c1_ids"]).cuda()
+    r = vision_path.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, px, [(336, 336)])
+    torch.cuda.synchronize()
+    assert r[0] is None and r[1] is None and r[2] is None and r[5] is None
+    emb = r[4].float().cpu().numpy()
+    assert list(emb.shape) == g["c1_embeds_shape"].tolist() == [1, 95, 4096]
+    vis = emb[0, 10:42]
+    ref = g["c1_vis"].astype(np.float32)
+    cos = cos_rows(vis, ref)
+    err = np.abs(vis - ref).max()
+    print(f"config1 visual tokens: min cos {cos.min():.6f} max_abs {err:.4g}")
+    assert cos.min() >= COS_MIN and err <= MAX_ABS
+    # text rows are exact copies of the (bf16) embedding table
+    table = vision_path.model.embed_tokens.weight
+    assert torch.equal(r[4][0, :10], table[ids[0, :10]]) and torch.equal(r[4][0, 42:], table[ids[0, 11:]])
+
+
+def test_anyres_two_samples_matches_reference(vision_path, golden_dir):
+    """5-tile + 3-tile images, ragged text (zero-padded conditioning rows with multiplicity), mask and labels."""
+    import vision_zephyr_b200 as vz
+    g = np.load(f"{golden_dir}/golden_model.npz")
+    lut = _lut(golden_dir)
+    imgs = [torch.from_numpy(synth_image(0, 1000, 900)).cuda(), torch.from_numpy(synth_image(1, 637, 336)).cuda()]
+    pb = vz.process_any_resolution_images(imgs, PINPOINTS_C3, lut, out_mode="patches")
+    assert pb.tiles_per_image == g["c3_tiles"].tolist()
+    ids, mask, labels = (torch.from_numpy(g[k]).cuda() for k in ("c3_ids", "c3_mask", "c3_labels"))
+    r = vision_path.prepare_inputs_labels_for_multimodal(ids, None, mask, None, labels, pb, [(1000, 900), (637, 336)])
+    torch.cuda.synchronize()
+    emb = r[4].float().cpu().numpy()
+    assert list(emb.shape) == g["c3_embeds_shape"].tolist()
+    assert np.array_equal(r[5].cpu().numpy(), g["c3_out_labels"])
+    assert r[2].dtype == torch.int64 and np.array_equal(r[2].cpu().numpy(), g["c3_out_mask"])
+    ref_vis = g["c3_vis"].astype(np.float32)            # [8,32,4096]
+    got0 = emb[0, 5:5 + 160].reshape(5, 32, 4096)
+    got1 = emb[1, 20:20 + 96].reshape(3, 32, 4096)
+    got = np.concatenate([got0, got1])
+    cos = cos_rows(got, ref_vis)
+    err = np.abs(got - ref_vis).max()
+    print(f"anyres visual tokens: min cos {cos.min():.6f} max_abs {err:.4g}")
+    assert cos.min() >= COS_MIN and err <= MAX_ABS
+    probe = r[4][:, :, ::512].float().cpu().numpy()
+    assert np.abs(probe - g["c3_embeds_probe"]).max() <= MAX_ABS
+
+
+def test_tensor_and_patchbatch_inputs_agree(vision_path, golden_dir):
+    """reference-style pixel tensors (list / 5-D) and the fused PatchBatch give identical bits."""
+    import vision_zephyr_b200 as vz
+    lut = _lut(golden_dir)
+    img = torch.from_numpy(synth_image(5, 700, 650)).cuda()
+    ids = torch.randint(3, 32000, (1, 40), generator=torch.Generator().manual_seed(1)).cuda()
+    ids[0, 7] = -200
+    pb = vz.process_any_resolution_images([img], PINPOINTS_C3, lut, out_mode="patches")
+    chw = vz.process_any_resolution_images([img], PINPOINTS_C3, lut, out_mode="chw")
+    a = vision_path.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, pb, [(700, 650)])[4]
+    b = vision_path.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, chw, [(700, 650)])[4]
+    c = vision_path.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, chw[0][None], None)[4]
+    assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_early_outs_and_errors(vision_path):
+    ids = torch.zeros((2, 1), dtype=torch.long, device="cuda")
+    out = vision_path.prepare_inputs_labels_for_multimodal(ids, None, None, "pkv", None, [torch.zeros(1)], None)
+    assert out[0] is ids and out[3] == "pkv" and out[4] is None      # decode step: untouched
+    ids = torch.zeros((2, 8), dtype=torch.long, device="cuda")
+    out = vision_path.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, None, None)
+    assert out[0] is ids and out[4] is None
+    with pytest.raises(RuntimeError):                                 # quirk Q1: 4-D tensor input
+        vision_path.prepare_inputs_labels_for_multimodal(ids, None, None, None, None,
+                                                         torch.zeros((2, 3, 336, 336), device="cuda"), None)

@@ -1,0 +1,150 @@
+"""GPU parity of the individual kernels through the C ABI (ctypes), against plain torch fp32 math
+on the same bf16 inputs (floating-point kernels) -- run with `-m gpu` on a B200."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    import vision_zephyr_b200  # noqa: F401
+    from vision_zephyr_b200 import _lib
+    return _lib, _lib.load()
+
+
+def run_gemm(A, W, bias=None, act=0, residual=None, row_mode=0, rows_per=0, out=None, out_rows=None, simple=0):
+    L, lib = _lib()
+    M, K = A.shape
+    N = W.shape[0]
+    if out is None:
+        out = torch.zeros((out_rows or M, N), dtype=torch.bfloat16, device=A.device)
+    g = L.GemmArgs()
+    g.A, g.W, g.out = A.data_ptr(), W.data_ptr(), out.data_ptr()
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.residual = residual.data_ptr() if residual is not None else None
+    g.M, g.N, g.K = M, N, K
+    g.lda, g.ldw, g.ldo = A.stride(0), W.stride(0), out.stride(0)
+    g.ldr = residual.stride(0) if residual is not None else 0
+    g.act, g.row_mode, g.rows_per, g.force_simple = act, row_mode, rows_per, simple
+    L.check(lib.vz_gemm_bf16(C.byref(g), L.stream_ptr()), "vz_gemm_bf16")
+    torch.cuda.synchronize()
+    return out
+
+
+def ref_gemm(A, W, bias=None, act=0, residual=None):
+    y = A.float() @ W.float().t()
+    if bias is not None:
+        y = y + bias
+    if act == 1:
+        y = y * torch.sigmoid(1.702 * y)
+    elif act == 2:
+        y = torch.nn.functional.gelu(y)
+    if residual is not None:
+        y = y + residual.float()
+    return y
+
+
+def _rand(shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(torch.bfloat16)
+
+
+def _check(out, ref, what, tol=2.0 ** -7):
+    err = (out.float() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"{what}: max_abs_err={err:.4g} ref_max={scale:.4g}")
+    assert err <= tol * max(scale, 1.0), what
+
+
+@pytest.mark.parametrize("simple", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 128, 64), (300, 512, 1024), (1154, 3072, 1024),
+                                   (32, 12288, 4096), (200, 384, 256), (1000, 4096, 8192), (130, 65536, 5120)])
+def test_gemm_plain(M, N, K, simple):
+    if simple and M * N * K > 3e10:
+        pytest.skip("debug kernel is slow")
+    A, W = _rand((M, K), 1.0, 1), _rand((N, K), K ** -0.5, 2)
+    out = run_gemm(A, W, simple=simple)
+    _check(out, ref_gemm(A, W), f"gemm {M}x{N}x{K} simple={simple}")
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_gemm_epilogues(act):
+    M, N, K = 1154, 1024, 4096
+    A, W = _rand((M, K), 1.0, 3), _rand((N, K), K ** -0.5, 4)
+    bias = torch.randn(N, device="cuda") * 0.5
+    res = _rand((M, N), 1.0, 5)
+    out = run_gemm(A, W, bias=bias, act=act, residual=res)
+    _check(out, ref_gemm(A, W, bias, act, res), f"gemm bias+act{act}+residual")
+    # in-place residual (out aliases residual), as the Q-Former blocks use it
+    x = res.clone()
+    run_gemm(A, W, bias=bias, act=act, residual=x, out=x)
+    _check(x, ref_gemm(A, W, bias, act, res), f"gemm in-place residual act{act}")
+
+
+def test_gemm_patch_embed_rows():
+    T = 3
+    A, W = _rand((T * 576, 592), 1.0, 6), _rand((1024, 592), 0.05, 7)
+    A[:, 588:] = 0
+    pos = _rand((577, 1024), 1.0, 8)
+    out = torch.full((T * 577, 1024), 7.0, dtype=torch.bfloat16, device="cuda")
+    run_gemm(A, W, residual=pos, row_mode=1, rows_per=576, out=out)
+    ref = (A.float() @ W.float().t()).view(T, 576, 1024) + pos[1:].float()[None]
+    _check(out.view(T, 577, 1024)[:, 1:], ref, "patch-embed rows")
+    assert (out.view(T, 577, 1024)[:, 0] == 7.0).all(), "CLS rows must be left to the CLS kernel"
+
+
+def test_gemm_residual_mod_rows():
+    A, W = _rand((96, 4096), 1.0, 9), _rand((4096, 4096), 4096 ** -0.5, 10)
+    lq = _rand((32, 4096), 1.0, 11)
+    out = run_gemm(A, W, residual=lq, row_mode=2, rows_per=32)
+    ref = ref_gemm(A, W) + lq.float().repeat(3, 1)
+    _check(out, ref, "residual row % 32")
+
+
+def test_gemm_rejects_bad_arguments():
+    L, lib = _lib()
+    A, W = _rand((64, 72), 1, 1), _rand((64, 72), 1, 2)
+    with pytest.raises(L.VzError):
+        run_gemm(A[:, :70], W[:, :70])          # K % 8 != 0
+    with pytest.raises(L.VzError):
+        run_gemm(_rand((64, 64)), _rand((40, 64)))  # N % 32 != 0
+
+
+@pytest.mark.parametrize("D,M", [(1024, 1154), (4096, 160), (5120, 576)])
+def test_layernorm(D, M):
+    L, lib = _lib()
+    x = _rand((M, D), 3.0, 12) + 1.5
+    g = (1 + 0.1 * torch.randn(D, device="cuda")).float()
+    b = (0.1 * torch.randn(D, device="cuda")).float()
+    out = torch.empty_like(x)
+    L.check(lib.vz_layernorm_bf16(L.ptr(x), D, L.ptr(g), L.ptr(b), L.ptr(out), D, M, D, 1e-5, L.stream_ptr()), "ln")
+    ref = torch.nn.functional.layer_norm(x.float(), (D,), g, b, 1e-5)
+    _check(out, ref, f"layernorm D={D}", tol=2.0 ** -8)
+
+
+def test_layernorm_of_zero_row_is_beta():
+    L, lib = _lib()
+    x = torch.zeros((2, 4096), dtype=torch.bfloat16, device="cuda")
+    g = torch.ones(4096, device="cuda")
+    b = torch.randn(4096, device="cuda").to(torch.bfloat16).float()
+    out = torch.empty_like(x)
+    L.check(lib.vz_layernorm_bf16(L.ptr(x), 4096, L.ptr(g), L.ptr(b), L.ptr(out), 4096, 2, 4096, 1e-5, L.stream_ptr()), "ln")
+    assert torch.equal(out.float(), b[None].expand(2, -1))
+
+
+@pytest.mark.parametrize("f32", [True, False])
+def test_patchify(f32):
+    L, lib = _lib()
+    from oracle import pil_ops as P
+    T = 2
+    px = torch.randn((T, 3, 336, 336), device="cuda")
+    src = px if f32 else px.to(torch.bfloat16)
+    out = torch.empty((T * 576, 592), dtype=torch.bfloat16, device="cuda")
+    L.check(lib.vz_patchify(L.ptr(src), 1 if f32 else 0, T, L.ptr(out), L.stream_ptr()), "patchify")
+    ref = torch.from_numpy(P.patchify(src.float().cpu().numpy())).to(torch.bfloat16)
+    assert torch.equal(out[:, :588].cpu(), ref)
+    assert (out[:, 588:] == 0).all()

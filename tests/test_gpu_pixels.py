@@ -1,0 +1,116 @@
+"""GPU parity of the fused preprocess kernel: bit-exact against the numpy oracle (which is pinned to
+Pillow and to the reference's digests), for anyres tiling, identity 336 input and visual prompts."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import PINPOINTS_C3, PINPOINTS_SHIPPED, synth_image, vip_overlays
+
+pytestmark = pytest.mark.gpu
+
+
+def _lut(golden_dir):
+    return np.load(f"{golden_dir}/golden_pixels.npz")["lut"]
+
+
+@pytest.mark.parametrize("case", [(0, 1000, 900, PINPOINTS_C3), (1, 637, 336, PINPOINTS_SHIPPED),
+                                  (2, 336, 900, PINPOINTS_C3), (3, 1920, 804, PINPOINTS_SHIPPED),
+                                  (4, 336, 336, PINPOINTS_SHIPPED), (6, 250, 180, PINPOINTS_C3)])
+def test_anyres_chw_bit_exact(case, golden_dir):
+    import vision_zephyr_b200 as vz
+    from oracle import pil_ops as P
+    i, W, H, pins = case
+    lut = _lut(golden_dir)
+    img = synth_image(i, W, H)
+    ref = P.process_any_resolution(img, pins, lut)
+    got = vz.process_any_resolution_images([torch.from_numpy(img).cuda()], pins, lut, out_mode="chw")[0]
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    assert got.shape == ref.shape
+    bad = int((got != ref).sum())
+    print(f"case {i} {W}x{H}: tiles={ref.shape[0]} mismatching elements={bad}")
+    assert bad == 0
+    # the reference's own digest travels as a golden
+    from helpers import sha
+    assert sha(got) == str(np.load(f"{golden_dir}/golden_pixels.npz")[f"case{i}_sha"])
+
+
+def test_anyres_patches_are_bf16_im2col_of_chw(golden_dir):
+    import vision_zephyr_b200 as vz
+    from oracle import pil_ops as P
+    lut = _lut(golden_dir)
+    imgs = [synth_image(0, 1000, 900), synth_image(5, 700, 650)]
+    dev = [torch.from_numpy(x).cuda() for x in imgs]
+    pb = vz.process_any_resolution_images(dev, PINPOINTS_C3, lut, out_mode="patches")
+    assert pb.tiles_per_image == [5, 5] and pb.patches.shape == (10 * 576, 592)
+    ref = np.concatenate([P.patchify(P.process_any_resolution(x, PINPOINTS_C3, lut)) for x in imgs])
+    ref = torch.from_numpy(ref).to(torch.bfloat16)
+    got = pb.patches.cpu()
+    assert torch.equal(got[:, :588], ref)
+    assert (got[:, 588:] == 0).all()
+
+
+def test_visual_prompts_fixed336_bit_exact(golden_dir):
+    """config 2: rectangle rasterised in the kernel, mask/arrow as host-rasterised RGBA layers."""
+    import vision_zephyr_b200 as vz
+    from oracle import pil_ops as P
+    g = np.load(f"{golden_dir}/golden_vip.npz")
+    lut = _lut(golden_dir)
+    imgs, prompts, refs = [], [], []
+    for i in range(4):
+        img = synth_image(100 + i, 336, 336)
+        ref = img
+        plist = []
+        for prim in vip_overlays(i, g[f"img{i}_specs"]):
+            if prim[0] == "rectangle":
+                _, bbox, width, rgba = prim
+                plist.append(vz.VisualPrompt("rectangle", rgba=rgba, bbox=tuple(bbox), width=width))
+                layer = np.zeros((336, 336, 4), np.uint8)
+                layer[P.draw_rectangle_mask(336, 336, bbox, width)] = rgba
+            else:
+                layer = prim[1]
+                plist.append(vz.VisualPrompt("layer", layer=layer))
+            ref = P.alpha_composite_rgb(ref, layer)
+        assert np.array_equal(ref[::31, ::29], g[f"img{i}_final_probe"])
+        imgs.append(torch.from_numpy(img).cuda())
+        prompts.append(plist)
+        refs.append(P.normalize_lut(ref[None], lut))
+    got = vz.process_fixed_images(imgs, lut, prompts, out_mode="chw")
+    for i in range(4):
+        assert np.array_equal(got[i].cpu().numpy(), refs[i]), i
+
+
+def test_rectangle_kernel_raster_matches_pillow_semantics(golden_dir):
+    import vision_zephyr_b200 as vz
+    from oracle import pil_ops as P
+    lut = _lut(golden_dir)
+    rng = np.random.default_rng(5)
+    imgs, prompts, refs = [], [], []
+    for i in range(16):
+        img = synth_image(200 + i, 336, 336)
+        x0, y0 = rng.uniform(-10, 300), rng.uniform(-10, 300)
+        bbox = (x0, y0, x0 + rng.uniform(0, 120), y0 + rng.uniform(0, 120))
+        width = int(rng.integers(0, 14))
+        rgba = tuple(int(v) for v in rng.integers(0, 256, 4))
+        layer = np.zeros((336, 336, 4), np.uint8)
+        layer[P.draw_rectangle_mask(336, 336, bbox, width)] = rgba
+        refs.append(P.normalize_lut(P.alpha_composite_rgb(img, layer)[None], lut))
+        imgs.append(torch.from_numpy(img).cuda())
+        prompts.append([vz.VisualPrompt("rectangle", rgba=rgba, bbox=bbox, width=width)])
+    got = vz.process_fixed_images(imgs, lut, prompts, out_mode="chw")
+    for i in range(16):
+        assert np.array_equal(got[i].cpu().numpy(), refs[i]), i
+
+
+def test_blend_then_resize_on_large_image(golden_dir):
+    """visual prompt on a non-square source, then the anyres path (blend feeds the resampler)."""
+    import vision_zephyr_b200 as vz
+    from oracle import pil_ops as P
+    lut = _lut(golden_dir)
+    img = synth_image(9, 900, 500)
+    layer = np.zeros((500, 900, 4), np.uint8)
+    layer[100:300, 200:700] = (10, 200, 30, 77)
+    ref = P.process_any_resolution(P.alpha_composite_rgb(img, layer), PINPOINTS_C3, lut)
+    got = vz.process_any_resolution_images([torch.from_numpy(img).cuda()], PINPOINTS_C3, lut,
+                                           prompts=[[vz.VisualPrompt("layer", layer=layer)]], out_mode="chw")[0]
+    assert np.array_equal(got.cpu().numpy(), ref)

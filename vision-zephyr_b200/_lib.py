@@ -88,6 +88,9 @@ SYMBOLS = {
     "vz_last_cuda_error": (_i, []),
     "vz_version": (_i, []),
     "vz_gemm_bf16": (_i, [C.POINTER(GemmArgs), _vp]),
+    "vz_kernel_launches": (C.c_longlong, []),
+    "vz_gemm_profile": (_i, [_i]),
+    "vz_gemm_profile_read": (_i, [C.POINTER(C.c_longlong), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "vz_layernorm_bf16": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, C.c_float, _vp]),
     "vz_preprocess": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp]),
     "vz_patchify": (_i, [_vp, _i, _i, _vp, _vp]),

@@ -61,14 +61,17 @@ def _slots_to_device(descs: List[dict], device):
 class SplicePlan:
     """Device outputs of vz_splice_plan + the host copy of the totals."""
 
-    def __init__(self, tok_dest, slot_dest, lengths, text_len, totals_dev, host_totals, host_lengths, event):
+    def __init__(self, tok_dest, slot_dest, lengths, text_len, totals_dev, host_meta, B, event):
         self.tok_dest, self.slot_dest, self.lengths, self.text_len = tok_dest, slot_dest, lengths, text_len
-        self.totals_dev, self._host_totals, self._host_lengths, self._event = totals_dev, host_totals, host_lengths, event
+        self.totals_dev, self._host, self._B, self._event = totals_dev, host_meta, B, event
 
     def wait(self):
+        """Block until the planned lengths are on the host (the only host round-trip of the path)."""
         self._event.synchronize()
-        t = self._host_totals
-        return dict(Lmax=int(t[0]), L_text=int(t[1]), slots_used=int(t[2]), text_rows=int(t[3]))
+        B, h = self._B, self._host
+        t = h[2 * B:]
+        return dict(Lmax=int(t[0]), L_text=int(t[1]), slots_used=int(t[2]), text_rows=int(t[3]),
+                    lengths=h[:B].tolist(), text_len=h[B:2 * B].tolist())
 
 
 def splice_plan(input_ids: torch.Tensor, mask_u8: Optional[torch.Tensor], slots_dev, n_slots: int,
@@ -87,19 +90,26 @@ def splice_plan(input_ids: torch.Tensor, mask_u8: Optional[torch.Tensor], slots_
     host.copy_(meta, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
-    return SplicePlan(tok_dest, slot_dest, lengths, text_len, totals, host[2 * B:], host[:B], ev)
+    return SplicePlan(tok_dest, slot_dest, lengths, text_len, totals, host, B, ev)
 
 
-def text_gather(input_ids: torch.Tensor, embed_weight: torch.Tensor, plan: SplicePlan, text_rows: int):
+def text_gather(input_ids: torch.Tensor, embed_weight: torch.Tensor, plan: SplicePlan, text_rows: int,
+                lo: int = 0, hi: Optional[int] = None):
+    """Packed non-image token embeddings of samples [lo, hi) (+ one zero row) and their offsets."""
     lib = _lib.load()
     B, S = input_ids.shape
+    hi = B if hi is None else hi
+    n = hi - lo
     D = embed_weight.shape[1]
     dev = input_ids.device
     text_emb = torch.empty((text_rows + 1, D), dtype=embed_weight.dtype, device=dev)
-    text_off = torch.empty((B + 1,), dtype=torch.int32, device=dev)
-    _lib.check(lib.vz_text_gather(_lib.ptr(input_ids), B, S, _lib.ptr(embed_weight), D, embed_weight.element_size(),
-                                  _lib.ptr(plan.text_len), _lib.ptr(text_emb), _lib.ptr(text_off),
-                                  _lib.stream_ptr()), "vz_text_gather")
+    text_off = torch.zeros((n + 1,), dtype=torch.int32, device=dev)
+    if n > 0:
+        _lib.check(lib.vz_text_gather(_lib.ptr(input_ids[lo:hi]), n, S, _lib.ptr(embed_weight), D,
+                                      embed_weight.element_size(), _lib.ptr(plan.text_len[lo:hi]),
+                                      _lib.ptr(text_emb), _lib.ptr(text_off), _lib.stream_ptr()), "vz_text_gather")
+    else:
+        text_emb.zero_()
     return text_emb, text_off
 
 
@@ -189,6 +199,21 @@ class VisZephyrB200MetaForCausalLM(ABC):
     def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values,
                                              labels, images, images_size=None):
         """vis_zephyr_arch.py:129-333, same arguments and return tuple."""
+        return self._prepare(input_ids, position_ids, attention_mask, past_key_values, labels, images,
+                             images_size, None, None, 0)
+
+    def prepare_inputs_labels_for_multimodal_sharded(self, input_ids, position_ids, attention_mask,
+                                                     past_key_values, labels, local_images, tiles_per_image,
+                                                     images_size=None, group=None, dst=0):
+        """Data-parallel form (north_star): every rank holds the (small) global text batch and encodes
+        only ITS contiguous block of images (`local_images`, a PatchBatch or list of tile tensors for the
+        images dist.shard_images assigns to this rank); the projected visual tokens are all-gathered and
+        rank `dst` splices the global batch.  Other ranks return None for the tensors."""
+        return self._prepare(input_ids, position_ids, attention_mask, past_key_values, labels, local_images,
+                             images_size, list(tiles_per_image), group, dst)
+
+    def _prepare(self, input_ids, position_ids, attention_mask, past_key_values, labels, images, images_size,
+                 global_tiles, group, dst):
         vision_tower = self.get_vision_tower()
         if vision_tower is None or images is None or input_ids.shape[1] == 1:
             return input_ids, position_ids, attention_mask, past_key_values, None, labels
@@ -200,17 +225,28 @@ class VisZephyrB200MetaForCausalLM(ABC):
 
         # ---- images -> per-image tile counts ----------------------------------------------------
         if isinstance(images, PatchBatch):
-            tiles_per_image = images.tiles_per_image
+            local_tiles = images.tiles_per_image
             patches = images.patches
         elif type(images) is list or images.ndim == 5:
             per_image = [x.unsqueeze(0) if x.ndim == 3 else x for x in images]
-            tiles_per_image = [int(x.shape[0]) for x in per_image]
-            concat = torch.cat([x for x in per_image], dim=0)
-            patches = vision_tower._patches_of(concat)
+            local_tiles = [int(x.shape[0]) for x in per_image]
+            patches = vision_tower._patches_of(torch.cat(per_image, dim=0)) if per_image else None
         else:
             # the reference's 4-D / 3-D branch fails inside QFormer.forward (quirk Q1)
             raise RuntimeError("Tensors must have same number of dimensions: got 3 and 2 "
                                "(pass images as a list of [T_i,3,336,336] tensors or a 5-D tensor)")
+        sharded = global_tiles is not None
+        if sharded:
+            import torch.distributed as tdist
+            from .dist import gather_visual_tokens, shard_images
+            world, rank = tdist.get_world_size(group), tdist.get_rank(group)
+            tiles_per_image = global_tiles
+            bounds = shard_images(tiles_per_image, world)
+            lo, hi = bounds[rank]
+            if list(local_tiles) != list(tiles_per_image[lo:hi]):
+                raise ValueError(f"rank {rank} was given tiles {local_tiles}, expected {tiles_per_image[lo:hi]}")
+        else:
+            tiles_per_image, lo, hi = list(local_tiles), 0, len(local_tiles)
         n_images = len(tiles_per_image)
         B, S = input_ids.shape
         if n_images > B:
@@ -221,36 +257,44 @@ class VisZephyrB200MetaForCausalLM(ABC):
             mask_u8 = attention_mask.to(dev).bool().to(torch.uint8).contiguous()
         labels_dev = labels.to(dev).contiguous() if labels is not None else None
 
-        # ---- plan (device) while the host prepares the tower launch -----------------------------
-        descs = self._slot_descs(tiles_per_image, images_size, model.mm_projector.num_queries)
+        # ---- plan on the device while the host queues the tower ----------------------------------
+        proj = model.mm_projector
+        descs = self._slot_descs(tiles_per_image, images_size, proj.num_queries)
         slots_dev, slot_prefix, total_vis_rows = _slots_to_device(descs, dev)
         max_len = getattr(self.config, "tokenizer_model_max_length", None) or 0
         plan = splice_plan(input_ids, mask_u8, slots_dev, n_images, max_len)
 
         # ---- tower (independent of the text) ---------------------------------------------------
-        proj = model.mm_projector
-        feats = vision_tower.encode_patches(patches, pre_norm=proj.pre_norm_params())
+        feats = None
+        if hi > lo:
+            feats = vision_tower.encode_patches(patches, pre_norm=proj.pre_norm_params())
 
-        # ---- text conditioning: one row set per SAMPLE, shared by its tiles --------------------
+        # ---- text conditioning: one row set per SAMPLE, shared by its tiles; the reference
+        # conditions image i on ids[i] (:163-176) and pads to the batch-global max (quirk Q3) -----
         info = plan.wait()
         if info["slots_used"] > n_images:
-            raise IndexError("tuple index out of range: more image slots consumed than image features")
-        # the reference conditions on ids[i] for i < n_images only (:163-176)
-        if n_images < B:
-            sub = splice_plan(input_ids[:n_images].contiguous(), None, slots_dev, n_images, 0)
-            sinfo = sub.wait()
-            text_plan, L_text, text_rows = sub, sinfo["L_text"], sinfo["text_rows"]
-            ids_for_text = input_ids[:n_images].contiguous()
+            raise IndexError("list index out of range: more image slots consumed than image features")
+        L_text = max(info["text_len"][:n_images])
+        vis_local = torch.empty((0, embed.shape[1]), dtype=torch.bfloat16, device=dev)
+        if hi > lo:
+            text_rows = sum(info["text_len"][lo:hi])
+            text_emb, text_off = text_gather(input_ids, embed, plan, text_rows, lo, hi)
+            if text_emb.dtype != torch.bfloat16:
+                text_emb = text_emb.to(torch.bfloat16)
+            tile_sample = torch.repeat_interleave(torch.arange(hi - lo, dtype=torch.int32),
+                                                  torch.tensor(tiles_per_image[lo:hi])).to(dev)
+            text = TextPack(text_emb, text_off, text_rows, hi - lo, L_text, tile_sample)
+            vis_local = proj.forward_packed(feats, text, feats_normed=True)      # [T,32,4096] bf16
+            vis_local = vis_local.reshape(-1, vis_local.shape[-1])
+
+        # ---- the one exchange step ------------------------------------------------------------
+        if sharded:
+            rows_per_rank = [sum(tiles_per_image[a:b]) * proj.num_queries for a, b in bounds]
+            vis = gather_visual_tokens(vis_local, rows_per_rank, group)
+            if rank != dst:
+                return None, None, None, past_key_values, None, None
         else:
-            text_plan, L_text, text_rows, ids_for_text = plan, info["L_text"], info["text_rows"], input_ids
-        text_emb, text_off = text_gather(ids_for_text, embed, text_plan, text_rows)
-        tile_sample = torch.repeat_interleave(
-            torch.arange(n_images, dtype=torch.int32), torch.tensor(tiles_per_image)).to(dev)
-        if text_emb.dtype != torch.bfloat16:
-            text_emb = text_emb.to(torch.bfloat16)
-        text = TextPack(text_emb, text_off, text_rows, n_images, L_text, tile_sample)
-        vis = proj.forward_packed(feats, text, feats_normed=True)      # [T,32,4096] bf16
-        vis = vis.reshape(-1, vis.shape[-1])
+            vis = vis_local
         if vis.dtype != embed.dtype:
             vis = vis.to(embed.dtype)
 

@@ -25,7 +25,13 @@ inline int cuda_fail(cudaError_t e) {
     cudaError_t _e = (expr);                                \
     if (_e != cudaSuccess) return ::vz::cuda_fail(_e);      \
   } while (0)
-#define VZ_LAUNCH_CHECK() VZ_CUDA_CHECK(cudaGetLastError())
+// every kernel launch of the library goes through this macro, which also feeds vz_kernel_launches()
+void count_launch();
+#define VZ_LAUNCH_CHECK()                  \
+  do {                                     \
+    ::vz::count_launch();                  \
+    VZ_CUDA_CHECK(cudaGetLastError());     \
+  } while (0)
 #define VZ_TRY(expr)            \
   do {                          \
     int _s = (expr);            \

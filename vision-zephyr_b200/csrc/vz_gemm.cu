@@ -8,9 +8,27 @@
 // q/k/v/out/fc1/fc2, K7 the stacked cross-attention K/V projection, K8 the Q-Former linears).
 #include "vz_common.cuh"
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 namespace vz {
 
 thread_local int g_last_cuda_error = 0;
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// Optional measurement hook (bench.py): CUDA events around every tcgen05 GEMM launch, on the
+// launching stream, plus the algorithmic FLOPs of that launch.  Off by default.
+struct GemmProf {
+  std::mutex mu;
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  std::vector<double> flops;
+};
+static GemmProf g_prof;
 
 namespace {
 
@@ -318,8 +336,24 @@ int launch_tc(const vz_gemm_args& a, const GemmDev& p, int num_sms, cudaStream_t
   }
   const int tiles = p.num_m * p.num_n;
   const int grid = tiles < num_sms ? tiles : num_sms;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_prof.on) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    if (g_prof.used + 2 > g_prof.pool.size()) {
+      for (int i = 0; i < 2; ++i) {
+        cudaEvent_t e;
+        VZ_CUDA_CHECK(cudaEventCreate(&e));
+        g_prof.pool.push_back(e);
+      }
+    }
+    e0 = g_prof.pool[g_prof.used++];
+    e1 = g_prof.pool[g_prof.used++];
+    g_prof.flops.push_back(2.0 * a.M * (double)a.N * a.K);
+    VZ_CUDA_CHECK(cudaEventRecord(e0, st));
+  }
   gemm_bf16_tcgen05_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, st>>>(tmA, tmB, p);
   VZ_LAUNCH_CHECK();
+  if (e1) VZ_CUDA_CHECK(cudaEventRecord(e1, st));
   return VZ_OK;
 }
 
@@ -368,6 +402,35 @@ int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
 }
 
 }  // namespace vz
+
+extern "C" long long vz_kernel_launches(void) { return vz::g_launches.load(); }
+
+extern "C" int vz_gemm_profile(int enable) {
+  std::lock_guard<std::mutex> lk(vz::g_prof.mu);
+  vz::g_prof.on = enable != 0;
+  vz::g_prof.used = 0;
+  vz::g_prof.flops.clear();
+  return VZ_OK;
+}
+
+// Synchronises the recorded events and returns launches, summed milliseconds and summed FLOPs.
+extern "C" int vz_gemm_profile_read(long long* launches, double* total_ms, double* total_flops) {
+  std::lock_guard<std::mutex> lk(vz::g_prof.mu);
+  double ms = 0, fl = 0;
+  const size_t n = vz::g_prof.used / 2;
+  for (size_t i = 0; i < n; ++i) {
+    float t = 0;
+    cudaError_t e = cudaEventSynchronize(vz::g_prof.pool[2 * i + 1]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, vz::g_prof.pool[2 * i], vz::g_prof.pool[2 * i + 1]);
+    if (e != cudaSuccess) return vz::cuda_fail(e);
+    ms += t;
+    fl += vz::g_prof.flops[i];
+  }
+  if (launches) *launches = (long long)n;
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  return VZ_OK;
+}
 
 extern "C" int vz_gemm_bf16(const vz_gemm_args* args, void* stream) {
   if (!args) return VZ_ERR_BAD_ARG;

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -108,7 +109,7 @@ class QFormerB200(nn.Module):
         self.blocks = nn.ModuleList([_Block(WIDTH, KV_WIDTH, FFN) for _ in range(BLOCKS)])
         self.pre_norm = _Norm(KV_WIDTH)
         self.norm = _Norm(WIDTH)
-        self.force_simple_gemm = False
+        self.force_simple_gemm = os.environ.get("VZ_FORCE_SIMPLE_GEMM") == "1"
         self._ws = Workspace()
         self._packed: Dict[str, torch.Tensor] = {}
         self._packed_key = None

@@ -63,3 +63,50 @@ class VisionEmbeddingPath(VisZephyrB200MetaForCausalLM):
         if image_newline is not None and hasattr(m, "image_newline"):
             m.image_newline.copy_(image_newline.to(self.dtype))
         return missing
+
+
+@torch.no_grad()
+def random_init_(path: VisionEmbeddingPath, seed: int = 0):
+    """Random-init weights of the right architecture, generated ON THE DEVICE (benchmarks have no
+    checkpoints; the tests use the CPU-seeded oracle weights instead).  Scales follow HF CLIP's
+    initialiser and torch's defaults for the projector."""
+    dev = path.device
+    g = torch.Generator(device=dev).manual_seed(seed)
+    W, L, MLP = 1024, 24, 4096
+
+    def n(shape, std):
+        return torch.randn(shape, generator=g, device=dev) * std
+
+    p = "vision_model."
+    sd = {p + "embeddings.class_embedding": n((W,), W ** -0.5),
+          p + "embeddings.patch_embedding.weight": n((W, 3, 14, 14), 0.02),
+          p + "embeddings.position_embedding.weight": n((577, W), 0.02),
+          p + "pre_layrnorm.weight": 1 + n((W,), 0.1), p + "pre_layrnorm.bias": n((W,), 0.1)}
+    in_std, out_std, fc_std = (W ** -0.5) * ((2 * L) ** -0.5), W ** -0.5, (2 * W) ** -0.5
+    for l in range(L):
+        q = f"{p}encoder.layers.{l}."
+        for nm in ("q_proj", "k_proj", "v_proj"):
+            sd[q + f"self_attn.{nm}.weight"] = n((W, W), 4 * in_std if nm != "v_proj" else in_std)
+            sd[q + f"self_attn.{nm}.bias"] = n((W,), 0.02)
+        sd[q + "self_attn.out_proj.weight"], sd[q + "self_attn.out_proj.bias"] = n((W, W), out_std * 0.5), n((W,), 0.02)
+        for k in ("layer_norm1", "layer_norm2"):
+            sd[q + k + ".weight"], sd[q + k + ".bias"] = 1 + n((W,), 0.1), n((W,), 0.05)
+        sd[q + "mlp.fc1.weight"], sd[q + "mlp.fc1.bias"] = n((MLP, W), fc_std), n((MLP,), 0.02)
+        sd[q + "mlp.fc2.weight"], sd[q + "mlp.fc2.bias"] = n((W, MLP), in_std), n((W,), 0.02)
+    path.model.vision_tower.load_model(state_dict=sd, device=dev)
+    del sd
+    proj = path.model.mm_projector
+    for name, prm in proj.named_parameters():
+        if name == "learned_queries":
+            prm.copy_(n(prm.shape, 1.0))
+        elif name.endswith("norm.weight") or ".norm" in name and name.endswith("weight") or name.startswith("pre_norm.w"):
+            prm.copy_(1 + n(prm.shape, 0.1))
+        elif prm.dim() == 1:
+            prm.copy_(n(prm.shape, 0.02))
+        else:
+            bound = (6.0 / (prm.shape[0] + prm.shape[1])) ** 0.5
+            prm.copy_((torch.rand(prm.shape, generator=g, device=dev) * 2 - 1) * bound)
+    path.model.embed_tokens.weight.copy_(n(path.model.embed_tokens.weight.shape, 0.02))
+    if hasattr(path.model, "image_newline"):
+        path.model.image_newline.copy_(n((path.config.hidden_size,), path.config.hidden_size ** -0.5))
+    return path

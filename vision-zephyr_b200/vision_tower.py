@@ -62,7 +62,8 @@ class CLIPVisionTowerB200(nn.Module):
             self.select_layers = [-2]  # parsed but unused by feature_select, like the reference (quirk Q5)
         self.cfg_only = default_clip_config()
         self.image_processor = None
-        self.force_simple_gemm = False
+        # bring-up switch: route every GEMM through the plain CUDA-core kernel instead of tcgen05
+        self.force_simple_gemm = os.environ.get("VZ_FORCE_SIMPLE_GEMM") == "1"
         self._w: Optional[_lib.VitWeights] = None
         self._packed: Dict[str, torch.Tensor] = {}
         self._ws = Workspace()
