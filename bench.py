@@ -45,41 +45,66 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe), through
+    NVML (the same counters nvidia-smi prints) from a background thread every 50 ms."""
+
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop_flag, self.thread = index, [], False, None
+        self.t0 = self.t1 = None
+        self.max_mhz = None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            return
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        def loop():
+            while not self.stop_flag:
+                try:
+                    sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    try:
+                        rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    self.rows.append((time.time(), float(sm), int(rs), pw))
+                except Exception:
+                    pass
+                time.sleep(0.05)
+
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(1.0)
+        rows = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or r[0])]
+        if not rows:
+            rows = self.rows
+        reasons = set()
+        for r in rows:
+            for name, bit in self.REASONS.items():
+                if r[2] & bit:
+                    reasons.add(name)
+        sm = [r[1] for r in rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max((r[3] for r in rows), default=None)}
 
 
 def make_inputs(rank, n_local=IMAGES_PER_GPU):
@@ -125,10 +150,10 @@ def run_reference_arm(args):
     one_image(imgs[0])
     t_first = time.perf_counter() - t0
     steps, warm = args.steps, max(args.warmup - 1, 0)
-    # bound the run to a few minutes: shrink the number of timed steps if one image is slow
-    budget = 240.0
-    if t_first * (steps + warm) > budget:
-        steps = max(1, int(budget / t_first) - warm)
+    # one image per step keeps K+W steps within minutes (about 3 s per image on 16 cores); only a
+    # pathological request (> 15 min) is cut short, and the line then reports the steps actually timed
+    if t_first * (steps + warm) > 900.0:
+        steps = max(1, int(900.0 / t_first) - warm)
     for i in range(warm):
         one_image(imgs[(i + 1) % len(imgs)])
     t0 = time.perf_counter()
@@ -151,7 +176,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

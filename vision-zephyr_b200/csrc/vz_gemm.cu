@@ -35,7 +35,9 @@ namespace {
 constexpr int BM = 128;       // UMMA M (cta_group::1)
 constexpr int BK = 64;        // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;    // fixed for 16-bit inputs
-constexpr int kThreads = 256; // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int kEpiWarps = 8;  // two warps per TMEM lane quarter, interleaved 32-column chunks
+constexpr int kThreads = 128 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-11 epilogue
+constexpr int EPI_STAGE_BYTES = 32 * 64;  // per epilogue warp: 32 rows x 32 bf16, chunk-swizzled
 constexpr int GROUP_N = 8;    // n-blocks per rasterisation band (keeps the W band + A strip in L2)
 
 template <int BN>
@@ -46,7 +48,8 @@ struct Cfg {
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + align slack
+  static constexpr int EPI_BYTES = kEpiWarps * EPI_STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + align slack
 };
 
 struct GemmDev {
@@ -71,7 +74,11 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int&
 
 __device__ __forceinline__ float act_apply(float x, int act) {
   if (act == VZ_ACT_QUICK_GELU) {
-    return x / (1.0f + __expf(-1.702f * x));
+    // x * sigmoid(1.702 x) = 0.5 x (1 + tanh(0.851 x)): one MUFU op per element
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
   } else if (act == VZ_ACT_GELU_ERF) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
   }
@@ -88,7 +95,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * C::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* sEpi = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + C::EPI_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + C::STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * C::STAGES;   // [2]
@@ -110,7 +118,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -166,33 +174,61 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     }
   } else if (warp >= 4) {
     // ============================ epilogue ================================
-    const int q = warp - 4;  // TMEM lane quarter == warp % 4
+    // warp e: TMEM lane quarter q = e % 4 (== warp % 4, the hardware's lane-access rule), column
+    // chunks c = e/4, e/4 + 2, ...  Each 32x32 chunk goes TMEM -> registers (row per lane) ->
+    // per-warp swizzled smem tile -> 8 rows x 64 B per store instruction (coalesced); the residual
+    // takes the same route in the opposite direction.
+    const int e = warp - 4;
+    const int q = e & 3;
+    const int half = e >> 2;
+    uint8_t* stg = sEpi + e * EPI_STAGE_BYTES;
+    const uint32_t stg_u32 = smem_u32(stg);
+    // own-row addressing (lane = row) and cooperative addressing (4 lanes per row)
+    const uint32_t own_off = (uint32_t)lane * 64u;
+    const uint32_t own_sw = (uint32_t)((lane >> 1) & 3);
+    const int co_r = lane >> 2, co_j = lane & 3;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
       tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk);
       mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
       tc_fence_after();
-      const int m = m_blk * BM + q * 32 + lane;
-      const bool row_ok = m < p.M;
-      int out_row = m, res_row = m;
-      if (p.row_mode == VZ_ROWS_PATCH_EMBED) {
-        const int img = m / p.rows_per;
-        out_row = m + img + 1;
-        res_row = 1 + (m - img * p.rows_per);
-      } else if (p.row_mode == VZ_ROWS_RES_MOD) {
-        res_row = m % p.rows_per;
+      const int m_base = m_blk * BM + q * 32;
+      // rows this lane touches in the cooperative phases: m_base + 8*i + co_r
+      size_t co_out[4], co_res[4];
+      bool co_ok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m_base + 8 * i + co_r;
+        co_ok[i] = m < p.M;
+        int out_row = m, res_row = m;
+        if (p.row_mode == VZ_ROWS_PATCH_EMBED) {
+          const int img = m / p.rows_per;
+          out_row = m + img + 1;
+          res_row = 1 + (m - img * p.rows_per);
+        } else if (p.row_mode == VZ_ROWS_RES_MOD) {
+          res_row = m % p.rows_per;
+        }
+        co_out[i] = (size_t)out_row * p.ldo + co_j * 8;
+        co_res[i] = (size_t)res_row * p.ldr + co_j * 8;
       }
-      __nv_bfloat16* out_ptr = p.out + (size_t)out_row * p.ldo;
-      const __nv_bfloat16* res_ptr =
-          p.residual ? p.residual + (size_t)res_row * p.ldr : nullptr;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         const int col0 = n_blk * BN + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c * 32, r);
+        if (p.residual) {
+          // coalesced residual chunk -> staging tile (overlaps the TMEM load)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 w = make_uint4(0, 0, 0, 0);
+            if (co_ok[i]) w = *reinterpret_cast<const uint4*>(p.residual + co_res[i] + col0);
+            const int rr = 8 * i + co_r;
+            *reinterpret_cast<uint4*>(stg + rr * 64 + ((co_j ^ ((rr >> 1) & 3)) << 4)) = w;
+          }
+        }
         tmem_ld_wait();
         float v[32];
 #pragma unroll
@@ -209,30 +245,36 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], p.act);
         }
-        if (row_ok) {
-          if (res_ptr) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(res_ptr + col0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 w = r4[i];
-              v[8 * i + 0] += bf16_lo(w.x); v[8 * i + 1] += bf16_hi(w.x);
-              v[8 * i + 2] += bf16_lo(w.y); v[8 * i + 3] += bf16_hi(w.y);
-              v[8 * i + 4] += bf16_lo(w.z); v[8 * i + 5] += bf16_hi(w.z);
-              v[8 * i + 6] += bf16_lo(w.w); v[8 * i + 7] += bf16_hi(w.w);
-            }
-          }
-          uint4* o4 = reinterpret_cast<uint4*>(out_ptr + col0);
+        if (p.residual) {
+          __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            uint4 w;
-            w.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-            w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-            w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-            w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-            o4[i] = w;
+            const uint4 w = *reinterpret_cast<const uint4*>(stg + own_off + (((uint32_t)i ^ own_sw) << 4));
+            v[8 * i + 0] += bf16_lo(w.x); v[8 * i + 1] += bf16_hi(w.x);
+            v[8 * i + 2] += bf16_lo(w.y); v[8 * i + 3] += bf16_hi(w.y);
+            v[8 * i + 4] += bf16_lo(w.z); v[8 * i + 5] += bf16_hi(w.z);
+            v[8 * i + 6] += bf16_lo(w.w); v[8 * i + 7] += bf16_hi(w.w);
           }
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 w;
+          w.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+          w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+          w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+          w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+          *reinterpret_cast<uint4*>(stg + own_off + (((uint32_t)i ^ own_sw) << 4)) = w;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = 8 * i + co_r;
+          const uint4 w = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((co_j ^ ((rr >> 1) & 3)) << 4));
+          if (co_ok[i]) *reinterpret_cast<uint4*>(p.out + co_out[i] + col0) = w;
+        }
+        __syncwarp();  // staging tile is reused by the next chunk
       }
+      (void)stg_u32;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
