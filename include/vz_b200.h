@@ -70,6 +70,12 @@ typedef struct {
   int row_mode;         /* VZ_ROWS_*                           */
   int rows_per;         /* see row_mode                        */
   int force_simple;     /* 1 = debug path: plain CUDA-core GEMM (no tcgen05); for bring-up only */
+  /* batched form (batch > 1): problem b uses A + b*a_bstride, W + b*w_bstride, out + b*o_bstride,
+   * residual + b*r_bstride, bias + b*bias_bstride (all in ELEMENTS; 0 = shared).  M, N, K and
+   * the leading dimensions are common to all problems.                                       */
+  int batch;
+  int out_f32;          /* 1 = write float32 instead of bf16 (no residual / row remap)          */
+  long long a_bstride, w_bstride, o_bstride, r_bstride, bias_bstride;
 } vz_gemm_args;
 
 int vz_gemm_bf16(const vz_gemm_args* args, void* stream);
@@ -206,7 +212,9 @@ typedef struct {
   const void* sa_out_w;  /* bf16 [4096,4096] */
   const float* sa_out_b;
   const void* ca_q_w;    /* bf16 [4096,4096] */
-  const float* ca_in_b;  /* f32 [12288] (q,k,v biases) */
+  const void* ca_kT_w;   /* bf16 [5120,4096] = k_proj_weight TRANSPOSED (row n, column h*512+d)   */
+  const void* ca_v_w;    /* bf16 [4096,5120] = v_proj_weight                                        */
+  const float* ca_in_b;  /* f32 [12288] (q,k,v biases; the k bias cancels in the softmax)          */
   const void* ca_out_w;  /* bf16 [4096,4096] */
   const float* ca_out_b;
   const void* ffn1_w;    /* bf16 [8192,4096] */
@@ -219,8 +227,6 @@ typedef struct {
   const void* learned_queries; /* bf16 [32,4096] */
   const float *pre_g, *pre_b;  /* LayerNorm(5120) */
   const float *norm_g, *norm_b;/* LayerNorm(4096) */
-  const void* kv_w;            /* bf16 [8*2*4096, 5120]: blocks' (k_proj_weight, v_proj_weight) stacked */
-  const float* kv_b;           /* f32 [65536]: matching slices of cross_attn.in_proj_bias        */
   vz_qf_block blocks[VZ_QF_BLOCKS];
 } vz_qf_weights;
 

@@ -148,3 +148,49 @@ def test_patchify(f32):
     ref = torch.from_numpy(P.patchify(src.float().cpu().numpy())).to(torch.bfloat16)
     assert torch.equal(out[:, :588].cpu(), ref)
     assert (out[:, 588:] == 0).all()
+
+
+def test_gemm_batched_heads_and_f32_output():
+    """batched form used by the reassociated cross-attention: strided A/W/out per batch, fp32 scores."""
+    L, lib = _lib()
+    # (1) batch over heads: A columns h*512.., W columns h*512.., out [(rows), h, N]
+    M, H, K, N = 96, 8, 512, 5120
+    q = _rand((M, H * K), 1.0, 21)
+    wT = _rand((N, H * K), K ** -0.5, 22)
+    out = torch.zeros((M, H, N), dtype=torch.bfloat16, device="cuda")
+    g = L.GemmArgs()
+    g.A, g.W, g.out = q.data_ptr(), wT.data_ptr(), out.data_ptr()
+    g.M, g.N, g.K, g.lda, g.ldw, g.ldo = M, N, K, H * K, H * K, H * N
+    g.batch, g.a_bstride, g.w_bstride, g.o_bstride = H, K, K, N
+    L.check(lib.vz_gemm_bf16(C.byref(g), L.stream_ptr()), "batched heads")
+    torch.cuda.synchronize()
+    ref = torch.einsum("mhk,nhk->mhn", q.float().view(M, H, K), wT.float().view(N, H, K))
+    _check(out, ref, "batched-heads gemm")
+    # (2) batch over tiles, N = 576 (partial last n-tile), fp32 output, per-batch bias
+    T, Mq, Kf, Np = 3, 256, 5120, 576
+    a = _rand((T, Mq, Kf), 1.0, 23)
+    f = _rand((T, Np, Kf), Kf ** -0.5, 24)
+    bias = torch.randn((T, Np), device="cuda")
+    s = torch.full((T, Mq, Np), float("nan"), dtype=torch.float32, device="cuda")
+    g = L.GemmArgs()
+    g.A, g.W, g.out, g.bias = a.data_ptr(), f.data_ptr(), s.data_ptr(), bias.data_ptr()
+    g.M, g.N, g.K, g.lda, g.ldw, g.ldo = Mq, Np, Kf, Kf, Kf, Np
+    g.batch, g.out_f32 = T, 1
+    g.a_bstride, g.w_bstride, g.o_bstride, g.bias_bstride = Mq * Kf, Np * Kf, Mq * Np, Np
+    L.check(lib.vz_gemm_bf16(C.byref(g), L.stream_ptr()), "batched f32")
+    torch.cuda.synchronize()
+    ref = torch.einsum("tmk,tnk->tmn", a.float(), f.float()) + bias[:, None, :]
+    err = (s - ref).abs().max().item()
+    print("batched f32 scores max_abs_err", err)
+    assert err < 2e-3
+    # (3) K = 576 (9 k-blocks), M not a multiple of 128 inside each batch
+    P_ = _rand((T, 200, 576), 0.1, 25)
+    fT = _rand((T, 640, 576), 1.0, 26)
+    o = torch.zeros((T, 200, 640), dtype=torch.bfloat16, device="cuda")
+    g = L.GemmArgs()
+    g.A, g.W, g.out = P_.data_ptr(), fT.data_ptr(), o.data_ptr()
+    g.M, g.N, g.K, g.lda, g.ldw, g.ldo = 200, 640, 576, 576, 576, 640
+    g.batch, g.a_bstride, g.w_bstride, g.o_bstride = T, 200 * 576, 640 * 576, 200 * 640
+    L.check(lib.vz_gemm_bf16(C.byref(g), L.stream_ptr()), "batched ragged")
+    torch.cuda.synchronize()
+    _check(o, torch.einsum("tmk,tnk->tmn", P_.float(), fT.float()), "batched ragged-M gemm")

@@ -26,6 +26,9 @@ class GemmArgs(C.Structure):
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
         ("lda", C.c_int), ("ldw", C.c_int), ("ldo", C.c_int), ("ldr", C.c_int),
         ("act", C.c_int), ("row_mode", C.c_int), ("rows_per", C.c_int), ("force_simple", C.c_int),
+        ("batch", C.c_int), ("out_f32", C.c_int),
+        ("a_bstride", C.c_longlong), ("w_bstride", C.c_longlong), ("o_bstride", C.c_longlong),
+        ("r_bstride", C.c_longlong), ("bias_bstride", C.c_longlong),
     ]
 
 
@@ -60,13 +63,12 @@ class VitWeights(C.Structure):
 class QfBlock(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "n1_g", "n1_b", "n2_g", "n2_b", "n3_g", "n3_b", "sa_in_w", "sa_in_b", "sa_out_w", "sa_out_b",
-        "ca_q_w", "ca_in_b", "ca_out_w", "ca_out_b", "ffn1_w", "ffn1_b", "ffn2_w", "ffn2_b")]
+        "ca_q_w", "ca_kT_w", "ca_v_w", "ca_in_b", "ca_out_w", "ca_out_b", "ffn1_w", "ffn1_b", "ffn2_w", "ffn2_b")]
 
 
 class QfWeights(C.Structure):
     _fields_ = [("learned_queries", C.c_void_p), ("pre_g", C.c_void_p), ("pre_b", C.c_void_p),
-                ("norm_g", C.c_void_p), ("norm_b", C.c_void_p), ("kv_w", C.c_void_p),
-                ("kv_b", C.c_void_p), ("blocks", QfBlock * QF_BLOCKS)]
+                ("norm_g", C.c_void_p), ("norm_b", C.c_void_p), ("blocks", QfBlock * QF_BLOCKS)]
 
 
 class SlotDesc(C.Structure):

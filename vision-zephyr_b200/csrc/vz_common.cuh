@@ -50,6 +50,8 @@ int fuse_launch(const void* const* hs21, int T, const float* g, const float* b, 
 int cls_rows_launch(const void* cls, const void* pos, void* emb, int T, cudaStream_t st);
 int gather_rows_launch(const void* in, void* out, int M, int row_bytes, const int32_t* row_map,
                        int rows_per, cudaStream_t st);
+int transpose_launch(const void* in, void* out, int batch, int R, int C, cudaStream_t st);
+int softmax_rows_launch(const float* s, void* p, int rows, int n, float scale, cudaStream_t st);
 int vit_attn_launch(const void* qkv, void* out, int T, cudaStream_t st);
 int qattn_launch(int mode, const void* q, int q_rs, int q_zrows, const void* k0, const void* v0,
                  int rs0, int zrows0, int count0, const void* k1, const void* v1, int rs1,
@@ -135,6 +137,17 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
       :
       : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0),
         "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* dst,
+                                            int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0),
+        "r"(c1), "r"(c2)
       : "memory");
 }
 

@@ -37,7 +37,7 @@ constexpr int BK = 64;        // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;    // fixed for 16-bit inputs
 constexpr int kEpiWarps = 8;  // two warps per TMEM lane quarter, interleaved 32-column chunks
 constexpr int kThreads = 128 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-11 epilogue
-constexpr int EPI_STAGE_BYTES = 32 * 64;  // per epilogue warp: 32 rows x 32 bf16, chunk-swizzled
+constexpr int EPI_STAGE_BYTES = 32 * 128;  // per epilogue warp: 32 rows x 32 values (bf16 or f32), chunk-swizzled
 constexpr int GROUP_N = 8;    // n-blocks per rasterisation band (keeps the W band + A strip in L2)
 
 template <int BN>
@@ -53,16 +53,21 @@ struct Cfg {
 };
 
 struct GemmDev {
-  __nv_bfloat16* out;
+  __nv_bfloat16* out;  // bf16, or float when out_f32
   const float* bias;
   const __nv_bfloat16* residual;
   int M, N, K;
   int ldo, ldr;
   int act, row_mode, rows_per;
   int num_m, num_n, num_k;
+  int batch, out_f32;
+  long long o_bstride, r_bstride, bias_bstride;  // elements between consecutive batches
 };
 
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk, int& b) {
+  const int per_batch = num_m * num_n;
+  b = tile / per_batch;
+  tile -= b * per_batch;
   const int per_band = num_m * GROUP_N;
   const int band = tile / per_band;
   const int within = tile - band * per_band;
@@ -105,7 +110,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.num_m * p.num_n;
+  const int total_tiles = p.num_m * p.num_n * p.batch;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -133,13 +138,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int m_blk, n_blk;
-        tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk);
+        int m_blk, n_blk, bz;
+        tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk, bz);
         for (int kb = 0; kb < p.num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
           mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          tma_load_2d(&tmA, &full_bar[stage], sA + stage * C::A_BYTES, kb * BK, m_blk * BM);
-          tma_load_2d(&tmB, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK, n_blk * BN);
+          tma_load_3d(&tmA, &full_bar[stage], sA + stage * C::A_BYTES, kb * BK, m_blk * BM, bz);
+          tma_load_3d(&tmB, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK, n_blk * BN, bz);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -189,11 +194,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     const int co_r = lane >> 2, co_j = lane & 3;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int m_blk, n_blk;
-      tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk);
+      int m_blk, n_blk, bz;
+      tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk, bz);
       mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
       tc_fence_after();
       const int m_base = m_blk * BM + q * 32;
+      const float* bias_b = p.bias ? p.bias + (size_t)bz * p.bias_bstride : nullptr;
+      const __nv_bfloat16* res_b = p.residual ? p.residual + (size_t)bz * p.r_bstride : nullptr;
       // rows this lane touches in the cooperative phases: m_base + 8*i + co_r
       size_t co_out[4], co_res[4];
       bool co_ok[4];
@@ -209,7 +216,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         } else if (p.row_mode == VZ_ROWS_RES_MOD) {
           res_row = m % p.rows_per;
         }
-        co_out[i] = (size_t)out_row * p.ldo + co_j * 8;
+        co_out[i] = (size_t)bz * p.o_bstride + (size_t)out_row * p.ldo;
         co_res[i] = (size_t)res_row * p.ldr + co_j * 8;
       }
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -219,12 +226,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c * 32, r);
-        if (p.residual) {
+        if (res_b) {
           // coalesced residual chunk -> staging tile (overlaps the TMEM load)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 w = make_uint4(0, 0, 0, 0);
-            if (co_ok[i]) w = *reinterpret_cast<const uint4*>(p.residual + co_res[i] + col0);
+            if (co_ok[i]) w = *reinterpret_cast<const uint4*>(res_b + co_res[i] + col0);
             const int rr = 8 * i + co_r;
             *reinterpret_cast<uint4*>(stg + rr * 64 + ((co_j ^ ((rr >> 1) & 3)) << 4)) = w;
           }
@@ -233,8 +240,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (p.bias) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+        if (bias_b) {
+          const float4* b4 = reinterpret_cast<const float4*>(bias_b + col0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 b = __ldg(b4 + i);
@@ -245,7 +252,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], p.act);
         }
-        if (p.residual) {
+        if (p.out_f32) {
+          // fp32 output (attention scores): 128 B per row, 8 chunks swizzled by row & 7; stores cover
+          // 4 rows x 128 B per instruction
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(stg + lane * 128 + (((uint32_t)i ^ (uint32_t)(lane & 7)) << 4)) =
+                make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          __syncwarp();
+          float* outf = reinterpret_cast<float*>(p.out);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3), jj = lane & 7;
+            const int m = m_base + rr;
+            const float4 w = *reinterpret_cast<const float4*>(stg + rr * 128 + ((jj ^ (rr & 7)) << 4));
+            if (m < p.M)
+              *reinterpret_cast<float4*>(outf + (size_t)bz * p.o_bstride + (size_t)m * p.ldo + col0 + jj * 4) = w;
+          }
+          __syncwarp();
+          continue;
+        }
+        if (res_b) {
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -270,7 +297,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         for (int i = 0; i < 4; ++i) {
           const int rr = 8 * i + co_r;
           const uint4 w = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((co_j ^ ((rr >> 1) & 3)) << 4));
-          if (co_ok[i]) *reinterpret_cast<uint4*>(p.out + co_out[i] + col0) = w;
+          if (co_ok[i]) *reinterpret_cast<uint4*>(p.out + co_out[i] + co_j * 8 + col0) = w;
         }
         __syncwarp();  // staging tile is reused by the next chunk
       }
@@ -346,15 +373,17 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map: inner dim = K (contiguous), outer dim = rows; box = {64, box_rows}.
-int make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows) {
+// 3-D bf16 tensor map: dim0 = K (contiguous), dim1 = rows, dim2 = batch; box = {64, box_rows, 1}.
+int make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows, int batch,
+              long long bstride) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return VZ_ERR_CUDA;
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+  if (batch <= 1) { batch = 1; bstride = (long long)rows * ld; }
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)bstride * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -368,16 +397,16 @@ template <int BN>
 int launch_tc(const vz_gemm_args& a, const GemmDev& p, int num_sms, cudaStream_t st) {
   using C = Cfg<BN>;
   CUtensorMap tmA, tmB;
-  VZ_TRY(make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM));
-  VZ_TRY(make_tmap(&tmB, a.W, a.N, a.K, a.ldw, BN));
+  VZ_TRY(make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM, a.batch, a.a_bstride));
+  VZ_TRY(make_tmap(&tmB, a.W, a.N, a.K, a.ldw, BN, a.batch, a.w_bstride));
   static bool attr_done = false;  // idempotent attribute; benign race
   if (!attr_done) {
     VZ_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_done = true;
   }
-  const int tiles = p.num_m * p.num_n;
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  const long tiles = (long)p.num_m * p.num_n * p.batch;
+  const int grid = tiles < num_sms ? (int)tiles : num_sms;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof.on) {
     std::lock_guard<std::mutex> lk(g_prof.mu);
@@ -390,7 +419,7 @@ int launch_tc(const vz_gemm_args& a, const GemmDev& p, int num_sms, cudaStream_t
     }
     e0 = g_prof.pool[g_prof.used++];
     e1 = g_prof.pool[g_prof.used++];
-    g_prof.flops.push_back(2.0 * a.M * (double)a.N * a.K);
+    g_prof.flops.push_back(2.0 * a.M * (double)a.N * a.K * p.batch);
     VZ_CUDA_CHECK(cudaEventRecord(e0, st));
   }
   gemm_bf16_tcgen05_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, st>>>(tmA, tmB, p);
@@ -410,6 +439,12 @@ int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
     return VZ_ERR_BAD_ARG;
   if (a.N % 32 != 0 || a.K % 8 != 0) return VZ_ERR_UNSUPPORTED;
   if (a.row_mode != VZ_ROWS_PLAIN && a.rows_per <= 0) return VZ_ERR_BAD_ARG;
+  const int batch = a.batch > 1 ? a.batch : 1;
+  if (batch > 1 && ((a.a_bstride & 7) || (a.w_bstride & 7) || (a.o_bstride & 7) || (a.r_bstride & 7) ||
+                    (a.bias_bstride & 3) || a.a_bstride <= 0 || a.w_bstride <= 0))
+    return VZ_ERR_BAD_ARG;
+  if (a.out_f32 && (a.residual || a.row_mode != VZ_ROWS_PLAIN || (a.ldo & 3))) return VZ_ERR_UNSUPPORTED;
+  if ((batch > 1 || a.out_f32) && a.force_simple) return VZ_ERR_UNSUPPORTED;
 
   GemmDev p;
   p.out = reinterpret_cast<__nv_bfloat16*>(a.out);
@@ -418,6 +453,9 @@ int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.ldo = a.ldo; p.ldr = a.ldr;
   p.act = a.act; p.row_mode = a.row_mode; p.rows_per = a.rows_per;
+  p.batch = batch; p.out_f32 = a.out_f32;
+  p.o_bstride = batch > 1 ? a.o_bstride : 0; p.r_bstride = batch > 1 ? a.r_bstride : 0;
+  p.bias_bstride = batch > 1 ? a.bias_bstride : 0;
   p.num_m = (a.M + BM - 1) / BM;
   p.num_k = (a.K + BK - 1) / BK;
 
@@ -434,7 +472,7 @@ int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
   VZ_CUDA_CHECK(cudaGetDevice(&dev));
   VZ_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   // 128x256 tiles when they still fill the machine, otherwise 128x128 for more CTAs
-  const long tiles256 = (long)p.num_m * ((a.N + 255) / 256);
+  const long tiles256 = (long)p.num_m * ((a.N + 255) / 256) * batch;
   if (a.N % 256 == 0 && tiles256 >= num_sms) {
     p.num_n = a.N / 256;
     return launch_tc<256>(a, p, num_sms, st);

@@ -25,6 +25,21 @@ int gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, co
   g.A = A; g.W = W; g.out = out; g.bias = bias; g.residual = residual;
   g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldo = ldo; g.ldr = ldr;
   g.act = act; g.row_mode = row_mode; g.rows_per = rows_per; g.force_simple = simple;
+  g.batch = 1; g.out_f32 = 0;
+  g.a_bstride = g.w_bstride = g.o_bstride = g.r_bstride = g.bias_bstride = 0;
+  return gemm_launch(g, st);
+}
+
+// batched tcgen05 GEMM (strides in elements); fp32 output when out_f32
+int gemm_batched(const void* A, int lda, long long sa, const void* W, int ldw, long long sw, int batch, int M,
+                 int N, int K, const float* bias, long long sbias, void* out, int ldo, long long so, int out_f32,
+                 cudaStream_t st) {
+  vz_gemm_args g;
+  g.A = A; g.W = W; g.out = out; g.bias = bias; g.residual = nullptr;
+  g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldo = ldo; g.ldr = 0;
+  g.act = VZ_ACT_NONE; g.row_mode = VZ_ROWS_PLAIN; g.rows_per = 0; g.force_simple = 0;
+  g.batch = batch; g.out_f32 = out_f32;
+  g.a_bstride = sa; g.w_bstride = sw; g.o_bstride = so; g.r_bstride = 0; g.bias_bstride = sbias;
   return gemm_launch(g, st);
 }
 
@@ -51,7 +66,7 @@ VitWs vit_layout(void* base, int T) {
 }
 
 struct QfWs {
-  void *featsN, *KV, *x, *xn, *qkv, *attn, *q, *hbuf, *q0n, *qkv0, *tn, *kv_text, *attn0, *x1;
+  void *featsN, *fT, *qk, *S, *Pm, *PF, *x, *xn, *qkv, *attn, *q, *hbuf, *q0n, *qkv0, *tn, *kv_text, *attn0, *x1;
   size_t total;
 };
 
@@ -61,7 +76,12 @@ QfWs qf_layout(void* base, int T, int n_samples, int text_rows) {
   const size_t R1 = (size_t)text_rows + 1, Bs = (size_t)(n_samples > 0 ? n_samples : 1) * VZ_QF_QUERIES;
   QfWs w;
   w.featsN = b.take(P * VZ_FUSED_WIDTH * kB16);
-  w.KV = b.take(P * (size_t)(VZ_QF_BLOCKS * 2 * VZ_QF_WIDTH) * kB16);
+  const size_t HQ = (size_t)VZ_QF_HEADS * VZ_QF_QUERIES;  // 256 (query, head) rows per tile
+  w.fT = b.take(P * VZ_FUSED_WIDTH * kB16);                          // [T][5120][576]
+  w.qk = b.take((size_t)T * HQ * VZ_FUSED_WIDTH * kB16);              // [T][32][8][5120]
+  w.S = b.take((size_t)T * HQ * VZ_VIT_PATCHES * 4);                  // [T][256][576] f32
+  w.Pm = b.take((size_t)T * HQ * VZ_VIT_PATCHES * kB16);              // [T][256][576]
+  w.PF = b.take((size_t)T * HQ * VZ_FUSED_WIDTH * kB16);              // [T][256][5120]
   w.x = b.take(M * VZ_QF_WIDTH * kB16);
   w.xn = b.take(M * VZ_QF_WIDTH * kB16);
   w.qkv = b.take(M * 3 * VZ_QF_WIDTH * kB16);
@@ -142,10 +162,9 @@ extern "C" int vz_qformer_forward(const vz_qf_weights* w, const void* feats, int
   if (ws.total > workspace_bytes) return VZ_ERR_WORKSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int P = T * VZ_VIT_PATCHES, M = T * VZ_QF_QUERIES, D = VZ_QF_WIDTH, D3 = 3 * VZ_QF_WIDTH;
-  const int KVW = VZ_QF_BLOCKS * 2 * VZ_QF_WIDTH;
+  const int FW = VZ_FUSED_WIDTH, NP = VZ_VIT_PATCHES, HQ = VZ_QF_HEADS * VZ_QF_QUERIES, HD = VZ_QF_HEAD_DIM;
   const __nv_bfloat16* qkv0 = reinterpret_cast<const __nv_bfloat16*>(ws.qkv0);
   const __nv_bfloat16* qkv = reinterpret_cast<const __nv_bfloat16*>(ws.qkv);
-  const __nv_bfloat16* KV = reinterpret_cast<const __nv_bfloat16*>(ws.KV);
 
   // pre_norm (builder.py:74) unless the fusion kernel already applied it
   const void* fn = feats;
@@ -154,10 +173,11 @@ extern "C" int vz_qformer_forward(const vz_qf_weights* w, const void* feats, int
                             VZ_FUSED_WIDTH, 1e-5f, nullptr, 1, st));
     fn = ws.featsN;
   }
-  // K/V projections of all 8 cross-attention blocks in ONE GEMM (features are block-invariant,
-  // builder.py:84-90): [P,5120] x [65536,5120]^T
-  VZ_TRY(gemm(fn, VZ_FUSED_WIDTH, w->kv_w, VZ_FUSED_WIDTH, P, KVW, VZ_FUSED_WIDTH, w->kv_b, VZ_ACT_NONE,
-              nullptr, 0, ws.KV, KVW, VZ_ROWS_PLAIN, 0, simple, st));
+  // Cross-attention without materialising K and V (exact reassociation):
+  //   scores_h = (q_h Wk_h) f^T            (the k bias adds a per-query constant: softmax-invariant)
+  //   out_h    = (P_h f) Wv_h^T + bv_h     (rows of P sum to 1)
+  // f^T is shared by all 8 blocks: one transpose per forward.
+  VZ_TRY(transpose_launch(fn, ws.fT, T, NP, FW, st));
 
   // ---- block 0 self-attention: queries are tile-invariant, text K/V are per sample --------------
   const vz_qf_block& B0 = w->blocks[0];
@@ -201,9 +221,20 @@ extern "C" int vz_qformer_forward(const vz_qf_weights* w, const void* feats, int
     VZ_TRY(layernorm_launch(ws.x, D, Bk.n2_g, Bk.n2_b, ws.xn, D, M, D, 1e-5f, nullptr, 1, st));
     VZ_TRY(gemm(ws.xn, D, Bk.ca_q_w, D, M, D, D, Bk.ca_in_b, VZ_ACT_NONE, nullptr, 0, ws.q, D, VZ_ROWS_PLAIN,
                 0, simple, st));
-    VZ_TRY(qattn_launch(2, ws.q, D, VZ_QF_QUERIES, KV + (size_t)(2 * i) * D, KV + (size_t)(2 * i + 1) * D, KVW,
-                        VZ_VIT_PATCHES, VZ_VIT_PATCHES, nullptr, nullptr, KVW, nullptr, nullptr, nullptr, 0,
-                        ws.attn, D, T, st));
+    // qk[(t,q),h,:] = q[(t,q), h*512:(h+1)*512] . Wk_h            batch = heads, K = 512
+    VZ_TRY(gemm_batched(ws.q, D, HD, Bk.ca_kT_w, D, HD, VZ_QF_HEADS, M, FW, HD, nullptr, 0, ws.qk,
+                        VZ_QF_HEADS * FW, FW, 0, st));
+    // S[t] = qk[t] (256 x 5120) . f[t]^T (5120 x 576), fp32            batch = tiles
+    VZ_TRY(gemm_batched(ws.qk, FW, (long long)HQ * FW, fn, FW, (long long)NP * FW, T, HQ, NP, FW, nullptr, 0,
+                        ws.S, NP, (long long)HQ * NP, 1, st));
+    VZ_TRY(softmax_rows_launch(reinterpret_cast<const float*>(ws.S), ws.Pm, T * HQ, NP,
+                               0.044194173824159216f /* 1/sqrt(512) */, st));
+    // PF[t] = P[t] (256 x 576) . f[t] (576 x 5120)                     batch = tiles, W = f^T
+    VZ_TRY(gemm_batched(ws.Pm, NP, (long long)HQ * NP, ws.fT, NP, (long long)FW * NP, T, HQ, FW, NP, nullptr, 0,
+                        ws.PF, FW, (long long)HQ * FW, 0, st));
+    // attn[(t,q), h*512:(h+1)*512] = PF[(t,q),h,:] . Wv_h^T + bv_h     batch = heads
+    VZ_TRY(gemm_batched(ws.PF, VZ_QF_HEADS * FW, FW, Bk.ca_v_w, FW, (long long)HD * FW, VZ_QF_HEADS, M, HD, FW,
+                        Bk.ca_in_b + 2 * D, HD, ws.attn, D, HD, 0, st));
     VZ_TRY(gemm(ws.attn, D, Bk.ca_out_w, D, M, D, D, Bk.ca_out_b, VZ_ACT_NONE, ws.x, D, ws.x, D, VZ_ROWS_PLAIN,
                 0, simple, st));
     // FFN, exact (erf) GELU

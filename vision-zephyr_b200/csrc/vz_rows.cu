@@ -200,7 +200,72 @@ patchify_kernel(const void* __restrict__ pix, __nv_bfloat16* __restrict__ patche
   for (int i = threadIdx.x; i < 24 * VZ_PATCH_K * 2 / 16; i += blockDim.x) dst[i] = s4[i];
 }
 
+// in [batch][R][C] bf16 -> out [batch][C][R]; 64x64 tiles through padded shared memory.
+__global__ void __launch_bounds__(256)
+transpose_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int C) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const size_t boff = (size_t)blockIdx.z * R * C;
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+    const int r = i >> 6, c = i & 63;
+    tile[r][c] = (r0 + r < R && c0 + c < C) ? in[boff + (size_t)(r0 + r) * C + c0 + c] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+    const int c = i >> 6, r = i & 63;
+    if (r0 + r < R && c0 + c < C) out[boff + (size_t)(c0 + c) * R + r0 + r] = tile[r][c];
+  }
+}
+
+// row softmax of fp32 scores (pre-scaled by `scale`) -> bf16 probabilities; one warp per row.
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int rows, int n, float scale_log2e) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* sr = s + (size_t)row * n;
+  float v[24];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < n ? sr[c] : -INFINITY;
+    mx = fmaxf(mx, v[i]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    v[i] = exp2f((v[i] - mx) * scale_log2e);
+    sum += v[i];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  __nv_bfloat16* pr = p + (size_t)row * n;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    const int c = lane + 32 * i;
+    if (c < n) pr[c] = __float2bfloat16_rn(v[i] * inv);
+  }
+}
+
 }  // namespace
+
+int transpose_launch(const void* in, void* out, int batch, int R, int C, cudaStream_t st) {
+  dim3 grid((C + 63) / 64, (R + 63) / 64, batch);
+  transpose_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+                                         reinterpret_cast<__nv_bfloat16*>(out), R, C);
+  VZ_LAUNCH_CHECK();
+  return VZ_OK;
+}
+
+int softmax_rows_launch(const float* s, void* p, int rows, int n, float scale, cudaStream_t st) {
+  if (n > 24 * 32) return VZ_ERR_UNSUPPORTED;
+  softmax_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(s, reinterpret_cast<__nv_bfloat16*>(p), rows, n,
+                                                      scale * 1.4426950408889634f);
+  VZ_LAUNCH_CHECK();
+  return VZ_OK;
+}
 
 int layernorm_launch(const void* x, int ldx, const float* g, const float* b, void* out, int ldo,
                      int M, int D, float eps, const int32_t* row_map, int rows_per_map,

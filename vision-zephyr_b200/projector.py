@@ -5,8 +5,8 @@ Drop-in for the reference's
   vis_zephyr/model/multimodal_projector/builder.py:12-101
 The module owns parameters with EXACTLY the reference's state-dict keys (so `mm_projector.bin`
 loads by name, vis_zephyr_arch.py:95-102) but its forward is `vz_qformer_forward`
-(csrc/vz_model.cu): one stacked K/V GEMM for the 8 cross-attention blocks, fused 32-query
-attention kernels, and block-0 text conditioning without the dead rows.
+(csrc/vz_model.cu): cross-attention reassociated so K and V are never materialised (batched tcgen05
+GEMMs), fused 32-query self-attention kernels, and block-0 text conditioning without the dead rows.
 """
 from __future__ import annotations
 
@@ -131,15 +131,9 @@ class QFormerB200(nn.Module):
         P["lq"] = bf(self.learned_queries)
         P["pre_g"], P["pre_b"] = f32(self.pre_norm.weight), f32(self.pre_norm.bias)
         P["norm_g"], P["norm_b"] = f32(self.norm.weight), f32(self.norm.bias)
-        # stacked K/V projection [8*(4096+4096), 5120] and its bias slices
-        kv_w = torch.empty((BLOCKS * 2 * WIDTH, KV_WIDTH), dtype=torch.bfloat16, device=dev)
-        kv_b = torch.empty((BLOCKS * 2 * WIDTH,), dtype=torch.float32, device=dev)
         w = _lib.QfWeights()
         for i, blk in enumerate(self.blocks):
             ca, sa = blk.cross_attn, blk.self_attn
-            kv_w[(2 * i) * WIDTH:(2 * i + 1) * WIDTH] = ca.k_proj_weight.detach()
-            kv_w[(2 * i + 1) * WIDTH:(2 * i + 2) * WIDTH] = ca.v_proj_weight.detach()
-            kv_b[(2 * i) * WIDTH:(2 * i + 2) * WIDTH] = ca.in_proj_bias.detach()[WIDTH:].float()
             ent = {
                 "n1_g": f32(blk.norm1.weight), "n1_b": f32(blk.norm1.bias),
                 "n2_g": f32(blk.norm2.weight), "n2_b": f32(blk.norm2.bias),
@@ -147,6 +141,8 @@ class QFormerB200(nn.Module):
                 "sa_in_w": bf(sa.in_proj_weight), "sa_in_b": f32(sa.in_proj_bias),
                 "sa_out_w": bf(sa.out_proj.weight), "sa_out_b": f32(sa.out_proj.bias),
                 "ca_q_w": bf(ca.q_proj_weight), "ca_in_b": f32(ca.in_proj_bias),
+                # K is never materialised: scores = (q Wk) f^T needs Wk^T with the head dim contiguous
+                "ca_kT_w": bf(ca.k_proj_weight).t().contiguous(), "ca_v_w": bf(ca.v_proj_weight),
                 "ca_out_w": bf(ca.out_proj.weight), "ca_out_b": f32(ca.out_proj.bias),
                 "ffn1_w": bf(blk.ffn["0"].weight), "ffn1_b": f32(blk.ffn["0"].bias),
                 "ffn2_w": bf(blk.ffn["2"].weight), "ffn2_b": f32(blk.ffn["2"].bias),
@@ -154,11 +150,9 @@ class QFormerB200(nn.Module):
             for name, t in ent.items():
                 P[f"{i}.{name}"] = t
                 setattr(w.blocks[i], name, t.data_ptr())
-        P["kv_w"], P["kv_b"] = kv_w, kv_b
         w.learned_queries = P["lq"].data_ptr()
         w.pre_g, w.pre_b = P["pre_g"].data_ptr(), P["pre_b"].data_ptr()
         w.norm_g, w.norm_b = P["norm_g"].data_ptr(), P["norm_b"].data_ptr()
-        w.kv_w, w.kv_b = kv_w.data_ptr(), kv_b.data_ptr()
         self._packed, self._w, self._packed_key = P, w, key
 
     def pre_norm_params(self):
