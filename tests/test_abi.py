@@ -30,7 +30,7 @@ def test_status_strings_and_version():
     assert lib.vz_status_string(0) == b"ok"
     assert b"workspace" in lib.vz_status_string(-5)
     assert lib.vz_vit_workspace_bytes(1) > 577 * 1024 * 2 * 25
-    assert lib.vz_qformer_workspace_bytes(1, 1, 63) > 576 * 65536 * 2
+    assert lib.vz_qformer_workspace_bytes(1, 1, 63) > 3 * 576 * 5120 * 2
 
 
 def test_bad_arguments_are_rejected_without_a_gpu():

@@ -78,6 +78,6 @@ def test_qformer_matches_oracle(vision_path, seeded_weights):
         cos = torch.nn.functional.cosine_similarity(got, ref, dim=-1)
         err = (got - ref).abs().max().item()
         print(f"qformer {name}: min cos {cos.min().item():.6f} max_abs {err:.4g}")
-        assert cos.min() > 0.999 and err < 0.1, name
+        assert cos.min() > 0.999 and err < 0.15, name   # stated tolerance, see tests/test_gpu_e2e.py
     # text conditioning must matter, otherwise the test above proves nothing
     assert (ref_t - ref_nt).abs().max() > 1e-3
