@@ -184,6 +184,10 @@ typedef struct {
 
 size_t vz_vit_workspace_bytes(int T);
 
+/* CLIP self-attention alone (HF CLIPAttention): qkv bf16 [T*577, 3072] (q | k | v, 16 heads x 64)
+ * -> out bf16 [T*577, 1024].  impl: 1 = tcgen05/TMEM kernel, 0 = legacy mma.sync kernel, -1 = default. */
+int vz_vit_attention(const void* qkv, void* out, int T, int impl, void* stream);
+
 /* patches: bf16 [T*576,592].  fused_out: bf16 [T*576,5120] =
  * cat(mean(h4..h8), mean(h9..h13), mean(h14..h18), mean(h19..h23), h24)[:,1:].
  * If norm_g/norm_b are non-NULL the QFormer.pre_norm LayerNorm(5120)

@@ -81,3 +81,25 @@ def test_qformer_matches_oracle(vision_path, seeded_weights):
         assert cos.min() > 0.999 and err < 0.15, name   # stated tolerance, see tests/test_gpu_e2e.py
     # text conditioning must matter, otherwise the test above proves nothing
     assert (ref_t - ref_nt).abs().max() > 1e-3
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+def test_vit_attention_kernels_match_torch(impl):
+    """both attention kernels (tcgen05 = 1, legacy mma.sync = 0) against fp32 torch attention."""
+    import vision_zephyr_b200  # noqa: F401
+    from vision_zephyr_b200 import _lib as L
+    lib = L.load()
+    T = 3
+    qkv = _rand((T * 577, 3072), 1.0, 31)
+    qkv[:, :2048] *= 1.7          # sharper softmax
+    out = torch.full((T * 577, 1024), float("nan"), dtype=torch.bfloat16, device="cuda")
+    L.check(lib.vz_vit_attention(L.ptr(qkv), L.ptr(out), T, impl, L.stream_ptr()), "vit attention")
+    torch.cuda.synchronize()
+    q, k, v = (qkv.float().view(T, 577, 3, 16, 64)[:, :, i].transpose(1, 2) for i in range(3))
+    ref = torch.softmax((q @ k.transpose(-1, -2)) * 0.125, dim=-1) @ v
+    ref = ref.transpose(1, 2).reshape(T * 577, 1024)
+    err = (out.float() - ref).abs().max().item()
+    cos = torch.nn.functional.cosine_similarity(out.float(), ref, dim=-1).min().item()
+    print(f"vit attention impl={impl}: max_abs_err {err:.4g} (ref max {ref.abs().max().item():.3g}) min row cos {cos:.6f}")
+    assert torch.isfinite(out.float()).all()
+    assert err < 0.03 and cos > 0.9995

@@ -97,6 +97,7 @@ SYMBOLS = {
     "vz_preprocess": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp]),
     "vz_patchify": (_i, [_vp, _i, _i, _vp, _vp]),
     "vz_vit_workspace_bytes": (_sz, [_i]),
+    "vz_vit_attention": (_i, [_vp, _vp, _i, _i, _vp]),
     "vz_vit_forward": (_i, [C.POINTER(VitWeights), _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "vz_qformer_workspace_bytes": (_sz, [_i, _i, _i]),
     "vz_qformer_forward": (_i, [C.POINTER(QfWeights), _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i,

@@ -1,0 +1,254 @@
+// vz_attn_tc.cu -- CLIP ViT self-attention (577 tokens, 16 heads x 64, non-causal) on the 5th-gen
+// tensor cores: S = Q K^T and O = P V are tcgen05.mma instructions with both accumulators in TMEM;
+// Q / K / V tiles arrive by TMA (128-byte swizzle) straight from the packed qkv activation.
+// Replaces HF CLIPAttention as called from vision_encoder/vision_encoder.py:101-105.
+//
+// One CTA = 128 query rows of one (tile, head); two CTAs are resident per SM so one CTA's softmax
+// overlaps the other's MMAs.  Warps 0-3: softmax (thread = query row = TMEM lane); warp 4: one thread
+// issues TMA and MMA.  Two passes over the 5 key blocks (keys padded 577 -> 640 and masked):
+//   pass 1: S_j = Q K_j^T -> running row maximum                       (no exponentials)
+//   pass 2: S_j again -> P_j = exp2((S_j - max) * scale) as bf16 in swizzled smem -> O += P_j V_j
+// With the final maximum known up front, O never needs rescaling, so the accumulator stays in TMEM
+// untouched until the epilogue divides by the row sum.
+#include "vz_common.cuh"
+
+namespace vz {
+namespace {
+
+constexpr int TOK = VZ_VIT_TOKENS;       // 577
+constexpr int HD = 64;                   // head dim
+constexpr int BQ = 128, BKV = 128;       // query rows per CTA, keys per block
+constexpr int NKB = (TOK + BKV - 1) / BKV;  // 5 key blocks
+constexpr int TILE_BYTES = 128 * 128;    // 128 rows x 64 bf16
+constexpr int SMEM_Q = 0, SMEM_P = TILE_BYTES, SMEM_RING = 3 * TILE_BYTES;   // P = 2 tiles
+constexpr int RING_STAGES = 2;
+constexpr int SMEM_BARS = SMEM_RING + RING_STAGES * 2 * TILE_BYTES;
+constexpr int SMEM_TOTAL = SMEM_BARS + 128;
+constexpr int THREADS = 160;
+constexpr uint32_t TMEM_COLS = 256;      // S: columns 0..127, O: columns 128..191
+constexpr float kLog2e = 1.4426950408889634f;
+
+__global__ void __launch_bounds__(THREADS, 2)
+vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, float scale) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem + SMEM_Q;
+  uint8_t* sP = smem + SMEM_P;
+  uint8_t* sRing = smem + SMEM_RING;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BARS);
+  uint64_t* bar_q = bars;             // Q landed
+  uint64_t* bar_full = bars + 1;      // [2] ring slot filled (TMA)
+  uint64_t* bar_empty = bars + 3;     // [2] ring slot consumed (tcgen05.commit)
+  uint64_t* bar_s_full = bars + 5;    // S ready in TMEM
+  uint64_t* bar_s_free = bars + 6;    // S copied to registers (4 warp arrivals)
+  uint64_t* bar_p_full = bars + 7;    // P written to smem (4 warp arrivals)
+  uint64_t* bar_pv_done = bars + 8;   // P V retired: P buffer reusable
+  uint64_t* bar_o_full = bars + 9;    // all MMAs retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int qb = blockIdx.x, h = blockIdx.y, t = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_base = t * TOK;  // first qkv row of this tile
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // the swizzled layouts need a 1024-byte aligned base
+  if (threadIdx.x == 0) {
+    mbar_init(bar_q, 1);
+    for (int i = 0; i < RING_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+    mbar_init(bar_s_full, 1);
+    mbar_init(bar_s_free, 4);
+    mbar_init(bar_p_full, 4);
+    mbar_init(bar_pv_done, 1);
+    mbar_init(bar_o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+
+  if (warp == 4) {
+    // ======================= control thread: TMA + MMA issue =======================
+    if (lane == 0) {
+      tma_prefetch_desc(&tm);
+      const int qcol = h * HD, kcol = VZ_VIT_WIDTH + h * HD, vcol = 2 * VZ_VIT_WIDTH + h * HD;
+      mbar_arrive_expect_tx(bar_q, TILE_BYTES);
+      tma_load_2d(&tm, bar_q, sQ, qcol, row_base + qb * BQ);
+      constexpr uint32_t idesc_qk = umma_idesc_bf16_ex(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16_ex(BQ, HD, 0, 1);   // B = V is MN-major (dims contiguous)
+      uint32_t stage = 0, phase = 0;       // ring consumer/producer position (loads and uses are in lock step)
+      uint32_t s_free_phase = 0, p_full_phase = 0;
+      int loads_issued = 0;
+      auto issue_load = [&](int n) {       // n-th load of the kernel: n < NKB -> pass 1 (K only)
+        const uint32_t st = n % RING_STAGES, ph = (n / RING_STAGES) & 1;
+        mbar_wait(&bar_empty[st], ph ^ 1, 500 + st);
+        const int j = n % NKB;
+        uint8_t* dK = sRing + st * 2 * TILE_BYTES;
+        if (n < NKB) {
+          mbar_arrive_expect_tx(&bar_full[st], TILE_BYTES);
+          tma_load_2d(&tm, &bar_full[st], dK, kcol, row_base + j * BKV);
+        } else {
+          mbar_arrive_expect_tx(&bar_full[st], 2 * TILE_BYTES);
+          tma_load_2d(&tm, &bar_full[st], dK, kcol, row_base + j * BKV);
+          tma_load_2d(&tm, &bar_full[st], dK + TILE_BYTES, vcol, row_base + j * BKV);
+        }
+      };
+      issue_load(0);
+      issue_load(1);
+      loads_issued = 2;
+      mbar_wait(bar_q, 0, 510);
+      const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(sQ));
+      for (int n = 0; n < 2 * NKB; ++n) {
+        const bool pass2 = n >= NKB;
+        uint8_t* dK = sRing + stage * 2 * TILE_BYTES;
+        mbar_wait(&bar_full[stage], phase, 520 + stage);
+        if (n > 0) {  // softmax warps must have copied the previous S out of TMEM
+          mbar_wait(bar_s_free, s_free_phase, 530);
+          s_free_phase ^= 1;
+        }
+        tc_fence_after();
+        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(dK));
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(tmem_s, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(bar_s_full);
+        if (!pass2) {
+          umma_commit(&bar_empty[stage]);      // K_j no longer needed once S_j is done
+        } else {
+          mbar_wait(bar_p_full, p_full_phase, 540);
+          p_full_phase ^= 1;
+          tc_fence_after();
+          const uint32_t p_addr = smem_u32(sP), v_addr = smem_u32(dK + TILE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BKV / 16; ++kk) {
+            const uint64_t a_desc = umma_smem_desc_sw128(p_addr + (kk >> 2) * TILE_BYTES + (kk & 3) * 32);
+            const uint64_t b_desc = umma_smem_desc_sw128(v_addr + kk * 2048);  // 16 keys = 2 x (8 rows x 128 B)
+            umma_bf16(tmem_o, a_desc, b_desc, idesc_pv, (n > NKB || kk != 0) ? 1u : 0u);
+          }
+          umma_commit(bar_pv_done);
+          umma_commit(&bar_empty[stage]);
+        }
+        if (loads_issued < 2 * NKB) { issue_load(loads_issued); ++loads_issued; }
+        if (++stage == RING_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(bar_o_full);
+    }
+  } else {
+    // ======================= softmax warps: thread = query row =======================
+    const int r = warp * 32 + lane;                      // row inside the CTA's 128-query block
+    const uint32_t t_lane = ((uint32_t)(warp * 32)) << 16;
+    const float sl2 = scale * kLog2e;
+    float m = -INFINITY;
+    uint32_t s_full_phase = 0, pv_phase = 0;
+    // ---- pass 1: row maximum ----
+    for (int j = 0; j < NKB; ++j) {
+      mbar_wait(bar_s_full, s_full_phase, 600);
+      s_full_phase ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_s + t_lane + c * 32, v);
+        tmem_ld_wait();
+        const int key0 = j * BKV + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (key0 + i < TOK) m = fmaxf(m, __uint_as_float(v[i]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_s_free);
+    }
+    // ---- pass 2: probabilities + row sum ----
+    float l = 0.f;
+    const float m_sl2 = m * sl2;
+    for (int j = 0; j < NKB; ++j) {
+      mbar_wait(bar_s_full, s_full_phase, 610);
+      s_full_phase ^= 1;
+      tc_fence_after();
+      uint32_t pk[64];  // 128 probabilities as packed bf16 pairs
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_s + t_lane + c * 32, v);
+        tmem_ld_wait();
+        const int key0 = j * BKV + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = exp2f(fmaf(__uint_as_float(v[i]), sl2, -m_sl2));
+          float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), sl2, -m_sl2));
+          if (key0 + i >= TOK) p0 = 0.f;
+          if (key0 + i + 1 >= TOK) p1 = 0.f;
+          // sum what the tensor core will actually see (bf16-rounded), like a bf16 softmax output
+          const __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
+          l += __bfloat162float(b.x) + __bfloat162float(b.y);
+          pk[c * 16 + (i >> 1)] = *reinterpret_cast<const uint32_t*>(&b);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_s_free);
+      if (j > 0) {  // previous P V must have retired before P is overwritten
+        mbar_wait(bar_pv_done, pv_phase, 620);
+        pv_phase ^= 1;
+      }
+      // P[r][key] in the K-major 128B-swizzled UMMA layout: two 64-key atoms of 128 rows x 128 B
+#pragma unroll
+      for (int ch = 0; ch < 16; ++ch) {
+        const int atom = ch >> 3, c = ch & 7;
+        uint4 w = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+        *reinterpret_cast<uint4*>(sP + atom * TILE_BYTES + r * 128 + ((c ^ (r & 7)) << 4)) = w;
+      }
+      fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p_full);
+    }
+    // ---- epilogue: O / l ----
+    mbar_wait(bar_o_full, 0, 630);
+    tc_fence_after();
+    const int qrow = qb * BQ + r;
+    const float inv = 1.0f / l;
+    __nv_bfloat16* orow = out + (size_t)(row_base + qrow) * VZ_VIT_WIDTH + h * HD;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_o + t_lane + c * 32, v);
+      tmem_ld_wait();
+      if (qrow < TOK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+int vit_attn_tc_launch(const void* qkv, void* out, int T, cudaStream_t st) {
+  CUtensorMap tm;
+  VZ_TRY(encode_tmap_2d_bf16(&tm, qkv, (long long)T * TOK, 3 * VZ_VIT_WIDTH, 3 * VZ_VIT_WIDTH, HD, 128));
+  static bool attr_done = false;
+  if (!attr_done) {
+    VZ_CUDA_CHECK(cudaFuncSetAttribute(vit_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    attr_done = true;
+  }
+  dim3 grid((TOK + BQ - 1) / BQ, VZ_VIT_HEADS, T);
+  vit_attn_tc_kernel<<<grid, THREADS, SMEM_TOTAL, st>>>(tm, reinterpret_cast<__nv_bfloat16*>(out), 0.125f);
+  VZ_LAUNCH_CHECK();
+  return VZ_OK;
+}
+
+}  // namespace vz

@@ -53,6 +53,8 @@ int gather_rows_launch(const void* in, void* out, int M, int row_bytes, const in
 int transpose_launch(const void* in, void* out, int batch, int R, int C, cudaStream_t st);
 int softmax_rows_launch(const float* s, void* p, int rows, int n, float scale, cudaStream_t st);
 int vit_attn_launch(const void* qkv, void* out, int T, cudaStream_t st);
+int vit_attn_tc_launch(const void* qkv, void* out, int T, cudaStream_t st);
+int encode_tmap_2d_bf16(CUtensorMap* tm, const void* base, long long rows, int cols, int ld, int box_cols, int box_rows);
 int qattn_launch(int mode, const void* q, int q_rs, int q_zrows, const void* k0, const void* v0,
                  int rs0, int zrows0, int count0, const void* k1, const void* v1, int rs1,
                  const int32_t* off1, const void* kpad, const void* vpad, int L, void* out, int ldo,
@@ -226,6 +228,23 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
+}
+
+// general form: a_mn / b_mn = 1 selects an MN-major (transposed) operand
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_ex(int M, int N, int a_mn, int b_mn) {
+  return umma_idesc_bf16(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
 }
 
 // ---- small math / packing ---------------------------------------------------------------

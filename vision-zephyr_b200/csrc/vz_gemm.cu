@@ -430,6 +430,25 @@ int launch_tc(const vz_gemm_args& a, const GemmDev& p, int num_sms, cudaStream_t
 
 }  // namespace
 
+// 2-D bf16 tensor map with 128-byte swizzle (box_cols * 2 must be 128 bytes); used by the attention kernel
+int encode_tmap_2d_bf16(CUtensorMap* tm, const void* base, long long rows, int cols, int ld, int box_cols,
+                        int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return VZ_ERR_CUDA;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_last_cuda_error = 100000 + (int)r;
+    return VZ_ERR_CUDA;
+  }
+  return VZ_OK;
+}
+
 int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
   if (!a.A || !a.W || !a.out) return VZ_ERR_BAD_ARG;
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return VZ_ERR_BAD_ARG;

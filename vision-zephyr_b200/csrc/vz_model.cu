@@ -4,6 +4,10 @@
 // Everything is enqueued on the caller's stream; no allocation, no synchronisation.
 #include "vz_common.cuh"
 
+#include <stdlib.h>
+
+extern "C" int vz_vit_attention(const void* qkv, void* out, int T, int impl, void* stream);
+
 namespace vz {
 namespace {
 
@@ -103,6 +107,19 @@ QfWs qf_layout(void* base, int T, int n_samples, int text_rows) {
 
 using namespace vz;
 
+// impl: 1 = tcgen05 kernel, 0 = legacy mma.sync kernel, -1 = default (tcgen05 unless the
+// environment variable VZ_VIT_ATTN_LEGACY=1 is set; bring-up switch only)
+extern "C" int vz_vit_attention(const void* qkv, void* out, int T, int impl, void* stream) {
+  if (!qkv || !out || T <= 0) return VZ_ERR_BAD_ARG;
+  if (!aligned16(qkv) || !aligned16(out)) return VZ_ERR_BAD_ARG;
+  if (impl < 0) {
+    static const int legacy = []() { const char* e = getenv("VZ_VIT_ATTN_LEGACY"); return (e && e[0] == '1') ? 1 : 0; }();
+    impl = legacy ? 0 : 1;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return impl ? vit_attn_tc_launch(qkv, out, T, st) : vit_attn_launch(qkv, out, T, st);
+}
+
 extern "C" size_t vz_vit_workspace_bytes(int T) { return T > 0 ? vit_layout(nullptr, T).total : 0; }
 
 extern "C" size_t vz_qformer_workspace_bytes(int T, int n_samples, int text_rows) {
@@ -132,7 +149,7 @@ extern "C" int vz_vit_forward(const vz_vit_weights* w, const void* patches, int 
     VZ_TRY(layernorm_launch(x, D, L.ln1_g, L.ln1_b, ws.xn, D, M, D, 1e-5f, nullptr, 1, st));
     VZ_TRY(gemm(ws.xn, D, L.w_qkv, D, M, 3 * D, D, L.b_qkv, VZ_ACT_NONE, nullptr, 0, ws.qkv, 3 * D,
                 VZ_ROWS_PLAIN, 0, simple, st));
-    VZ_TRY(vit_attn_launch(ws.qkv, ws.attn, T, st));
+    VZ_TRY(vz_vit_attention(ws.qkv, ws.attn, T, -1, st));
     VZ_TRY(gemm(ws.attn, D, L.w_o, D, M, D, D, L.b_o, VZ_ACT_NONE, x, D, ws.mid, D, VZ_ROWS_PLAIN, 0,
                 simple, st));
     VZ_TRY(layernorm_launch(ws.mid, D, L.ln2_g, L.ln2_b, ws.xn, D, M, D, 1e-5f, nullptr, 1, st));
