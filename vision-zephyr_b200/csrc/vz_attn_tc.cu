@@ -5,11 +5,12 @@
 //
 // One CTA = 128 query rows of one (tile, head); two CTAs are resident per SM so one CTA's softmax
 // overlaps the other's MMAs.  Warps 0-3: softmax (thread = query row = TMEM lane); warp 4: one thread
-// issues TMA and MMA.  Two passes over the 5 key blocks (keys padded 577 -> 640 and masked):
-//   pass 1: S_j = Q K_j^T -> running row maximum                       (no exponentials)
-//   pass 2: S_j again -> P_j = exp2((S_j - max) * scale) as bf16 in swizzled smem -> O += P_j V_j
-// With the final maximum known up front, O never needs rescaling, so the accumulator stays in TMEM
-// untouched until the epilogue divides by the row sum.
+// issues TMA and MMA.  One pass over the 5 key blocks (keys padded 577 -> 640 and masked):
+//   S_j = Q K_j^T -> registers -> P_j = exp2((S_j - m) * scale) as bf16 in swizzled smem -> O += P_j V_j
+// with an online softmax whose accumulator rescale is LAZY: O (in TMEM) is only multiplied by
+// exp2(m_old - m_new) when the running maximum grew by more than 2^8, which is rare after the first
+// block, so O normally stays untouched in TMEM until the epilogue divides by the row sum.
+// Q K_{j+1}^T is issued as soon as S_j sits in registers, so it overlaps the exponentials of block j.
 #include "vz_common.cuh"
 
 namespace vz {
@@ -28,6 +29,18 @@ constexpr int THREADS = 160;
 constexpr uint32_t TMEM_COLS = 256;      // S: columns 0..127, O: columns 128..191
 constexpr float kLog2e = 1.4426950408889634f;
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// exp2 may run up to 2^8 above the value it would have with the exact running maximum before the
+// accumulator is rescaled (FA-4 style lazy rescaling): keeps O untouched in TMEM most of the time.
+constexpr float kRescaleLog2 = 8.0f;
+
 __global__ void __launch_bounds__(THREADS, 2)
 vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, float scale) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -40,8 +53,8 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __rest
   uint64_t* bar_empty = bars + 3;     // [2] ring slot consumed (tcgen05.commit)
   uint64_t* bar_s_full = bars + 5;    // S ready in TMEM
   uint64_t* bar_s_free = bars + 6;    // S copied to registers (4 warp arrivals)
-  uint64_t* bar_p_full = bars + 7;    // P written to smem (4 warp arrivals)
-  uint64_t* bar_pv_done = bars + 8;   // P V retired: P buffer reusable
+  uint64_t* bar_p_full = bars + 7;    // P written to smem, O rescaled if needed (4 warp arrivals)
+  uint64_t* bar_pv_done = bars + 8;   // P V retired: P buffer and O reusable
   uint64_t* bar_o_full = bars + 9;    // all MMAs retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
@@ -76,61 +89,48 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __rest
       tma_load_2d(&tm, bar_q, sQ, qcol, row_base + qb * BQ);
       constexpr uint32_t idesc_qk = umma_idesc_bf16_ex(BQ, BKV, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16_ex(BQ, HD, 0, 1);   // B = V is MN-major (dims contiguous)
-      uint32_t stage = 0, phase = 0;       // ring consumer/producer position (loads and uses are in lock step)
-      uint32_t s_free_phase = 0, p_full_phase = 0;
-      int loads_issued = 0;
-      auto issue_load = [&](int n) {       // n-th load of the kernel: n < NKB -> pass 1 (K only)
-        const uint32_t st = n % RING_STAGES, ph = (n / RING_STAGES) & 1;
+      auto issue_load = [&](int j) {       // K_j and V_j into ring slot j % 2
+        const uint32_t st = j % RING_STAGES, ph = (j / RING_STAGES) & 1;
         mbar_wait(&bar_empty[st], ph ^ 1, 500 + st);
-        const int j = n % NKB;
         uint8_t* dK = sRing + st * 2 * TILE_BYTES;
-        if (n < NKB) {
-          mbar_arrive_expect_tx(&bar_full[st], TILE_BYTES);
-          tma_load_2d(&tm, &bar_full[st], dK, kcol, row_base + j * BKV);
-        } else {
-          mbar_arrive_expect_tx(&bar_full[st], 2 * TILE_BYTES);
-          tma_load_2d(&tm, &bar_full[st], dK, kcol, row_base + j * BKV);
-          tma_load_2d(&tm, &bar_full[st], dK + TILE_BYTES, vcol, row_base + j * BKV);
+        mbar_arrive_expect_tx(&bar_full[st], 2 * TILE_BYTES);
+        tma_load_2d(&tm, &bar_full[st], dK, kcol, row_base + j * BKV);
+        tma_load_2d(&tm, &bar_full[st], dK + TILE_BYTES, vcol, row_base + j * BKV);
+      };
+      auto issue_pv = [&](int j) {         // O (+)= P_j V_j, then release P, O and the ring slot
+        const uint32_t st = j % RING_STAGES;
+        mbar_wait(bar_p_full, j & 1, 540);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(sP), v_addr = smem_u32(sRing + st * 2 * TILE_BYTES + TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          const uint64_t a_desc = umma_smem_desc_sw128(p_addr + (kk >> 2) * TILE_BYTES + (kk & 3) * 32);
+          const uint64_t b_desc = umma_smem_desc_sw128(v_addr + kk * 2048);  // 16 keys = 2 x (8 rows x 128 B)
+          umma_bf16(tmem_o, a_desc, b_desc, idesc_pv, (j > 0 || kk != 0) ? 1u : 0u);
         }
+        umma_commit(bar_pv_done);
+        umma_commit(&bar_empty[st]);
       };
       issue_load(0);
       issue_load(1);
-      loads_issued = 2;
       mbar_wait(bar_q, 0, 510);
       const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(sQ));
-      for (int n = 0; n < 2 * NKB; ++n) {
-        const bool pass2 = n >= NKB;
-        uint8_t* dK = sRing + stage * 2 * TILE_BYTES;
-        mbar_wait(&bar_full[stage], phase, 520 + stage);
-        if (n > 0) {  // softmax warps must have copied the previous S out of TMEM
-          mbar_wait(bar_s_free, s_free_phase, 530);
-          s_free_phase ^= 1;
-        }
+      for (int j = 0; j < NKB; ++j) {
+        const uint32_t st = j % RING_STAGES, ph = (j / RING_STAGES) & 1;
+        mbar_wait(&bar_full[st], ph, 520 + st);
+        if (j > 0) mbar_wait(bar_s_free, (j - 1) & 1, 530);  // S_{j-1} is in the softmax registers
         tc_fence_after();
-        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(dK));
+        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(sRing + st * 2 * TILE_BYTES));
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
           umma_bf16(tmem_s, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_qk, k != 0 ? 1u : 0u);
         umma_commit(bar_s_full);
-        if (!pass2) {
-          umma_commit(&bar_empty[stage]);      // K_j no longer needed once S_j is done
-        } else {
-          mbar_wait(bar_p_full, p_full_phase, 540);
-          p_full_phase ^= 1;
-          tc_fence_after();
-          const uint32_t p_addr = smem_u32(sP), v_addr = smem_u32(dK + TILE_BYTES);
-#pragma unroll
-          for (int kk = 0; kk < BKV / 16; ++kk) {
-            const uint64_t a_desc = umma_smem_desc_sw128(p_addr + (kk >> 2) * TILE_BYTES + (kk & 3) * 32);
-            const uint64_t b_desc = umma_smem_desc_sw128(v_addr + kk * 2048);  // 16 keys = 2 x (8 rows x 128 B)
-            umma_bf16(tmem_o, a_desc, b_desc, idesc_pv, (n > NKB || kk != 0) ? 1u : 0u);
-          }
-          umma_commit(bar_pv_done);
-          umma_commit(&bar_empty[stage]);
+        if (j > 0) {
+          issue_pv(j - 1);                     // overlaps the softmax of block j
+          if (j + 1 < NKB) issue_load(j + 1);  // slot (j+1)%2 == (j-1)%2 is free once P V_{j-1} retires
         }
-        if (loads_issued < 2 * NKB) { issue_load(loads_issued); ++loads_issued; }
-        if (++stage == RING_STAGES) { stage = 0; phase ^= 1; }
       }
+      issue_pv(NKB - 1);
       umma_commit(bar_o_full);
     }
   } else {
@@ -138,59 +138,71 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __rest
     const int r = warp * 32 + lane;                      // row inside the CTA's 128-query block
     const uint32_t t_lane = ((uint32_t)(warp * 32)) << 16;
     const float sl2 = scale * kLog2e;
-    float m = -INFINITY;
-    uint32_t s_full_phase = 0, pv_phase = 0;
-    // ---- pass 1: row maximum ----
+    float m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < NKB; ++j) {
-      mbar_wait(bar_s_full, s_full_phase, 600);
-      s_full_phase ^= 1;
+      mbar_wait(bar_s_full, j & 1, 600);
       tc_fence_after();
+      uint32_t v[128];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_s + t_lane + c * 32, v);
-        tmem_ld_wait();
-        const int key0 = j * BKV + c * 32;
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (key0 + i < TOK) m = fmaxf(m, __uint_as_float(v[i]));
-      }
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tmem_s + t_lane + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_s_free);
-    }
-    // ---- pass 2: probabilities + row sum ----
-    float l = 0.f;
-    const float m_sl2 = m * sl2;
-    for (int j = 0; j < NKB; ++j) {
-      mbar_wait(bar_s_full, s_full_phase, 610);
-      s_full_phase ^= 1;
-      tc_fence_after();
-      uint32_t pk[64];  // 128 probabilities as packed bf16 pairs
+      // keys of the last block beyond the tile's 577 tokens belong to the next tile: mask them
+      // (only block NKB-1 pays for the masking; -inf scores become exact zeros below)
+      if (j == NKB - 1) {
+        constexpr int nvalid = TOK - (NKB - 1) * BKV;   // 65
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_s + t_lane + c * 32, v);
-        tmem_ld_wait();
-        const int key0 = j * BKV + c * 32;
+        for (int i = nvalid; i < 128; ++i) v[i] = 0xff800000u;  // -inf
+      }
+      // four independent chains for the maximum (and for the sum below): no 128-long dependency
+      float bm4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = exp2f(fmaf(__uint_as_float(v[i]), sl2, -m_sl2));
-          float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), sl2, -m_sl2));
-          if (key0 + i >= TOK) p0 = 0.f;
-          if (key0 + i + 1 >= TOK) p1 = 0.f;
-          // sum what the tensor core will actually see (bf16-rounded), like a bf16 softmax output
-          const __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
-          l += __bfloat162float(b.x) + __bfloat162float(b.y);
-          pk[c * 16 + (i >> 1)] = *reinterpret_cast<const uint32_t*>(&b);
+      for (int i = 0; i < 128; i += 4) {
+        bm4[0] = fmaxf(bm4[0], __uint_as_float(v[i]));
+        bm4[1] = fmaxf(bm4[1], __uint_as_float(v[i + 1]));
+        bm4[2] = fmaxf(bm4[2], __uint_as_float(v[i + 2]));
+        bm4[3] = fmaxf(bm4[3], __uint_as_float(v[i + 3]));
+      }
+      const float bm = fmaxf(fmaxf(bm4[0], bm4[1]), fmaxf(bm4[2], bm4[3]));
+      // lazy rescale: only when the running maximum grows by more than 2^kRescaleLog2
+      float alpha = 1.f;
+      const bool need = (bm - m_used) * sl2 > kRescaleLog2;   // true on the first block (m_used = -inf)
+      if (need) {
+        alpha = ex2_approx((m_used - bm) * sl2);               // 0 on the first block
+        m_used = bm;
+        l *= alpha;
+      }
+      const bool any_need = __any_sync(0xffffffffu, need) && j > 0;
+      const float m_sl2 = m_used * sl2;
+      uint32_t pk[64];
+      float ls4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 128; i += 8) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(v[i + 2 * u]), sl2, -m_sl2));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 2 * u + 1]), sl2, -m_sl2));
+          ls4[u] += p0 + p1;
+          pk[(i >> 1) + u] = pack_bf16x2(p0, p1);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_s_free);
-      if (j > 0) {  // previous P V must have retired before P is overwritten
-        mbar_wait(bar_pv_done, pv_phase, 620);
-        pv_phase ^= 1;
+      l += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
+      if (j > 0) mbar_wait(bar_pv_done, (j - 1) & 1, 620);   // P V_{j-1} retired: P and O are ours
+      if (any_need) {
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(tmem_o + t_lane + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32b_x32(tmem_o + t_lane + c * 32, o);
+        }
+        tmem_st_wait();
+        tc_fence_before();
       }
       // P[r][key] in the K-major 128B-swizzled UMMA layout: two 64-key atoms of 128 rows x 128 B
 #pragma unroll
@@ -211,17 +223,17 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __rest
     __nv_bfloat16* orow = out + (size_t)(row_base + qrow) * VZ_VIT_WIDTH + h * HD;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_o + t_lane + c * 32, v);
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tmem_o + t_lane + c * 32, o);
       tmem_ld_wait();
       if (qrow < TOK) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
-          w.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
-          w.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
-          w.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+          w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
           *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = w;
         }
       }
