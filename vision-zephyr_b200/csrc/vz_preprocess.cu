@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PreArgs a)
   int32_t* s_vkk = reinterpret_cast<int32_t*>(s_row + 2 * a.row_buf_bytes);  // [BAND][ksv]
   int32_t* s_vmin = s_vkk + BAND * a.max_ksize;
   int32_t* s_vcnt = s_vmin + BAND;
+  int32_t* s_hkk = s_vcnt + BAND + 4;  // [ksh][336]: tap k of output column x (zero outside the taps)
 
   // ---- vertical taps of the band's 14 output rows ------------------------------------------
   const int ry0 = td.tile_y + band * BAND - td.off_y;  // resized-image row of band row 0
@@ -100,19 +101,24 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PreArgs a)
     const int ry = ry0 + y;
     s_vkk[y * a.max_ksize + k] = (ry >= 0 && ry < td.out_h) ? v_kk[ry * ksv + k] : 0;
   }
+  // ---- horizontal coefficients of the tile's 336 columns, tap-major (conflict-free reads) ---------
+  for (int i = tid; i < ksh * TILE; i += PP_THREADS) {
+    const int k = i / TILE, x = i - k * TILE;
+    const int rx = td.tile_x + x - td.off_x;
+    s_hkk[i] = (rx >= 0 && rx < td.out_w) ? h_kk[rx * ksh + k] : 0;
+  }
   // ---- this thread's columns ------------------------------------------------------------------
-  int hx_min[COLS_PER_THREAD], hx_cnt[COLS_PER_THREAD], hx_c[COLS_PER_THREAD];
-  const int32_t* hx_kk[COLS_PER_THREAD];
+  int hx_min[COLS_PER_THREAD], hx_cnt[COLS_PER_THREAD], hx_c[COLS_PER_THREAD], hx_x[COLS_PER_THREAD];
 #pragma unroll
   for (int i = 0; i < COLS_PER_THREAD; ++i) {
     const int j = tid + i * PP_THREADS;
-    const int x = j / 3;
-    hx_c[i] = j - x * 3;
+    const int x = (j < NCOL) ? j / 3 : 0;
+    hx_x[i] = x;
+    hx_c[i] = (j < NCOL) ? j - x * 3 : 0;
     const int rx = td.tile_x + x - td.off_x;
     const bool ok = (j < NCOL) && rx >= 0 && rx < td.out_w;
-    hx_min[i] = ok ? h_min[rx] : 0;
+    hx_min[i] = ok ? h_min[rx] : -1;
     hx_cnt[i] = ok ? h_cnt[rx] : 0;
-    hx_kk[i] = h_kk + (ok ? rx : 0) * ksh;
   }
   // source column window needed by this tile (uniform per CTA)
   int sx0, sx1;
@@ -123,6 +129,9 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PreArgs a)
     if (rxa <= rxb) { sx0 = h_min[rxa]; sx1 = h_min[rxb] + h_cnt[rxb]; }
     else { sx0 = 0; sx1 = 0; }
   }
+#pragma unroll
+  for (int i = 0; i < COLS_PER_THREAD; ++i)
+    if (hx_min[i] < 0) hx_min[i] = sx0;  // invalid column: all-zero taps, any in-buffer address will do
   __syncthreads();
   // source row window of the band
   int sy0 = 0, sy1 = 0;
@@ -141,24 +150,42 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PreArgs a)
     for (int i = 0; i < COLS_PER_THREAD; ++i) acc[y][i] = 1 << (PREC - 1);
 
   const int nbytes = (sx1 - sx0) * 3;
+  const uint8_t* img_end = im.src + (size_t)im.W * im.H * 3;
+  // Rows land in smem at the same 16-byte phase they have in global memory, so the copy is made of
+  // aligned 128-bit loads; `row_phase(sy)` is where the first needed byte sits in the buffer.
+  auto row_phase = [&](int sy) -> int {
+    return (int)(reinterpret_cast<uintptr_t>(im.src + ((size_t)sy * im.W + sx0) * 3) & 15);
+  };
   auto load_row = [&](int sy, uint8_t* dst) {
     const uint8_t* srow = im.src + ((size_t)sy * im.W + sx0) * 3;
-    for (int bidx = tid; bidx < nbytes; bidx += PP_THREADS) {
-      int v = srow[bidx];
-      if (im.prim_count > 0) {
-        const int px = bidx / 3, c = bidx - px * 3;
-        const int x = sx0 + px;
-        for (int pi = 0; pi < im.prim_count; ++pi) {
-          const vz_prim p = a.prims[im.prim_begin + pi];
-          if (p.type == VZ_PRIM_LAYER) {
-            const uint8_t* lp = im.layers + (((size_t)p.layer * im.H + sy) * im.W + x) * 4;
-            v = blend_over(v, lp[c], lp[3]);
-          } else if (rect_covers(p, x, sy)) {
-            v = blend_over(v, (int)((p.rgba >> (8 * c)) & 0xff), (int)(p.rgba >> 24));
-          }
+    const int ph = (int)(reinterpret_cast<uintptr_t>(srow) & 15);
+    if (im.prim_count == 0) {
+      const uint8_t* g0 = srow - ph;
+      const int nvec = (nbytes + ph + 15) >> 4;
+      for (int i = tid; i < nvec; i += PP_THREADS) {
+        const uint8_t* g = g0 + 16 * i;
+        if (g + 16 <= img_end) {
+          *reinterpret_cast<uint4*>(dst + 16 * i) = __ldg(reinterpret_cast<const uint4*>(g));
+        } else {
+          for (int b = 0; b < 16; ++b) dst[16 * i + b] = (g + b < img_end) ? g[b] : (uint8_t)0;
         }
       }
-      dst[bidx] = (uint8_t)v;
+      return;
+    }
+    for (int bidx = tid; bidx < nbytes; bidx += PP_THREADS) {
+      int v = srow[bidx];
+      const int px = bidx / 3, c = bidx - px * 3;
+      const int x = sx0 + px;
+      for (int pi = 0; pi < im.prim_count; ++pi) {
+        const vz_prim p = a.prims[im.prim_begin + pi];
+        if (p.type == VZ_PRIM_LAYER) {
+          const uint8_t* lp = im.layers + (((size_t)p.layer * im.H + sy) * im.W + x) * 4;
+          v = blend_over(v, lp[c], lp[3]);
+        } else if (rect_covers(p, x, sy)) {
+          v = blend_over(v, (int)((p.rgba >> (8 * c)) & 0xff), (int)(p.rgba >> 24));
+        }
+      }
+      dst[ph + bidx] = (uint8_t)v;
     }
   };
 
@@ -167,14 +194,28 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PreArgs a)
   for (int sy = sy0; sy < sy1; ++sy) {
     const uint8_t* cur = s_row + ((sy - sy0) & 1) * a.row_buf_bytes;
     if (sy + 1 < sy1) load_row(sy + 1, s_row + ((sy + 1 - sy0) & 1) * a.row_buf_bytes);
+    // horizontal pass: uniform tap loop (taps beyond a column's count have zero coefficients), four
+    // independent accumulators per thread
     int hv[COLS_PER_THREAD];
-#pragma unroll
-    for (int i = 0; i < COLS_PER_THREAD; ++i) {
-      int ss = 1 << (PREC - 1);
-      const uint8_t* sp = cur + (hx_min[i] - sx0) * 3 + hx_c[i];
-      const int32_t* kk = hx_kk[i];
-      for (int k = 0; k < hx_cnt[i]; ++k) ss += (int)sp[k * 3] * __ldg(kk + k);
-      hv[i] = clip8(ss);
+    {
+      const uint8_t* base = cur + row_phase(sy);
+      const uint8_t* sp0 = base + (hx_min[0] - sx0) * 3 + hx_c[0];
+      const uint8_t* sp1 = base + (hx_min[1] - sx0) * 3 + hx_c[1];
+      const uint8_t* sp2 = base + (hx_min[2] - sx0) * 3 + hx_c[2];
+      const uint8_t* sp3 = base + (hx_min[3] - sx0) * 3 + hx_c[3];
+      const int32_t* c0 = s_hkk + hx_x[0];
+      const int32_t* c1 = s_hkk + hx_x[1];
+      const int32_t* c2 = s_hkk + hx_x[2];
+      const int32_t* c3 = s_hkk + hx_x[3];
+      int s0 = 1 << (PREC - 1), s1 = s0, s2 = s0, s3 = s0;
+#pragma unroll 4
+      for (int k = 0; k < ksh; ++k) {
+        s0 += (int)sp0[k * 3] * c0[k * TILE];
+        s1 += (int)sp1[k * 3] * c1[k * TILE];
+        s2 += (int)sp2[k * 3] * c2[k * TILE];
+        s3 += (int)sp3[k * 3] * c3[k * TILE];
+      }
+      hv[0] = clip8(s0); hv[1] = clip8(s1); hv[2] = clip8(s2); hv[3] = clip8(s3);
     }
 #pragma unroll
     for (int y = 0; y < BAND; ++y) {
@@ -249,10 +290,11 @@ extern "C" int vz_preprocess(const vz_image_desc* images, int n_images, const vz
   PreArgs a;
   a.images = images; a.prims = prims; a.tiles = tiles; a.tables = tables; a.lut = lut768;
   a.out = out; a.out_mode = out_mode;
-  a.row_buf_bytes = ((max_src_w * 3 + 15) / 16) * 16;
+  a.row_buf_bytes = ((max_src_w * 3 + 3 * max_ksize + 32 + 15) / 16) * 16;  // + phase + tap overrun slack
   a.max_ksize = max_ksize;
   const int stage_bytes = (out_mode == VZ_OUT_CHW_F32) ? 3 * BAND * TILE * 4 : 24 * VZ_PATCH_K * 2;
-  const size_t smem = (size_t)stage_bytes + 2 * (size_t)a.row_buf_bytes + (size_t)BAND * max_ksize * 4 + 2 * BAND * 4;
+  const size_t smem = (size_t)stage_bytes + 2 * (size_t)a.row_buf_bytes + (size_t)BAND * max_ksize * 4 + 2 * BAND * 4 +
+                      16 + (size_t)max_ksize * TILE * 4;
   if (smem > 220 * 1024) return VZ_ERR_UNSUPPORTED;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static bool attr_done = false;
