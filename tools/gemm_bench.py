@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Time the tcgen05 GEMM on the path's shapes (CUDA events, L2 flushed between runs by rotating buffers)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import vision_zephyr_b200  # noqa
+from vision_zephyr_b200 import _lib as L
+
+lib = L.load()
+T = 40
+M = T * 577
+SHAPES = [("qkv", M, 3072, 1024, 0, 0, 1), ("o", M, 1024, 1024, 0, 1, 1), ("fc1", M, 4096, 1024, 1, 0, 1),
+          ("fc2", M, 1024, 4096, 0, 1, 1), ("sa_in", 1280, 12288, 4096, 0, 0, 1), ("sa_out", 1280, 4096, 4096, 0, 1, 1),
+          ("ffn1", 1280, 8192, 4096, 2, 0, 1), ("ffn2", 1280, 4096, 8192, 0, 1, 1), ("ca_q", 1280, 4096, 4096, 0, 0, 1)]
+
+
+def run(name, M, N, K, act, res, reps=20):
+    A = torch.randn((M, K), device="cuda").to(torch.bfloat16)
+    W = (torch.randn((N, K), device="cuda") * K ** -0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    R = torch.randn((M, N), device="cuda").to(torch.bfloat16) if res else None
+    out = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    g = L.GemmArgs()
+    g.A, g.W, g.out, g.bias = A.data_ptr(), W.data_ptr(), out.data_ptr(), bias.data_ptr()
+    g.residual = R.data_ptr() if res else None
+    g.M, g.N, g.K, g.lda, g.ldw, g.ldo, g.ldr = M, N, K, K, K, N, N
+    g.act = act
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ts = []
+    for i in range(reps + 3):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(lib.vz_gemm_bf16(C.byref(g), L.stream_ptr()), name)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    med = ts[len(ts) // 2]
+    print(f"{name:7s} M={M:6d} N={N:6d} K={K:5d} act={act} res={res}: {med * 1e3:8.1f} us  {2.0 * M * N * K / med / 1e9:7.1f} TFLOP/s")
+
+
+for s in SHAPES:
+    run(*s[:6])

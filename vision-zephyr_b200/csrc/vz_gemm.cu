@@ -8,6 +8,8 @@
 // q/k/v/out/fc1/fc2, K7 the stacked cross-attention K/V projection, K8 the Q-Former linears).
 #include "vz_common.cuh"
 
+#include <stdlib.h>
+
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -45,8 +47,8 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 4 : 6);
+  static constexpr int TMEM_COLS = (BN == 192) ? 512 : 2 * BN;  // two accumulator stages (power of two)
   static constexpr int BAR_BYTES = 256;
   static constexpr int EPI_BYTES = kEpiWarps * EPI_STAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + align slack
@@ -187,17 +189,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     const int q = e & 3;
     const int half = e >> 2;
     uint8_t* stg = sEpi + e * EPI_STAGE_BYTES;
-    const uint32_t stg_u32 = smem_u32(stg);
     // own-row addressing (lane = row) and cooperative addressing (4 lanes per row)
     const uint32_t own_off = (uint32_t)lane * 64u;
     const uint32_t own_sw = (uint32_t)((lane >> 1) & 3);
     const int co_r = lane >> 2, co_j = lane & 3;
     uint32_t acc = 0, acc_phase = 0;
+    uint32_t cc = 0;  // chunk counter: selects which half of the warp's staging area is current
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int m_blk, n_blk, bz;
       tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk, bz);
-      mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
-      tc_fence_after();
       const int m_base = m_blk * BM + q * 32;
       const float* bias_b = p.bias ? p.bias + (size_t)bz * p.bias_bstride : nullptr;
       const __nv_bfloat16* res_b = p.residual ? p.residual + (size_t)bz * p.r_bstride : nullptr;
@@ -219,22 +219,34 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         co_out[i] = (size_t)bz * p.o_bstride + (size_t)out_row * p.ldo;
         co_res[i] = (size_t)res_row * p.ldr + co_j * 8;
       }
+      // Residual chunks travel global -> smem with cp.async (no registers), one chunk ahead of their
+      // use; the first chunk of a tile is requested BEFORE waiting for the accumulator, so its HBM/L2
+      // latency hides behind the tile's MMAs.  Chunk cc lives in staging half (cc & 1).
+      auto prefetch_residual = [&](int col0_, uint32_t which) {
+        uint8_t* dst = stg + (which & 1u) * 2048u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = 8 * i + co_r;
+          cp_async_16(dst + rr * 64 + ((co_j ^ ((rr >> 1) & 3)) << 4),
+                      co_ok[i] ? (const void*)(res_b + co_res[i] + col0_) : (const void*)res_b, co_ok[i]);
+        }
+        cp_async_commit();
+      };
+      if (res_b && n_blk * BN + half * 32 < p.N) prefetch_residual(n_blk * BN + half * 32, cc);
+      mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+      tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
+      for (int c = half; c < BN / 32; c += 2, ++cc) {
         const int col0 = n_blk * BN + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
+        uint8_t* stg = sEpi + e * EPI_STAGE_BYTES + (cc & 1u) * 2048u;  // shadows the warp base on purpose
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c * 32, r);
         if (res_b) {
-          // coalesced residual chunk -> staging tile (overlaps the TMEM load)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 w = make_uint4(0, 0, 0, 0);
-            if (co_ok[i]) w = *reinterpret_cast<const uint4*>(res_b + co_res[i] + col0);
-            const int rr = 8 * i + co_r;
-            *reinterpret_cast<uint4*>(stg + rr * 64 + ((co_j ^ ((rr >> 1) & 3)) << 4)) = w;
-          }
+          const bool more = (c + 2 < BN / 32) && (col0 + 64 < p.N);
+          if (more) { prefetch_residual(col0 + 64, cc + 1); cp_async_wait<1>(); }
+          else cp_async_wait<0>();
         }
         tmem_ld_wait();
         float v[32];
@@ -255,6 +267,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         if (p.out_f32) {
           // fp32 output (attention scores): 128 B per row, 8 chunks swizzled by row & 7; stores cover
           // 4 rows x 128 B per instruction
+          uint8_t* stg = sEpi + e * EPI_STAGE_BYTES;  // fp32 rows need the warp's whole 4 KB
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             *reinterpret_cast<float4*>(stg + lane * 128 + (((uint32_t)i ^ (uint32_t)(lane & 7)) << 4)) =
@@ -301,7 +314,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         }
         __syncwarp();  // staging tile is reused by the next chunk
       }
-      (void)stg_u32;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -490,11 +502,28 @@ int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
   int dev = 0, num_sms = 0;
   VZ_CUDA_CHECK(cudaGetDevice(&dev));
   VZ_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  // 128x256 tiles when they still fill the machine, otherwise 128x128 for more CTAs
+  // Tile width.  128x256 tiles run the tensor pipe at full rate and amortise the A re-reads best;
+  // measured on B200, 128x128 tiles reach only ~0.68 of that rate, so they are used only when N is
+  // not a multiple of 256 or the problem has fewer 256-wide tiles than SMs.  The persistent grid works
+  // in rounds of num_sms tiles; for mid-sized problems (the Q-Former's M = 32*T rows) 128x192 tiles
+  // (~0.78 of the time of a 256-wide tile) need fewer, cheaper rounds.
+  static const int forced_bn = []() { const char* e = getenv("VZ_GEMM_BN"); return e ? atoi(e) : 0; }();
   const long tiles256 = (long)p.num_m * ((a.N + 255) / 256) * batch;
-  if (a.N % 256 == 0 && tiles256 >= num_sms) {
+  const long tiles192 = (long)p.num_m * ((a.N + 191) / 192) * batch;
+  const double cost256 = (double)((tiles256 + num_sms - 1) / num_sms);
+  const double cost192 = 0.78 * (double)((tiles192 + num_sms - 1) / num_sms);
+  int bn = 128;
+  if (a.N % 256 == 0 && tiles256 >= num_sms) bn = (cost192 < 0.9 * cost256 && tiles256 < 8 * num_sms) ? 192 : 256;
+  if (forced_bn == 256 && a.N % 256 == 0) bn = 256;
+  if (forced_bn == 192 && a.N >= 192) bn = 192;
+  if (forced_bn == 128) bn = 128;
+  if (bn == 256) {
     p.num_n = a.N / 256;
     return launch_tc<256>(a, p, num_sms, st);
+  }
+  if (bn == 192) {
+    p.num_n = (a.N + 191) / 192;
+    return launch_tc<192>(a, p, num_sms, st);
   }
   p.num_n = (a.N + 127) / 128;
   return launch_tc<128>(a, p, num_sms, st);
