@@ -25,6 +25,7 @@ constexpr int NCOL = TILE * 3;  // 1008 byte-columns per band row
 constexpr int PP_THREADS = 256;
 constexpr int COLS_PER_THREAD = 4;  // 4*256 >= 1008
 constexpr int PREC = 22;
+constexpr int MAX_PRIMS = 32;  // visual-prompt instances per image (the reference draws 1-4)
 
 struct PreArgs {
   const vz_image_desc* images;
@@ -87,6 +88,11 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PreArgs a)
   int32_t* s_vmin = s_vkk + BAND * a.max_ksize;
   int32_t* s_vcnt = s_vmin + BAND;
   int32_t* s_hkk = s_vcnt + BAND + 4;  // [ksh][336]: tap k of output column x (zero outside the taps)
+
+  // ---- instance list of this image (visual prompts) -> shared memory ---------------------------
+  __shared__ vz_prim s_prims[MAX_PRIMS];
+  const int n_prims = im.prim_count < MAX_PRIMS ? im.prim_count : MAX_PRIMS;
+  for (int i = tid; i < n_prims; i += PP_THREADS) s_prims[i] = a.prims[im.prim_begin + i];
 
   // ---- vertical taps of the band's 14 output rows ------------------------------------------
   const int ry0 = td.tile_y + band * BAND - td.off_y;  // resized-image row of band row 0
@@ -172,20 +178,29 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PreArgs a)
       }
       return;
     }
-    for (int bidx = tid; bidx < nbytes; bidx += PP_THREADS) {
-      int v = srow[bidx];
-      const int px = bidx / 3, c = bidx - px * 3;
+    // blend path: one thread per PIXEL; the instance list sits in shared memory and every RGBA
+    // overlay pixel is one aligned 32-bit load
+    const int npx = sx1 - sx0;
+    for (int px = tid; px < npx; px += PP_THREADS) {
       const int x = sx0 + px;
-      for (int pi = 0; pi < im.prim_count; ++pi) {
-        const vz_prim p = a.prims[im.prim_begin + pi];
+      int r = srow[px * 3], g = srow[px * 3 + 1], b = srow[px * 3 + 2];
+      for (int pi = 0; pi < n_prims; ++pi) {
+        const vz_prim& p = s_prims[pi];
+        uint32_t ov;
         if (p.type == VZ_PRIM_LAYER) {
-          const uint8_t* lp = im.layers + (((size_t)p.layer * im.H + sy) * im.W + x) * 4;
-          v = blend_over(v, lp[c], lp[3]);
-        } else if (rect_covers(p, x, sy)) {
-          v = blend_over(v, (int)((p.rgba >> (8 * c)) & 0xff), (int)(p.rgba >> 24));
+          ov = __ldg(reinterpret_cast<const uint32_t*>(im.layers) + ((size_t)p.layer * im.H + sy) * im.W + x);
+        } else {
+          if (!rect_covers(p, x, sy)) continue;
+          ov = p.rgba;
         }
+        const int al = (int)(ov >> 24);
+        r = blend_over(r, (int)(ov & 0xff), al);
+        g = blend_over(g, (int)((ov >> 8) & 0xff), al);
+        b = blend_over(b, (int)((ov >> 16) & 0xff), al);
       }
-      dst[ph + bidx] = (uint8_t)v;
+      dst[ph + px * 3] = (uint8_t)r;
+      dst[ph + px * 3 + 1] = (uint8_t)g;
+      dst[ph + px * 3 + 2] = (uint8_t)b;
     }
   };
 

@@ -145,6 +145,8 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
         d.layers = lay_dev.data_ptr() if lay_dev is not None else None
         d.W, d.H = W, H
         d.prim_begin, d.prim_count = begin, len(prim_list) - begin
+        if d.prim_count > 32:
+            raise ValueError("at most 32 visual-prompt instances per image")
         tiles_per_image.append(len(views[i]))
         for v in views[i]:
             t = _lib.TileDesc()
