@@ -4,8 +4,8 @@
 // Replaces HF CLIPAttention as called from vision_encoder/vision_encoder.py:101-105.
 //
 // One CTA = 128 query rows of one (tile, head); two CTAs are resident per SM so one CTA's softmax
-// overlaps the other's MMAs.  Warps 0-3: softmax (thread = query row = TMEM lane); warp 4: one thread
-// issues TMA and MMA.  One pass over the 5 key blocks (keys padded 577 -> 640 and masked):
+// overlaps the other's MMAs.  Warps 0-7: softmax (two threads per query row, each owning 64 of the
+// block's 128 keys); warp 8: one thread issues TMA and MMA.  One pass over the 5 key blocks (keys padded 577 -> 640 and masked):
 //   S_j = Q K_j^T -> registers -> P_j = exp2((S_j - m) * scale) as bf16 in swizzled smem -> O += P_j V_j
 // with an online softmax whose accumulator rescale is LAZY: O (in TMEM) is only multiplied by
 // exp2(m_old - m_new) when the running maximum grew by more than 2^8, which is rare after the first
@@ -24,8 +24,12 @@ constexpr int TILE_BYTES = 128 * 128;    // 128 rows x 64 bf16
 constexpr int SMEM_Q = 0, SMEM_P = TILE_BYTES, SMEM_RING = 3 * TILE_BYTES;   // P = 2 tiles
 constexpr int RING_STAGES = 2;
 constexpr int SMEM_BARS = SMEM_RING + RING_STAGES * 2 * TILE_BYTES;
-constexpr int SMEM_TOTAL = SMEM_BARS + 128;
-constexpr int THREADS = 160;
+constexpr int SMEM_XCHG = SMEM_BARS + 128;            // 512 B: u16 [2 halves][128 rows] / float [128 rows]
+constexpr int SMEM_TOTAL = SMEM_XCHG + 512;
+// two CTAs per SM: 2 * (SMEM_TOTAL + 1 KB reserved) must fit the SM's 228 KB
+static_assert(2 * (SMEM_TOTAL + 1024) <= 228 * 1024, "attention kernel must keep 2 CTAs per SM");
+constexpr int THREADS = 288;        // 8 softmax warps (2 threads per query row) + 1 control warp
+constexpr int SOFTMAX_THREADS = 256;
 constexpr uint32_t TMEM_COLS = 256;      // S: columns 0..127, O: columns 128..191
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -67,20 +71,20 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __rest
     mbar_init(bar_q, 1);
     for (int i = 0; i < RING_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
     mbar_init(bar_s_full, 1);
-    mbar_init(bar_s_free, 4);
-    mbar_init(bar_p_full, 4);
+    mbar_init(bar_s_free, 8);
+    mbar_init(bar_p_full, 8);
     mbar_init(bar_pv_done, 1);
     mbar_init(bar_o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 8) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ======================= control thread: TMA + MMA issue =======================
     if (lane == 0) {
       tma_prefetch_desc(&tm);
@@ -134,38 +138,51 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __rest
       umma_commit(bar_o_full);
     }
   } else {
-    // ======================= softmax warps: thread = query row =======================
-    const int r = warp * 32 + lane;                      // row inside the CTA's 128-query block
-    const uint32_t t_lane = ((uint32_t)(warp * 32)) << 16;
+    // ======================= softmax warps: TWO threads per query row =======================
+    // warp w: TMEM lane quarter q = w & 3 (rows 32q..32q+31), key half hf = w >> 2 (64 of the block's 128
+    // keys, i.e. one 64-key swizzle atom of P, and 32 of O's 64 columns).  The two threads of a row
+    // exchange their half maxima / sums through shared memory so both take identical rescale decisions.
+    const int q4 = warp & 3, hf = warp >> 2;
+    const int r = q4 * 32 + lane;                        // row inside the CTA's 128-query block
+    const uint32_t t_lane = ((uint32_t)(q4 * 32)) << 16;
+    uint16_t* xch16 = reinterpret_cast<uint16_t*>(smem + SMEM_XCHG);   // [half][row]
+    float* xl = reinterpret_cast<float*>(smem + SMEM_XCHG);            // [row], epilogue only
     const float sl2 = scale * kLog2e;
     float m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < NKB; ++j) {
       mbar_wait(bar_s_full, j & 1, 600);
       tc_fence_after();
-      uint32_t v[128];
+      uint32_t v[64];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tmem_s + t_lane + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+      for (int c = 0; c < 2; ++c)
+        tmem_ld_32x32b_x32(tmem_s + t_lane + hf * 64 + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_s_free);
       // keys of the last block beyond the tile's 577 tokens belong to the next tile: mask them
-      // (only block NKB-1 pays for the masking; -inf scores become exact zeros below)
       if (j == NKB - 1) {
-        constexpr int nvalid = TOK - (NKB - 1) * BKV;   // 65
+        constexpr int nvalid = TOK - (NKB - 1) * BKV;   // 65 valid keys in the last block
 #pragma unroll
-        for (int i = nvalid; i < 128; ++i) v[i] = 0xff800000u;  // -inf
+        for (int i = 0; i < 64; ++i)
+          if (hf * 64 + i >= nvalid) v[i] = 0xff800000u;  // -inf
       }
-      // four independent chains for the maximum (and for the sum below): no 128-long dependency
       float bm4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
+      for (int i = 0; i < 64; i += 4) {
         bm4[0] = fmaxf(bm4[0], __uint_as_float(v[i]));
         bm4[1] = fmaxf(bm4[1], __uint_as_float(v[i + 1]));
         bm4[2] = fmaxf(bm4[2], __uint_as_float(v[i + 2]));
         bm4[3] = fmaxf(bm4[3], __uint_as_float(v[i + 3]));
       }
-      const float bm = fmaxf(fmaxf(bm4[0], bm4[1]), fmaxf(bm4[2], bm4[3]));
+      const float hm = fmaxf(fmaxf(bm4[0], bm4[1]), fmaxf(bm4[2], bm4[3]));
+      // The two threads of a row swap their half maxima as the upper 16 bits of the float; both then
+      // use max(trunc(own), trunc(partner)), so they take IDENTICAL decisions (the reference point of
+      // the exponentials only has to be common and close to the maximum, not the exact maximum).
+      const uint32_t hb = __float_as_uint(hm) >> 16;
+      xch16[hf * 128 + r] = (uint16_t)hb;
+      asm volatile("bar.sync 1, %0;" ::"n"(SOFTMAX_THREADS) : "memory");
+      const float bm = fmaxf(__uint_as_float(hb << 16), __uint_as_float((uint32_t)xch16[(hf ^ 1) * 128 + r] << 16));
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_s_free);   // S_j is in registers AND the exchange slot is free again
       // lazy rescale: only when the running maximum grows by more than 2^kRescaleLog2
       float alpha = 1.f;
       const bool need = (bm - m_used) * sl2 > kRescaleLog2;   // true on the first block (m_used = -inf)
@@ -176,10 +193,10 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __rest
       }
       const bool any_need = __any_sync(0xffffffffu, need) && j > 0;
       const float m_sl2 = m_used * sl2;
-      uint32_t pk[64];
+      uint32_t pk[32];
       float ls4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < 128; i += 8) {
+      for (int i = 0; i < 64; i += 8) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const float p0 = ex2_approx(fmaf(__uint_as_float(v[i + 2 * u]), sl2, -m_sl2));
@@ -192,39 +209,40 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __rest
       if (j > 0) mbar_wait(bar_pv_done, (j - 1) & 1, 620);   // P V_{j-1} retired: P and O are ours
       if (any_need) {
         tc_fence_after();
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(tmem_o + t_lane + hf * 32, o);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t o[32];
-          tmem_ld_32x32b_x32(tmem_o + t_lane + c * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32b_x32(tmem_o + t_lane + c * 32, o);
-        }
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_32x32b_x32(tmem_o + t_lane + hf * 32, o);
         tmem_st_wait();
         tc_fence_before();
       }
-      // P[r][key] in the K-major 128B-swizzled UMMA layout: two 64-key atoms of 128 rows x 128 B
+      // this thread's 64 keys are exactly atom `hf` of P (K-major, 128B swizzle): 8 chunks of row r
 #pragma unroll
-      for (int ch = 0; ch < 16; ++ch) {
-        const int atom = ch >> 3, c = ch & 7;
-        uint4 w = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
-        *reinterpret_cast<uint4*>(sP + atom * TILE_BYTES + r * 128 + ((c ^ (r & 7)) << 4)) = w;
+      for (int c = 0; c < 8; ++c) {
+        uint4 w = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+        *reinterpret_cast<uint4*>(sP + hf * TILE_BYTES + r * 128 + ((c ^ (r & 7)) << 4)) = w;
       }
       fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p_full);
     }
-    // ---- epilogue: O / l ----
+    // ---- epilogue: O / l (row sum = both halves) ----
+    asm volatile("bar.sync 1, %0;" ::"n"(SOFTMAX_THREADS) : "memory");   // last exchange fully consumed
+    if (hf == 0) xl[r] = l;
+    asm volatile("bar.sync 1, %0;" ::"n"(SOFTMAX_THREADS) : "memory");
+    if (hf == 1) { l += xl[r]; xl[r] = l; }
+    asm volatile("bar.sync 1, %0;" ::"n"(SOFTMAX_THREADS) : "memory");
+    if (hf == 0) l = xl[r];
     mbar_wait(bar_o_full, 0, 630);
     tc_fence_after();
     const int qrow = qb * BQ + r;
     const float inv = 1.0f / l;
-    __nv_bfloat16* orow = out + (size_t)(row_base + qrow) * VZ_VIT_WIDTH + h * HD;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    __nv_bfloat16* orow = out + (size_t)(row_base + qrow) * VZ_VIT_WIDTH + h * HD + hf * 32;
+    {
       uint32_t o[32];
-      tmem_ld_32x32b_x32(tmem_o + t_lane + c * 32, o);
+      tmem_ld_32x32b_x32(tmem_o + t_lane + hf * 32, o);
       tmem_ld_wait();
       if (qrow < TOK) {
 #pragma unroll
@@ -234,14 +252,14 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __rest
           w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
           w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
           w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = w;
+          *reinterpret_cast<uint4*>(orow + i * 8) = w;
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
