@@ -76,9 +76,23 @@ typedef struct {
   int batch;
   int out_f32;          /* 1 = write float32 instead of bf16 (no residual / row remap)          */
   long long a_bstride, w_bstride, o_bstride, r_bstride, bias_bstride;
+  /* LayerNorm fused around the GEMM (ViT layers).  Producer: stats_out != NULL makes the epilogue write,
+   * per output row and per (n-tile, column half), the partial (sum, sum of squares) of the row it
+   * just produced into stats_out[M][stats_np][2] (stats_np = vz_gemm_stats_partials(M, N)).
+   * Consumer: ln_stats != NULL treats A as the INPUT of a LayerNorm over its K columns whose gamma
+   * is already folded into W (W' = W * gamma) and whose beta is folded into bias
+   * (b' = b + W beta): out = rstd * (A W'^T - mean * ln_colsum) + b', ln_colsum[n] = sum_k W'[n,k].  */
+  const float* ln_stats;
+  const float* ln_colsum;
+  int ln_np;
+  float ln_eps;
+  float* stats_out;
+  int stats_np;
 } vz_gemm_args;
 
 int vz_gemm_bf16(const vz_gemm_args* args, void* stream);
+/* number of partial-statistics slots per row that a stats_out GEMM of this shape writes */
+int vz_gemm_stats_partials(int M, int N);
 
 /* Measurement hooks (bench.py / tests; no effect on results).
  * vz_kernel_launches: number of CUDA kernels this library has launched in the process.
@@ -161,15 +175,18 @@ int vz_patchify(const void* pixel_values, int src_is_f32, int T, void* patches, 
 #define VZ_PATCH_K 592
 #define VZ_FUSED_WIDTH 5120
 
+/* LayerNorm 1/2 of every encoder layer are FOLDED into the following Linear (see vz_gemm_args):
+ * w_qkv = cat(q,k,v)_proj.weight * layer_norm1.weight, b_qkv = bias + W layer_norm1.bias,
+ * s_qkv[n] = sum_k w_qkv[n,k]; likewise w_fc1 / b_fc1 / s_fc1 with layer_norm2.               */
 typedef struct {
-  const float *ln1_g, *ln1_b;
-  const void* w_qkv;   /* bf16 [3072,1024] = cat(q_proj, k_proj, v_proj) */
-  const float* b_qkv;  /* f32 [3072] */
+  const void* w_qkv;   /* bf16 [3072,1024] (gamma folded) */
+  const float* b_qkv;  /* f32 [3072] (beta folded)        */
+  const float* s_qkv;  /* f32 [3072] column sums          */
   const void* w_o;     /* bf16 [1024,1024] */
   const float* b_o;
-  const float *ln2_g, *ln2_b;
-  const void* w_fc1;   /* bf16 [4096,1024] */
-  const float* b_fc1;
+  const void* w_fc1;   /* bf16 [4096,1024] (gamma folded) */
+  const float* b_fc1;  /* f32 [4096] (beta folded)        */
+  const float* s_fc1;  /* f32 [4096] column sums          */
   const void* w_fc2;   /* bf16 [1024,4096] */
   const float* b_fc2;
 } vz_vit_layer;

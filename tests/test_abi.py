@@ -43,10 +43,10 @@ def test_bad_arguments_are_rejected_without_a_gpu():
 
 def test_struct_layouts_match_the_header():
     from vision_zephyr_b200 import _lib
-    assert ctypes.sizeof(_lib.GemmArgs) == 5 * 8 + 13 * 4 + 4 + 5 * 8  # ints padded to 8
+    assert ctypes.sizeof(_lib.GemmArgs) == 5 * 8 + 13 * 4 + 4 + 5 * 8 + 2 * 8 + 2 * 4 + 8 + 4 + 4
     assert ctypes.sizeof(_lib.ImageDesc) == 32
     assert ctypes.sizeof(_lib.Prim) == 32
     assert ctypes.sizeof(_lib.TileDesc) == 36
     assert ctypes.sizeof(_lib.SlotDesc) == 48
-    assert ctypes.sizeof(_lib.VitWeights) == 5 * 8 + 24 * 12 * 8
+    assert ctypes.sizeof(_lib.VitWeights) == 5 * 8 + 24 * 10 * 8
     assert ctypes.sizeof(_lib.QfWeights) == 5 * 8 + 8 * 20 * 8

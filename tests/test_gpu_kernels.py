@@ -194,3 +194,41 @@ def test_gemm_batched_heads_and_f32_output():
     L.check(lib.vz_gemm_bf16(C.byref(g), L.stream_ptr()), "batched ragged")
     torch.cuda.synchronize()
     _check(o, torch.einsum("tmk,tnk->tmn", P_.float(), fT.float()), "batched ragged-M gemm")
+
+
+def test_gemm_fused_layernorm_producer_and_consumer():
+    """LayerNorm folded around the GEMM: the producer epilogue emits partial row statistics, the consumer
+    (gamma/beta folded into its weights) finishes the normalisation in its epilogue."""
+    L, lib = _lib()
+    M, D, N = 1154, 1024, 3072
+    A0, W0 = _rand((M, 512), 1.0, 41), _rand((D, 512), 512 ** -0.5, 42)
+    res = _rand((M, D), 1.0, 43) + 0.7                       # non-zero row means
+    np_ = lib.vz_gemm_stats_partials(M, D)
+    stats = torch.full((M, np_, 2), float("nan"), dtype=torch.float32, device="cuda")
+    x = torch.zeros((M, D), dtype=torch.bfloat16, device="cuda")
+    g = L.GemmArgs()
+    g.A, g.W, g.out, g.residual = A0.data_ptr(), W0.data_ptr(), x.data_ptr(), res.data_ptr()
+    g.M, g.N, g.K, g.lda, g.ldw, g.ldo, g.ldr = M, D, 512, 512, 512, D, D
+    g.stats_out, g.stats_np = stats.data_ptr(), np_
+    L.check(lib.vz_gemm_bf16(C.byref(g), L.stream_ptr()), "producer")
+    torch.cuda.synchronize()
+    xf = ref_gemm(A0, W0, residual=res)                      # fp32 values the epilogue summed
+    s = stats.sum(1)
+    assert torch.allclose(s[:, 0], xf.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[:, 1], (xf * xf).sum(1), rtol=1e-4, atol=1e-2)
+    # consumer
+    gamma = (1 + 0.1 * torch.randn(D, device="cuda")).float()
+    beta = (0.1 * torch.randn(D, device="cuda")).float()
+    W, b = _rand((N, D), D ** -0.5, 44), torch.randn(N, device="cuda") * 0.1
+    Wf = (W.float() * gamma[None]).to(torch.bfloat16).contiguous()
+    bf_ = (b + W.float() @ beta).contiguous()
+    cs = Wf.float().sum(1).contiguous()
+    out = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
+    g = L.GemmArgs()
+    g.A, g.W, g.out, g.bias = x.data_ptr(), Wf.data_ptr(), out.data_ptr(), bf_.data_ptr()
+    g.M, g.N, g.K, g.lda, g.ldw, g.ldo = M, N, D, D, D, N
+    g.ln_stats, g.ln_colsum, g.ln_np, g.ln_eps = stats.data_ptr(), cs.data_ptr(), np_, 1e-5
+    L.check(lib.vz_gemm_bf16(C.byref(g), L.stream_ptr()), "consumer")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x.float(), (D,), gamma, beta, 1e-5) @ W.float().t() + b
+    _check(out, ref, "fused LayerNorm + GEMM", tol=2.0 ** -6)

@@ -29,6 +29,8 @@ class GemmArgs(C.Structure):
         ("batch", C.c_int), ("out_f32", C.c_int),
         ("a_bstride", C.c_longlong), ("w_bstride", C.c_longlong), ("o_bstride", C.c_longlong),
         ("r_bstride", C.c_longlong), ("bias_bstride", C.c_longlong),
+        ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_np", C.c_int), ("ln_eps", C.c_float),
+        ("stats_out", C.c_void_p), ("stats_np", C.c_int),
     ]
 
 
@@ -50,8 +52,7 @@ class TileDesc(C.Structure):
 
 class VitLayer(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
-        "ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_g", "ln2_b", "w_fc1", "b_fc1",
-        "w_fc2", "b_fc2")]
+        "w_qkv", "b_qkv", "s_qkv", "w_o", "b_o", "w_fc1", "b_fc1", "s_fc1", "w_fc2", "b_fc2")]
 
 
 class VitWeights(C.Structure):
@@ -90,6 +91,7 @@ SYMBOLS = {
     "vz_last_cuda_error": (_i, []),
     "vz_version": (_i, []),
     "vz_gemm_bf16": (_i, [C.POINTER(GemmArgs), _vp]),
+    "vz_gemm_stats_partials": (_i, [_i, _i]),
     "vz_kernel_launches": (C.c_longlong, []),
     "vz_gemm_profile": (_i, [_i]),
     "vz_gemm_profile_read": (_i, [C.POINTER(C.c_longlong), C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -64,6 +64,14 @@ struct GemmDev {
   int num_m, num_n, num_k;
   int batch, out_f32;
   long long o_bstride, r_bstride, bias_bstride;  // elements between consecutive batches
+  // LayerNorm fused around the GEMM (see vz_gemm_args): consumer side ...
+  const float* ln_stats;   // [M][ln_np][2] partial (sum, sum of squares) of every A row, or NULL
+  const float* ln_colsum;  // [N] sum_k W'[n,k]
+  int ln_np;
+  float ln_eps;
+  // ... and producer side: partial row statistics of THIS GEMM's output
+  float* stats_out;        // [M][stats_np][2] or NULL
+  int stats_np;
 };
 
 __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk, int& b) {
@@ -201,8 +209,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const int m_base = m_blk * BM + q * 32;
       const float* bias_b = p.bias ? p.bias + (size_t)bz * p.bias_bstride : nullptr;
       const __nv_bfloat16* res_b = p.residual ? p.residual + (size_t)bz * p.r_bstride : nullptr;
-      // rows this lane touches in the cooperative phases: m_base + 8*i + co_r
-      size_t co_out[4], co_res[4];
+      __nv_bfloat16* out_b = p.out + (size_t)bz * p.o_bstride;
+      // fused LayerNorm (consumer): mean / rstd of this lane's own row from the producer's partials,
+      // summed in a fixed order (deterministic)
+      float ln_mu = 0.f, ln_rstd = 1.f;
+      if (p.ln_stats && m_base + lane < p.M) {
+        const float2* ps = reinterpret_cast<const float2*>(p.ln_stats) + (size_t)(m_base + lane) * p.ln_np;
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = 0; i < p.ln_np; ++i) { const float2 t = ps[i]; s1 += t.x; s2 += t.y; }
+        const float inv_k = 1.0f / (float)p.K;
+        ln_mu = s1 * inv_k;
+        ln_rstd = rsqrtf(fmaxf(s2 * inv_k - ln_mu * ln_mu, 0.f) + p.ln_eps);
+      }
+      float st1 = 0.f, st2 = 0.f;  // producer side: partial statistics of this lane's output row
+      // rows this lane touches in the cooperative phases: m_base + 8*i + co_r (32-bit element offsets)
+      uint32_t co_out[4], co_res[4];
       bool co_ok[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -216,8 +237,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         } else if (p.row_mode == VZ_ROWS_RES_MOD) {
           res_row = m % p.rows_per;
         }
-        co_out[i] = (size_t)bz * p.o_bstride + (size_t)out_row * p.ldo;
-        co_res[i] = (size_t)res_row * p.ldr + co_j * 8;
+        co_out[i] = (uint32_t)out_row * (uint32_t)p.ldo + (uint32_t)(co_j * 8);
+        co_res[i] = (uint32_t)res_row * (uint32_t)p.ldr + (uint32_t)(co_j * 8);
       }
       // Residual chunks travel global -> smem with cp.async (no registers), one chunk ahead of their
       // use; the first chunk of a tile is requested BEFORE waiting for the accumulator, so its HBM/L2
@@ -252,7 +273,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (bias_b) {
+        if (p.ln_stats) {
+          // LN(x) W^T + b  ==  rstd * (x W'^T - mu * colsum(W')) + b'   (gamma folded into W', beta into b')
+          const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + col0);
+          const float4* b4 = reinterpret_cast<const float4*>(bias_b + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 cs = __ldg(c4 + i), b = __ldg(b4 + i);
+            v[4 * i + 0] = fmaf(ln_rstd, fmaf(-ln_mu, cs.x, v[4 * i + 0]), b.x);
+            v[4 * i + 1] = fmaf(ln_rstd, fmaf(-ln_mu, cs.y, v[4 * i + 1]), b.y);
+            v[4 * i + 2] = fmaf(ln_rstd, fmaf(-ln_mu, cs.z, v[4 * i + 2]), b.z);
+            v[4 * i + 3] = fmaf(ln_rstd, fmaf(-ln_mu, cs.w, v[4 * i + 3]), b.w);
+          }
+        } else if (bias_b) {
           const float4* b4 = reinterpret_cast<const float4*>(bias_b + col0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -296,6 +329,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             v[8 * i + 6] += bf16_lo(w.w); v[8 * i + 7] += bf16_hi(w.w);
           }
         }
+        if (p.stats_out) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { st1 += v[i]; st2 = fmaf(v[i], v[i], st2); }
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 w;
@@ -310,7 +347,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         for (int i = 0; i < 4; ++i) {
           const int rr = 8 * i + co_r;
           const uint4 w = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((co_j ^ ((rr >> 1) & 3)) << 4));
-          if (co_ok[i]) *reinterpret_cast<uint4*>(p.out + co_out[i] + co_j * 8 + col0) = w;
+          if (co_ok[i]) *reinterpret_cast<uint4*>(out_b + co_out[i] + col0) = w;
         }
         __syncwarp();  // staging tile is reused by the next chunk
       }
@@ -319,6 +356,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      if (p.stats_out && m_base + lane < p.M)
+        reinterpret_cast<float2*>(p.stats_out)[(size_t)(m_base + lane) * p.stats_np + n_blk * 2 + half] =
+            make_float2(st1, st2);
     }
   }
 
@@ -363,7 +403,18 @@ gemm_bf16_simple_kernel(const __nv_bfloat16* __restrict__ A, int lda,
     res_row = m % p.rows_per;
   }
   float v = acc;
-  if (p.bias) v += p.bias[n];
+  if (p.ln_stats) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = 0; i < p.ln_np; ++i) {
+      s1 += p.ln_stats[((size_t)m * p.ln_np + i) * 2];
+      s2 += p.ln_stats[((size_t)m * p.ln_np + i) * 2 + 1];
+    }
+    const float mu = s1 / (float)p.K;
+    const float rstd = rsqrtf(fmaxf(s2 / (float)p.K - mu * mu, 0.f) + p.ln_eps);
+    v = rstd * (v - mu * p.ln_colsum[n]) + p.bias[n];
+  } else if (p.bias) {
+    v += p.bias[n];
+  }
   v = act_apply(v, p.act);
   if (p.residual) v += __bfloat162float(p.residual[(size_t)res_row * p.ldr + n]);
   p.out[(size_t)out_row * p.ldo + n] = __float2bfloat16_rn(v);
@@ -461,6 +512,33 @@ int encode_tmap_2d_bf16(CUtensorMap* tm, const void* base, long long rows, int c
   return VZ_OK;
 }
 
+namespace {
+// tile width the launcher will use for a problem (shared with the orchestration, which sizes the
+// LayerNorm partial-statistics buffers from it)
+int pick_tile_n(int M, int N, int batch, int num_sms) {
+  static const int forced_bn = []() { const char* e = getenv("VZ_GEMM_BN"); return e ? atoi(e) : 0; }();
+  const long num_m = (M + BM - 1) / BM;
+  const long tiles256 = num_m * ((N + 255) / 256) * batch;
+  const long tiles192 = num_m * ((N + 191) / 192) * batch;
+  const double cost256 = (double)((tiles256 + num_sms - 1) / num_sms);
+  const double cost192 = 0.78 * (double)((tiles192 + num_sms - 1) / num_sms);
+  int bn = 128;
+  if (N % 256 == 0 && tiles256 >= num_sms) bn = (cost192 < 0.9 * cost256 && tiles256 < 8 * num_sms) ? 192 : 256;
+  if (forced_bn == 256 && N % 256 == 0) bn = 256;
+  if (forced_bn == 192 && N >= 192) bn = 192;
+  if (forced_bn == 128) bn = 128;
+  return bn;
+}
+}  // namespace
+
+int gemm_stats_partials(int M, int N) {
+  int dev = 0, num_sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  const int bn = pick_tile_n(M, N, 1, num_sms);
+  return ((N + bn - 1) / bn) * 2;
+}
+
 int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
   if (!a.A || !a.W || !a.out) return VZ_ERR_BAD_ARG;
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return VZ_ERR_BAD_ARG;
@@ -487,11 +565,19 @@ int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
   p.batch = batch; p.out_f32 = a.out_f32;
   p.o_bstride = batch > 1 ? a.o_bstride : 0; p.r_bstride = batch > 1 ? a.r_bstride : 0;
   p.bias_bstride = batch > 1 ? a.bias_bstride : 0;
+  p.ln_stats = a.ln_stats; p.ln_colsum = a.ln_colsum; p.ln_np = a.ln_np; p.ln_eps = a.ln_eps;
+  p.stats_out = a.stats_out; p.stats_np = a.stats_np;
+  if (a.ln_stats && (!a.ln_colsum || !a.bias || a.ln_np <= 0 || !aligned16(a.ln_colsum))) return VZ_ERR_BAD_ARG;
+  if (a.stats_out && (a.stats_np <= 0 || a.out_f32 || batch > 1)) return VZ_ERR_BAD_ARG;
+  // the epilogue addresses rows with 32-bit element offsets
+  if ((double)(a.M + a.M / 2 + 2) * a.ldo >= 2147483647.0 || (a.residual && (double)(a.M + 2) * a.ldr >= 2147483647.0))
+    return VZ_ERR_UNSUPPORTED;
   p.num_m = (a.M + BM - 1) / BM;
   p.num_k = (a.K + BK - 1) / BK;
 
   if (a.force_simple) {
     p.num_n = 0;
+    if (a.stats_out) return VZ_ERR_UNSUPPORTED;  // the debug path gets its statistics from vz::row_stats_launch
     dim3 grid((a.N + 15) / 16, (a.M + 15) / 16);
     gemm_bf16_simple_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a.A), a.lda,
                                                   reinterpret_cast<const __nv_bfloat16*>(a.W), a.ldw, p);
@@ -506,17 +592,8 @@ int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
   // measured on B200, 128x128 tiles reach only ~0.68 of that rate, so they are used only when N is
   // not a multiple of 256 or the problem has fewer 256-wide tiles than SMs.  The persistent grid works
   // in rounds of num_sms tiles; for mid-sized problems (the Q-Former's M = 32*T rows) 128x192 tiles
-  // (~0.78 of the time of a 256-wide tile) need fewer, cheaper rounds.
-  static const int forced_bn = []() { const char* e = getenv("VZ_GEMM_BN"); return e ? atoi(e) : 0; }();
-  const long tiles256 = (long)p.num_m * ((a.N + 255) / 256) * batch;
-  const long tiles192 = (long)p.num_m * ((a.N + 191) / 192) * batch;
-  const double cost256 = (double)((tiles256 + num_sms - 1) / num_sms);
-  const double cost192 = 0.78 * (double)((tiles192 + num_sms - 1) / num_sms);
-  int bn = 128;
-  if (a.N % 256 == 0 && tiles256 >= num_sms) bn = (cost192 < 0.9 * cost256 && tiles256 < 8 * num_sms) ? 192 : 256;
-  if (forced_bn == 256 && a.N % 256 == 0) bn = 256;
-  if (forced_bn == 192 && a.N >= 192) bn = 192;
-  if (forced_bn == 128) bn = 128;
+  // need fewer, cheaper rounds.  (VZ_GEMM_BN=256|192|128 overrides, for experiments.)
+  const int bn = pick_tile_n(a.M, a.N, batch, num_sms);
   if (bn == 256) {
     p.num_n = a.N / 256;
     return launch_tc<256>(a, p, num_sms, st);
@@ -559,6 +636,8 @@ extern "C" int vz_gemm_profile_read(long long* launches, double* total_ms, doubl
   if (total_flops) *total_flops = fl;
   return VZ_OK;
 }
+
+extern "C" int vz_gemm_stats_partials(int M, int N) { return vz::gemm_stats_partials(M, N); }
 
 extern "C" int vz_gemm_bf16(const vz_gemm_args* args, void* stream) {
   if (!args) return VZ_ERR_BAD_ARG;

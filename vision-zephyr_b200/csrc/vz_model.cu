@@ -31,7 +31,26 @@ int gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, co
   g.act = act; g.row_mode = row_mode; g.rows_per = rows_per; g.force_simple = simple;
   g.batch = 1; g.out_f32 = 0;
   g.a_bstride = g.w_bstride = g.o_bstride = g.r_bstride = g.bias_bstride = 0;
+  g.ln_stats = nullptr; g.ln_colsum = nullptr; g.ln_np = 0; g.ln_eps = 0.f; g.stats_out = nullptr; g.stats_np = 0;
   return gemm_launch(g, st);
+}
+
+// GEMM with a LayerNorm folded in front (consumer) and/or partial row statistics behind (producer)
+int gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act,
+            const void* residual, int ldr, void* out, int ldo, const float* ln_stats, int ln_np,
+            const float* ln_colsum, float* stats_out, int stats_np, int simple, cudaStream_t st) {
+  vz_gemm_args g;
+  g.A = A; g.W = W; g.out = out; g.bias = bias; g.residual = residual;
+  g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldo = ldo; g.ldr = ldr;
+  g.act = act; g.row_mode = VZ_ROWS_PLAIN; g.rows_per = 0; g.force_simple = simple;
+  g.batch = 1; g.out_f32 = 0;
+  g.a_bstride = g.w_bstride = g.o_bstride = g.r_bstride = g.bias_bstride = 0;
+  g.ln_stats = ln_stats; g.ln_colsum = ln_colsum; g.ln_np = ln_np; g.ln_eps = 1e-5f;
+  g.stats_out = simple ? nullptr : stats_out; g.stats_np = stats_np;
+  VZ_TRY(gemm_launch(g, st));
+  // the debug GEMM has no statistics epilogue: a row kernel produces the single partial instead
+  if (simple && stats_out) VZ_TRY(row_stats_launch(out, ldo, M, N, stats_out, st));
+  return VZ_OK;
 }
 
 // batched tcgen05 GEMM (strides in elements); fp32 output when out_f32
@@ -44,12 +63,14 @@ int gemm_batched(const void* A, int lda, long long sa, const void* W, int ldw, l
   g.act = VZ_ACT_NONE; g.row_mode = VZ_ROWS_PLAIN; g.rows_per = 0; g.force_simple = 0;
   g.batch = batch; g.out_f32 = out_f32;
   g.a_bstride = sa; g.w_bstride = sw; g.o_bstride = so; g.r_bstride = 0; g.bias_bstride = sbias;
+  g.ln_stats = nullptr; g.ln_colsum = nullptr; g.ln_np = 0; g.ln_eps = 0.f; g.stats_out = nullptr; g.stats_np = 0;
   return gemm_launch(g, st);
 }
 
 struct VitWs {
   void* hs[VZ_VIT_LAYERS + 1];
   void *xn, *qkv, *attn, *mid, *h;
+  float *statsA, *statsB;  // [M][<=16][2] partial row statistics (LayerNorm fused into the GEMMs)
   size_t total;
 };
 
@@ -65,6 +86,8 @@ VitWs vit_layout(void* base, int T) {
   w.attn = b.take(M * VZ_VIT_WIDTH * kB16);
   w.mid = b.take(M * VZ_VIT_WIDTH * kB16);
   w.h = b.take(M * VZ_VIT_MLP * kB16);
+  w.statsA = reinterpret_cast<float*>(b.take(M * 16 * 2 * sizeof(float)));
+  w.statsB = reinterpret_cast<float*>(b.take(M * 16 * 2 * sizeof(float)));
   w.total = b.off + 256;
   return w;
 }
@@ -143,20 +166,27 @@ extern "C" int vz_vit_forward(const vz_vit_weights* w, const void* patches, int 
               w->pos_emb, D, ws.mid, D, VZ_ROWS_PATCH_EMBED, VZ_VIT_PATCHES, simple, st));
   VZ_TRY(layernorm_launch(ws.mid, D, w->pre_ln_g, w->pre_ln_b, ws.hs[0], D, M, D, 1e-5f, nullptr, 1, st));
 
+  // layer_norm1 / layer_norm2 never run as kernels: every GEMM that writes the residual stream also
+  // writes per-row partial (sum, sum of squares); the next Linear (gamma/beta folded into its weights)
+  // finishes the normalisation in its epilogue.  hs[0] comes from a LayerNorm kernel, so its
+  // statistics come from a row kernel (one partial).
+  const int np_gemm = simple ? 1 : gemm_stats_partials(M, D);
+  if (np_gemm > 16) return VZ_ERR_UNSUPPORTED;
+  VZ_TRY(row_stats_launch(ws.hs[0], D, M, D, ws.statsA, st));
+  int npA = 1;
   for (int l = 0; l < VZ_VIT_LAYERS; ++l) {
     const vz_vit_layer& L = w->layers[l];
     const void* x = ws.hs[l];
-    VZ_TRY(layernorm_launch(x, D, L.ln1_g, L.ln1_b, ws.xn, D, M, D, 1e-5f, nullptr, 1, st));
-    VZ_TRY(gemm(ws.xn, D, L.w_qkv, D, M, 3 * D, D, L.b_qkv, VZ_ACT_NONE, nullptr, 0, ws.qkv, 3 * D,
-                VZ_ROWS_PLAIN, 0, simple, st));
+    VZ_TRY(gemm_ln(x, D, L.w_qkv, D, M, 3 * D, D, L.b_qkv, VZ_ACT_NONE, nullptr, 0, ws.qkv, 3 * D, ws.statsA, npA,
+                   L.s_qkv, nullptr, 0, simple, st));
     VZ_TRY(vz_vit_attention(ws.qkv, ws.attn, T, -1, st));
-    VZ_TRY(gemm(ws.attn, D, L.w_o, D, M, D, D, L.b_o, VZ_ACT_NONE, x, D, ws.mid, D, VZ_ROWS_PLAIN, 0,
-                simple, st));
-    VZ_TRY(layernorm_launch(ws.mid, D, L.ln2_g, L.ln2_b, ws.xn, D, M, D, 1e-5f, nullptr, 1, st));
-    VZ_TRY(gemm(ws.xn, D, L.w_fc1, D, M, VZ_VIT_MLP, D, L.b_fc1, VZ_ACT_QUICK_GELU, nullptr, 0, ws.h,
-                VZ_VIT_MLP, VZ_ROWS_PLAIN, 0, simple, st));
-    VZ_TRY(gemm(ws.h, VZ_VIT_MLP, L.w_fc2, VZ_VIT_MLP, M, D, VZ_VIT_MLP, L.b_fc2, VZ_ACT_NONE, ws.mid, D,
-                ws.hs[l + 1], D, VZ_ROWS_PLAIN, 0, simple, st));
+    VZ_TRY(gemm_ln(ws.attn, D, L.w_o, D, M, D, D, L.b_o, VZ_ACT_NONE, x, D, ws.mid, D, nullptr, 0, nullptr,
+                   ws.statsB, np_gemm, simple, st));
+    VZ_TRY(gemm_ln(ws.mid, D, L.w_fc1, D, M, VZ_VIT_MLP, D, L.b_fc1, VZ_ACT_QUICK_GELU, nullptr, 0, ws.h,
+                   VZ_VIT_MLP, ws.statsB, np_gemm, L.s_fc1, nullptr, 0, simple, st));
+    VZ_TRY(gemm_ln(ws.h, VZ_VIT_MLP, L.w_fc2, VZ_VIT_MLP, M, D, VZ_VIT_MLP, L.b_fc2, VZ_ACT_NONE, ws.mid, D,
+                   ws.hs[l + 1], D, nullptr, 0, nullptr, ws.statsA, np_gemm, simple, st));
+    npA = np_gemm;
   }
   // hidden_states[-21:], CLS dropped, 4 x mean-of-5 + last (+ pre_norm)
   VZ_TRY(fuse_launch(&ws.hs[4], T, norm_g, norm_b, fused_out, st));

@@ -249,7 +249,33 @@ softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, 
   }
 }
 
+// (sum, sum of squares) of every row -> stats[m][0..1]  (one partial per row; the debug GEMM path and
+// the first ViT layer use it where no producing GEMM epilogue exists).  One warp per row.
+__global__ void __launch_bounds__(256)
+row_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int M, int D, float* __restrict__ stats) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (m >= M) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane * 8; c < D; c += 256) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + (size_t)m * ldx + c), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s1 += f[i]; s2 = fmaf(f[i], f[i], s2); }
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) { stats[(size_t)m * 2] = s1; stats[(size_t)m * 2 + 1] = s2; }
+}
+
 }  // namespace
+
+int row_stats_launch(const void* x, int ldx, int M, int D, float* stats, cudaStream_t st) {
+  if (D % 8) return VZ_ERR_UNSUPPORTED;
+  row_stats_kernel<<<(M + 7) / 8, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, D, stats);
+  VZ_LAUNCH_CHECK();
+  return VZ_OK;
+}
 
 int transpose_launch(const void* in, void* out, int batch, int R, int C, cudaStream_t st) {
   dim3 grid((C + 63) / 64, (R + 63) / 64, batch);

@@ -97,7 +97,9 @@ class CLIPVisionTowerB200(nn.Module):
 
     def _pack(self, sd: Dict[str, torch.Tensor], dev):
         """HF layout -> kernel layout: bf16 weights ([N,K] row-major, q/k/v stacked, conv weight
-        flattened (c,ky,kx) and K-padded 588->592), fp32 biases and LayerNorm parameters."""
+        flattened (c,ky,kx) and K-padded 588->592), fp32 biases; layer_norm1/2 folded into the
+        following Linear (gamma into the weight, beta into the bias, plus the column sums the fused
+        epilogue needs)."""
         sd = {k[len("vision_tower."):] if k.startswith("vision_tower.") else k: v for k, v in sd.items()}
         p = "vision_model."
         bf = lambda t: t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
@@ -113,14 +115,20 @@ class CLIPVisionTowerB200(nn.Module):
         P["pre_ln_b"] = f32(sd[p + "pre_layrnorm.bias"])
         for l in range(LAYERS):
             q = f"{p}encoder.layers.{l}."
-            P[f"{l}.w_qkv"] = bf(torch.cat([sd[q + "self_attn.q_proj.weight"], sd[q + "self_attn.k_proj.weight"],
-                                            sd[q + "self_attn.v_proj.weight"]], 0))
-            P[f"{l}.b_qkv"] = f32(torch.cat([sd[q + "self_attn.q_proj.bias"], sd[q + "self_attn.k_proj.bias"],
-                                             sd[q + "self_attn.v_proj.bias"]], 0))
+            # LayerNorm folding (csrc/vz_gemm.cu): LN(x) W^T + b = rstd (x W'^T - mu colsum(W')) + b'
+            def fold(W, b, g, beta):
+                W32, g32, beta32 = W.detach().float().to(dev), g.detach().float().to(dev), beta.detach().float().to(dev)
+                Wf = (W32 * g32[None, :]).to(torch.bfloat16).contiguous()
+                return Wf, (b.detach().float().to(dev) + W32 @ beta32).contiguous(), Wf.float().sum(1).contiguous()
+            Wqkv = torch.cat([sd[q + "self_attn.q_proj.weight"], sd[q + "self_attn.k_proj.weight"],
+                              sd[q + "self_attn.v_proj.weight"]], 0)
+            bqkv = torch.cat([sd[q + "self_attn.q_proj.bias"], sd[q + "self_attn.k_proj.bias"],
+                              sd[q + "self_attn.v_proj.bias"]], 0)
+            P[f"{l}.w_qkv"], P[f"{l}.b_qkv"], P[f"{l}.s_qkv"] = fold(Wqkv, bqkv, sd[q + "layer_norm1.weight"],
+                                                                    sd[q + "layer_norm1.bias"])
             P[f"{l}.w_o"], P[f"{l}.b_o"] = bf(sd[q + "self_attn.out_proj.weight"]), f32(sd[q + "self_attn.out_proj.bias"])
-            P[f"{l}.ln1_g"], P[f"{l}.ln1_b"] = f32(sd[q + "layer_norm1.weight"]), f32(sd[q + "layer_norm1.bias"])
-            P[f"{l}.ln2_g"], P[f"{l}.ln2_b"] = f32(sd[q + "layer_norm2.weight"]), f32(sd[q + "layer_norm2.bias"])
-            P[f"{l}.w_fc1"], P[f"{l}.b_fc1"] = bf(sd[q + "mlp.fc1.weight"]), f32(sd[q + "mlp.fc1.bias"])
+            P[f"{l}.w_fc1"], P[f"{l}.b_fc1"], P[f"{l}.s_fc1"] = fold(sd[q + "mlp.fc1.weight"], sd[q + "mlp.fc1.bias"],
+                                                                    sd[q + "layer_norm2.weight"], sd[q + "layer_norm2.bias"])
             P[f"{l}.w_fc2"], P[f"{l}.b_fc2"] = bf(sd[q + "mlp.fc2.weight"]), f32(sd[q + "mlp.fc2.bias"])
         self._packed = P
         self._rebuild_pointers()
@@ -140,8 +148,7 @@ class CLIPVisionTowerB200(nn.Module):
         w.patch_w, w.class_emb, w.pos_emb = P["patch_w"].data_ptr(), P["class_emb"].data_ptr(), P["pos_emb"].data_ptr()
         w.pre_ln_g, w.pre_ln_b = P["pre_ln_g"].data_ptr(), P["pre_ln_b"].data_ptr()
         for l in range(LAYERS):
-            for name in ("ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_g", "ln2_b", "w_fc1", "b_fc1",
-                         "w_fc2", "b_fc2"):
+            for name in ("w_qkv", "b_qkv", "s_qkv", "w_o", "b_o", "w_fc1", "b_fc1", "s_fc1", "w_fc2", "b_fc2"):
                 setattr(w.layers[l], name, P[f"{l}.{name}"].data_ptr())
         self._w = w
 
