@@ -18,7 +18,7 @@ SHAPES = [("qkv", M, 3072, 1024, 0, 0, 1), ("o", M, 1024, 1024, 0, 1, 1), ("fc1"
           ("ffn1", 1280, 8192, 4096, 2, 0, 1), ("ffn2", 1280, 4096, 8192, 0, 1, 1), ("ca_q", 1280, 4096, 4096, 0, 0, 1)]
 
 
-def run(name, M, N, K, act, res, reps=20):
+def run(name, M, N, K, act, res, reps=20, ln=False, stats=False):
     A = torch.randn((M, K), device="cuda").to(torch.bfloat16)
     W = (torch.randn((N, K), device="cuda") * K ** -0.5).to(torch.bfloat16)
     bias = torch.randn(N, device="cuda")
@@ -29,6 +29,19 @@ def run(name, M, N, K, act, res, reps=20):
     g.residual = R.data_ptr() if res else None
     g.M, g.N, g.K, g.lda, g.ldw, g.ldo, g.ldr = M, N, K, K, K, N, N
     g.act = act
+    keep = []
+    if ln:
+        npp = 8
+        st = torch.rand((M, npp, 2), device="cuda") + 1.0
+        st[:, :, 1] += 200.0
+        cs = torch.randn(N, device="cuda")
+        keep += [st, cs]
+        g.ln_stats, g.ln_colsum, g.ln_np, g.ln_eps = st.data_ptr(), cs.data_ptr(), npp, 1e-5
+    if stats:
+        npp = lib.vz_gemm_stats_partials(M, N)
+        so = torch.empty((M, npp, 2), device="cuda")
+        keep.append(so)
+        g.stats_out, g.stats_np = so.data_ptr(), npp
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     ts = []
     for i in range(reps + 3):
@@ -42,8 +55,17 @@ def run(name, M, N, K, act, res, reps=20):
             ts.append(e0.elapsed_time(e1))
     ts.sort()
     med = ts[len(ts) // 2]
-    print(f"{name:7s} M={M:6d} N={N:6d} K={K:5d} act={act} res={res}: {med * 1e3:8.1f} us  {2.0 * M * N * K / med / 1e9:7.1f} TFLOP/s")
+    name = name + ("+ln" if ln else "") + ("+st" if stats else "")
+    print(f"{name:10s} M={M:6d} N={N:6d} K={K:5d} act={act} res={res}: {med * 1e3:8.1f} us  {2.0 * M * N * K / med / 1e9:7.1f} TFLOP/s")
 
 
-for s in SHAPES:
-    run(*s[:6])
+if os.environ.get("VZ_BENCH_LN") == "1":
+    for nm in ("qkv", "fc1"):
+        sh = [x for x in SHAPES if x[0] == nm][0]
+        run(*sh[:6]); run(*sh[:6], ln=True)
+    for nm in ("o", "fc2"):
+        sh = [x for x in SHAPES if x[0] == nm][0]
+        run(*sh[:6]); run(*sh[:6], stats=True)
+else:
+    for s in SHAPES:
+        run(*s[:6])

@@ -100,7 +100,10 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   return x;
 }
 
-template <int BN>
+// Epilogue features are template parameters (ACT activation, RES residual, LN fused LayerNorm
+// consumer, STATS fused LayerNorm producer, F32 fp32 output): the epilogue sits at the register
+// limit of a 384-thread CTA, so each instantiation only carries the state it needs.
+template <int BN, int ACT, bool RES, bool LN, bool STATS, bool F32>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                          const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
@@ -208,12 +211,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk, bz);
       const int m_base = m_blk * BM + q * 32;
       const float* bias_b = p.bias ? p.bias + (size_t)bz * p.bias_bstride : nullptr;
-      const __nv_bfloat16* res_b = p.residual ? p.residual + (size_t)bz * p.r_bstride : nullptr;
+      const __nv_bfloat16* res_b = RES ? p.residual + (size_t)bz * p.r_bstride : nullptr;
       __nv_bfloat16* out_b = p.out + (size_t)bz * p.o_bstride;
       // fused LayerNorm (consumer): mean / rstd of this lane's own row from the producer's partials,
       // summed in a fixed order (deterministic)
       float ln_mu = 0.f, ln_rstd = 1.f;
-      if (p.ln_stats && m_base + lane < p.M) {
+      if (LN && m_base + lane < p.M) {
         const float2* ps = reinterpret_cast<const float2*>(p.ln_stats) + (size_t)(m_base + lane) * p.ln_np;
         float s1 = 0.f, s2 = 0.f;
         for (int i = 0; i < p.ln_np; ++i) { const float2 t = ps[i]; s1 += t.x; s2 += t.y; }
@@ -253,7 +256,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         }
         cp_async_commit();
       };
-      if (res_b && n_blk * BN + half * 32 < p.N) prefetch_residual(n_blk * BN + half * 32, cc);
+      if (RES && n_blk * BN + half * 32 < p.N) prefetch_residual(n_blk * BN + half * 32, cc);
       mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -264,7 +267,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         uint8_t* stg = sEpi + e * EPI_STAGE_BYTES + (cc & 1u) * 2048u;  // shadows the warp base on purpose
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_row + c * 32, r);
-        if (res_b) {
+        if (RES) {
           const bool more = (c + 2 < BN / 32) && (col0 + 64 < p.N);
           if (more) { prefetch_residual(col0 + 64, cc + 1); cp_async_wait<1>(); }
           else cp_async_wait<0>();
@@ -273,7 +276,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (p.ln_stats) {
+        if (LN) {
           // LN(x) W^T + b  ==  rstd * (x W'^T - mu * colsum(W')) + b'   (gamma folded into W', beta into b')
           const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + col0);
           const float4* b4 = reinterpret_cast<const float4*>(bias_b + col0);
@@ -293,11 +296,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
           }
         }
-        if (p.act != VZ_ACT_NONE) {
+        if (ACT != VZ_ACT_NONE) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], p.act);
+          for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], ACT);
         }
-        if (p.out_f32) {
+        if (F32) {
           // fp32 output (attention scores): 128 B per row, 8 chunks swizzled by row & 7; stores cover
           // 4 rows x 128 B per instruction
           uint8_t* stg = sEpi + e * EPI_STAGE_BYTES;  // fp32 rows need the warp's whole 4 KB
@@ -318,7 +321,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           __syncwarp();
           continue;
         }
-        if (res_b) {
+        if (RES) {
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -329,7 +332,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             v[8 * i + 6] += bf16_lo(w.w); v[8 * i + 7] += bf16_hi(w.w);
           }
         }
-        if (p.stats_out) {
+        if (STATS) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) { st1 += v[i]; st2 = fmaf(v[i], v[i], st2); }
         }
@@ -356,7 +359,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
-      if (p.stats_out && m_base + lane < p.M)
+      if (STATS && m_base + lane < p.M)
         reinterpret_cast<float2*>(p.stats_out)[(size_t)(m_base + lane) * p.stats_np + n_blk * 2 + half] =
             make_float2(st1, st2);
     }
@@ -456,7 +459,7 @@ int make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int
   return VZ_OK;
 }
 
-template <int BN>
+template <int BN, int ACT, bool RES, bool LN, bool STATS, bool F32>
 int launch_tc(const vz_gemm_args& a, const GemmDev& p, int num_sms, cudaStream_t st) {
   using C = Cfg<BN>;
   CUtensorMap tmA, tmB;
@@ -464,7 +467,7 @@ int launch_tc(const vz_gemm_args& a, const GemmDev& p, int num_sms, cudaStream_t
   VZ_TRY(make_tmap(&tmB, a.W, a.N, a.K, a.ldw, BN, a.batch, a.w_bstride));
   static bool attr_done = false;  // idempotent attribute; benign race
   if (!attr_done) {
-    VZ_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>,
+    VZ_CUDA_CHECK(cudaFuncSetAttribute((gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32>),
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_done = true;
   }
@@ -485,10 +488,35 @@ int launch_tc(const vz_gemm_args& a, const GemmDev& p, int num_sms, cudaStream_t
     g_prof.flops.push_back(2.0 * a.M * (double)a.N * a.K * p.batch);
     VZ_CUDA_CHECK(cudaEventRecord(e0, st));
   }
-  gemm_bf16_tcgen05_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+  gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32><<<grid, kThreads, C::SMEM_BYTES, st>>>(tmA, tmB, p);
   VZ_LAUNCH_CHECK();
   if (e1) VZ_CUDA_CHECK(cudaEventRecord(e1, st));
   return VZ_OK;
+}
+
+// pick the epilogue instantiation for the requested feature combination
+template <int BN>
+int launch_bn(const vz_gemm_args& a, const GemmDev& p, int num_sms, cudaStream_t st) {
+  const int act = a.act;
+  const bool res = a.residual != nullptr, ln = a.ln_stats != nullptr, stt = a.stats_out != nullptr, f32 = a.out_f32 != 0;
+#define VZ_GO(ACT, RES, LN, ST, F32) return launch_tc<BN, ACT, RES, LN, ST, F32>(a, p, num_sms, st)
+  if (f32) { if (act || res || ln || stt) return VZ_ERR_UNSUPPORTED; VZ_GO(0, false, false, false, true); }
+  if (stt) { if (!res || act || ln) return VZ_ERR_UNSUPPORTED; VZ_GO(0, true, false, true, false); }
+  if (ln) {
+    if (res) return VZ_ERR_UNSUPPORTED;
+    if (act == VZ_ACT_NONE) VZ_GO(0, false, true, false, false);
+    if (act == VZ_ACT_QUICK_GELU) VZ_GO(1, false, true, false, false);
+    VZ_GO(2, false, true, false, false);
+  }
+  if (res) {
+    if (act == VZ_ACT_NONE) VZ_GO(0, true, false, false, false);
+    if (act == VZ_ACT_QUICK_GELU) VZ_GO(1, true, false, false, false);
+    VZ_GO(2, true, false, false, false);
+  }
+  if (act == VZ_ACT_NONE) VZ_GO(0, false, false, false, false);
+  if (act == VZ_ACT_QUICK_GELU) VZ_GO(1, false, false, false, false);
+  VZ_GO(2, false, false, false, false);
+#undef VZ_GO
 }
 
 }  // namespace
@@ -596,14 +624,14 @@ int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
   const int bn = pick_tile_n(a.M, a.N, batch, num_sms);
   if (bn == 256) {
     p.num_n = a.N / 256;
-    return launch_tc<256>(a, p, num_sms, st);
+    return launch_bn<256>(a, p, num_sms, st);
   }
   if (bn == 192) {
     p.num_n = (a.N + 191) / 192;
-    return launch_tc<192>(a, p, num_sms, st);
+    return launch_bn<192>(a, p, num_sms, st);
   }
   p.num_n = (a.N + 127) / 128;
-  return launch_tc<128>(a, p, num_sms, st);
+  return launch_bn<128>(a, p, num_sms, st);
 }
 
 }  // namespace vz
