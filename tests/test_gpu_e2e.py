@@ -123,3 +123,33 @@ def test_bf16_eager_noise_floor(vision_path, seeded_weights, golden_dir):
           f"B200 path vs fp32: max_abs {e_ours:.4g} min cos {c_ours:.6f}")
     assert e_ours <= max(1.5 * e_eager, 0.05)
     assert (1 - c_ours) <= max(2 * (1 - c_eager), 1e-4)
+
+
+def test_sharded_path_world1_equals_unsharded(vision_path, golden_dir):
+    """The data-parallel entry point (plan on the global batch, encode the local shard, all-gather,
+    splice on dst) must give the same bits as the single-process call; world_size 1 over NCCL."""
+    import os
+    import torch.distributed as dist
+    import vision_zephyr_b200 as vz
+    lut = _lut(golden_dir)
+    imgs = [torch.from_numpy(synth_image(0, 1000, 900)).cuda(), torch.from_numpy(synth_image(1, 637, 336)).cuda()]
+    pb = vz.process_any_resolution_images(imgs, PINPOINTS_C3, lut, out_mode="patches")
+    ids = torch.randint(3, 32000, (2, 40), generator=torch.Generator().manual_seed(2)).cuda()
+    ids[0, 3] = -200
+    ids[1, 30] = -200
+    mask = torch.ones_like(ids)
+    mask[1, 35:] = 0
+    sizes = [(1000, 900), (637, 336)]
+    ref = vision_path.prepare_inputs_labels_for_multimodal(ids, None, mask, None, ids.clone(), pb, sizes)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1)
+    try:
+        got = vision_path.prepare_inputs_labels_for_multimodal_sharded(ids, None, mask, None, ids.clone(), pb,
+                                                                       pb.tiles_per_image, sizes)
+    finally:
+        if created:
+            dist.destroy_process_group()
+    assert torch.equal(ref[4], got[4]) and torch.equal(ref[5], got[5]) and torch.equal(ref[2], got[2])
