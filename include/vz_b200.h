@@ -318,6 +318,14 @@ int vz_splice_scatter(const int64_t* input_ids, const int64_t* labels, int B, in
                       int Lout, int pad_left, void* out_embeds, int64_t* out_labels,
                       uint8_t* out_mask, int64_t* out_pos, void* stream);
 
+/* "Next" row: the collator in front of the splice.
+ * DataCollatorForSupervisedDataset (train/train.py:657-707) from packed ragged rows:
+ * out_ids[b,s] = s < len_b ? flat_ids[offsets[b]+s] : pad_id, labels padded with IGNORE_INDEX, both
+ * truncated to S_out columns (S_out = min(max len, model_max_length), host-known),
+ * out_mask = out_ids != pad_id.                                                               */
+int vz_collate(const int64_t* flat_ids, const int64_t* flat_labels, const int32_t* offsets, int B, int S_out,
+               int64_t pad_id, int64_t* out_ids, int64_t* out_labels, uint8_t* out_mask, void* stream);
+
 /* Merge only (vis_zephyr_arch.py:396-473) for one slot list: out rows [sum n_rows, D].          */
 int vz_merge_rows(const void* vis, int ldv, const void* image_newline, int D, int elem_bytes,
                   const vz_slot_desc* slots, int n_slots, const int32_t* out_row_base, void* out,

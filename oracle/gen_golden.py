@@ -10,6 +10,7 @@ What is pinned
   golden_merge.npz    _process_image_patches row maps for flat / spatial / spatial_unpad
   golden_splice.npz   prepare_inputs_labels_for_multimodal index/label/mask/position outputs with a
                       stubbed encode_images (integer-coded features)
+  golden_text.npz     tokenizer_image_token (stub word-hash tokenizer) and DataCollatorForSupervisedDataset
   golden_model.npz    CLIPVisionTower + QFormer outputs (fp32, seeded weights from oracle/weights.py)
                       for config 1 (one 336x336 tile, 63 text tokens) and a 5-tile anyres image
 """
@@ -253,6 +254,58 @@ def gen_splice():
 
 
 # --------------------------------------------------------------------------------------------
+class StubTokenizer:
+    """word-hash tokenizer: enough to drive tokenizer_image_token and the collator deterministically."""
+
+    def __init__(self, with_bos=True, pad_token_id=2, model_max_length=40):
+        self.bos_token_id, self.pad_token_id, self.model_max_length, self.with_bos = 1, pad_token_id, model_max_length, with_bos
+
+    def __call__(self, text):
+        ids = ([self.bos_token_id] if self.with_bos else []) + [3 + (sum(map(ord, w)) % 997) for w in text.split()]
+        return types.SimpleNamespace(input_ids=ids)
+
+
+TEXT_PROMPTS = ["<image>\nwhat is shown here ?", "describe <image> and also <image> please", "no picture at all",
+                "<image>", "tail image <image>", "", "a <image><image> b"]
+
+
+def gen_text():
+    stub_shapely()
+    from vis_zephyr.model.mm_utils import tokenizer_image_token
+    # vis_zephyr/train/vis_zephyr_trainer.py imports a symbol that transformers 5.5 no longer has; the
+    # collator does not use the trainer, so a placeholder module lets train.py import unmodified
+    fake = types.ModuleType("vis_zephyr.train.vis_zephyr_trainer")
+    fake.VisZephyrTrainer = object
+    fake.maybe_zero = lambda *a, **k: None
+    sys.modules["vis_zephyr.train.vis_zephyr_trainer"] = fake
+    from vis_zephyr.train.train import DataCollatorForSupervisedDataset
+    out = {}
+    for bi, with_bos in enumerate([True, False]):
+        tok = StubTokenizer(with_bos)
+        for pi, prompt in enumerate(TEXT_PROMPTS):
+            out[f"tok{bi}_{pi}"] = np.array(tokenizer_image_token(prompt, tok), np.int64)
+    rng = np.random.default_rng(11)
+    for ci, (B, max_len, mml) in enumerate([(4, 30, 40), (3, 70, 40), (1, 5, 40), (6, 40, 17)]):
+        tok = StubTokenizer(True, 2, mml)
+        inst = []
+        for b in range(B):
+            n = int(rng.integers(1, max_len + 1))
+            ids = rng.integers(0, 50, n).astype(np.int64)          # includes real tokens equal to the pad id 2
+            ids[rng.integers(0, n)] = -200
+            labels = ids.copy()
+            labels[: n // 2] = -100
+            inst.append(dict(input_ids=torch.from_numpy(ids), labels=torch.from_numpy(labels)))
+            out[f"col{ci}_ids{b}"], out[f"col{ci}_labels{b}"] = ids, labels
+        batch = DataCollatorForSupervisedDataset(tokenizer=tok)(inst)
+        out[f"col{ci}_cfg"] = np.array([B, 2, mml], np.int64)
+        out[f"col{ci}_out_ids"] = batch["input_ids"].numpy()
+        out[f"col{ci}_out_labels"] = batch["labels"].numpy()
+        out[f"col{ci}_out_mask"] = batch["attention_mask"].numpy()
+    np.savez_compressed(os.path.join(GOLD, "golden_text.npz"), **out)
+    print("golden_text.npz written", len(out))
+
+
+# --------------------------------------------------------------------------------------------
 def gen_model():
     import tempfile
     from PIL import Image
@@ -370,9 +423,10 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
-    todo = a.only.split(",") if a.only else ["pixels", "vip", "merge", "splice", "model"]
+    todo = a.only.split(",") if a.only else ["pixels", "vip", "merge", "splice", "text", "model"]
     if "pixels" in todo: gen_pixels()
     if "vip" in todo: gen_vip()
     if "merge" in todo: gen_merge()
     if "splice" in todo: gen_splice()
+    if "text" in todo: gen_text()
     if "model" in todo and not a.skip_model: gen_model()

@@ -115,3 +115,31 @@ def splice(input_ids, attention_mask, labels, position_ids_given, embed, image_f
         out_m[b, sl] = True
         out_p[b, sl] = np.arange(n)
     return out_e, out_l, out_m, out_p, np.array(lengths)
+
+
+def collate(instances, pad_token_id, model_max_length):
+    """DataCollatorForSupervisedDataset (vis_zephyr/train/train.py:657-707): returns ids, labels, mask."""
+    B = len(instances)
+    L = max(len(x["input_ids"]) for x in instances)
+    ids = np.full((B, L), pad_token_id, np.int64)
+    labels = np.full((B, L), IGNORE_INDEX, np.int64)
+    for b, x in enumerate(instances):
+        n = len(x["input_ids"])
+        ids[b, :n] = x["input_ids"]
+        labels[b, :n] = x["labels"]
+    ids, labels = ids[:, :model_max_length], labels[:, :model_max_length]
+    return ids, labels, ids != pad_token_id
+
+
+def tokenizer_image_token(prompt, tokenizer, image_token_index=IMAGE_TOKEN_INDEX):
+    """vis_zephyr/model/mm_utils.py:91-128, followed step by step (separator insertion, offset trick)."""
+    chunks = [tokenizer(c).input_ids for c in prompt.split("<image>")]
+    out, offset = [], 0
+    if len(chunks) > 0 and len(chunks[0]) > 0 and chunks[0][0] == tokenizer.bos_token_id:
+        offset = 1
+        out.append(chunks[0][0])
+    seps = [[image_token_index] * (offset + 1)] * len(chunks)
+    inter = [e for pair in zip(chunks, seps) for e in pair][:-1]
+    for x in inter:
+        out.extend(x[offset:])
+    return out

@@ -15,6 +15,7 @@ from .vision_tower import CLIPVisionTowerB200, build_vision_tower
 from .projector import QFormerB200, TextPack, build_multimodal_projector, build_vision_projector
 from .arch import (VisZephyrB200MetaModel, VisZephyrB200MetaForCausalLM, merge_rows, splice_plan,
                    splice_scatter, text_gather)
+from .text_inputs import tokenizer_image_token, collate_supervised
 from . import dist as parallel
 
 __all__ = [
@@ -23,4 +24,5 @@ __all__ = [
     "VisualPrompt", "VisZephyrB200MetaModel", "VisZephyrB200MetaForCausalLM",
     "process_any_resolution_images", "process_fixed_images", "clip_lut", "lut_from_processor",
     "calculate_grid_shape", "select_best_fit_resolution", "unpad_bounds", "merge_rows",
+    "tokenizer_image_token", "collate_supervised",
 ]

@@ -401,3 +401,40 @@ extern "C" int vz_merge_rows(const void* vis, int ldv, const void* image_newline
   VZ_LAUNCH_CHECK();
   return VZ_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// collate (next row of the scope table): DataCollatorForSupervisedDataset, train/train.py:657-707
+// pad_sequence(input_ids, pad_token_id), pad_sequence(labels, IGNORE_INDEX), truncate to
+// model_max_length, attention_mask = input_ids.ne(pad_token_id) -- from packed ragged rows.
+// ------------------------------------------------------------------------------------------
+namespace vz {
+namespace {
+__global__ void __launch_bounds__(256)
+collate_kernel(const int64_t* __restrict__ flat_ids, const int64_t* __restrict__ flat_labels,
+               const int32_t* __restrict__ offsets, int S_out, int64_t pad_id, int64_t* __restrict__ out_ids,
+               int64_t* __restrict__ out_labels, uint8_t* __restrict__ out_mask) {
+  const int b = blockIdx.y;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S_out) return;
+  const int off = offsets[b], len = offsets[b + 1] - off;
+  const bool in = s < len;
+  const int64_t id = in ? flat_ids[off + s] : pad_id;
+  const size_t o = (size_t)b * S_out + s;
+  out_ids[o] = id;
+  out_labels[o] = in ? flat_labels[off + s] : (int64_t)VZ_IGNORE_INDEX;
+  out_mask[o] = id != pad_id;  // like the reference: a real token equal to the pad id is masked too
+}
+}  // namespace
+}  // namespace vz
+
+extern "C" int vz_collate(const int64_t* flat_ids, const int64_t* flat_labels, const int32_t* offsets, int B,
+                          int S_out, int64_t pad_id, int64_t* out_ids, int64_t* out_labels, uint8_t* out_mask,
+                          void* stream) {
+  if (!flat_ids || !flat_labels || !offsets || !out_ids || !out_labels || !out_mask || B <= 0 || S_out <= 0)
+    return VZ_ERR_BAD_ARG;
+  dim3 grid((S_out + 255) / 256, B);
+  vz::collate_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(flat_ids, flat_labels, offsets, S_out,
+                                                                              pad_id, out_ids, out_labels, out_mask);
+  VZ_LAUNCH_CHECK();
+  return VZ_OK;
+}
