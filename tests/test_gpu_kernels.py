@@ -232,3 +232,14 @@ def test_gemm_fused_layernorm_producer_and_consumer():
     torch.cuda.synchronize()
     ref = torch.nn.functional.layer_norm(x.float(), (D,), gamma, beta, 1e-5) @ W.float().t() + b
     _check(out, ref, "fused LayerNorm + GEMM", tol=2.0 ** -6)
+
+
+@pytest.mark.parametrize("M,N,K,act,res", [(9000, 3072, 1024, 0, False), (10050, 1024, 4096, 0, True),
+                                           (9000, 4096, 1024, 1, False), (9000, 1024, 1024, 2, True)])
+def test_gemm_two_cta_form(M, N, K, act, res):
+    """large problems take the cta_group::2 form (256-row pair tiles); ragged M tail included"""
+    A, W = _rand((M, K), 1.0, 51), _rand((N, K), K ** -0.5, 52)
+    bias = torch.randn(N, device="cuda") * 0.3
+    R = _rand((M, N), 1.0, 53) if res else None
+    out = run_gemm(A, W, bias=bias, act=act, residual=R)
+    _check(out, ref_gemm(A, W, bias, act, R), f"2-CTA gemm {M}x{N}x{K} act={act} res={res}")

@@ -42,12 +42,14 @@ constexpr int kThreads = 128 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA, warp2 T
 constexpr int EPI_STAGE_BYTES = 32 * 128;  // per epilogue warp: 32 rows x 32 values (bf16 or f32), chunk-swizzled
 constexpr int GROUP_N = 8;    // n-blocks per rasterisation band (keeps the W band + A strip in L2)
 
-template <int BN>
+// TWO = 2-CTA form (cta_group::2): a pair of SMs computes a 256 x BN tile, each CTA stages its own 128
+// A rows and HALF of the B tile, which cuts the shared-memory traffic per FLOP by a third.
+template <int BN, bool TWO = false>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (TWO ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 4 : 6);
+  static constexpr int STAGES = TWO ? 6 : ((BN == 256) ? 4 : (BN == 192 ? 4 : 6));
   static constexpr int TMEM_COLS = (BN == 192) ? 512 : 2 * BN;  // two accumulator stages (power of two)
   static constexpr int BAR_BYTES = 256;
   static constexpr int EPI_BYTES = kEpiWarps * EPI_STAGE_BYTES;
@@ -103,11 +105,17 @@ __device__ __forceinline__ float act_apply(float x, int act) {
 // Epilogue features are template parameters (ACT activation, RES residual, LN fused LayerNorm
 // consumer, STATS fused LayerNorm producer, F32 fp32 output): the epilogue sits at the register
 // limit of a 384-thread CTA, so each instantiation only carries the state it needs.
-template <int BN, int ACT, bool RES, bool LN, bool STATS, bool F32>
+template <int BN, int ACT, bool RES, bool LN, bool STATS, bool F32, bool TWO>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                          const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, TWO>;
+  // 2-CTA form: `rank` is this CTA's position in its pair; tiles are 256 rows tall and the pair index
+  // walks them.  1-CTA form: rank 0, every CTA is its own "pair".
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;
+  const int worker = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int TILE_M = TWO ? 2 * BM : BM;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -131,18 +139,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], TWO ? 2 : 1);   // 2-CTA: one arrive per CTA's producer (on the leader's barrier)
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], TWO ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (of the pair)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 2) {
+    if (TWO) tmem_alloc_2cta(tmem_slot, C::TMEM_COLS);
+    else tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if (TWO) cluster_sync_all();   // the peer's barriers must exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -150,24 +162,34 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     // ============================ TMA producer ============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < total_tiles; tile += n_workers) {
         int m_blk, n_blk, bz;
         tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk, bz);
         for (int kb = 0; kb < p.num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
-          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          tma_load_3d(&tmA, &full_bar[stage], sA + stage * C::A_BYTES, kb * BK, m_blk * BM, bz);
-          tma_load_3d(&tmB, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK, n_blk * BN, bz);
+          if (TWO) {
+            // both CTAs' bytes are counted on the leader's barrier
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+            else mbar_arrive_cluster(&full_bar[stage], 0);
+            tma_load_3d_2cta(&tmA, &full_bar[stage], sA + stage * C::A_BYTES, kb * BK,
+                             m_blk * TILE_M + (int)rank * BM, bz);
+            tma_load_3d_2cta(&tmB, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK,
+                             n_blk * BN + (int)rank * (BN / 2), bz);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            tma_load_3d(&tmA, &full_bar[stage], sA + stage * C::A_BYTES, kb * BK, m_blk * BM, bz);
+            tma_load_3d(&tmB, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK, n_blk * BN, bz);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    if (lane == 0 && rank == 0) {   // 2-CTA: only the leader issues; the MMA spans both SMs
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < total_tiles; tile += n_workers) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -179,13 +201,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 32 B (16 bf16) along K inside the swizzle atom: +2 in the (addr>>4) field
-            umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+            if (TWO) umma_bf16_2cta(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                    (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs) once these MMAs retire
+          if (TWO) umma_commit_2cta(&empty_bar[stage], 3);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (TWO) umma_commit_2cta(&tfull_bar[acc], 3);
+        else umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -206,10 +234,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     const int co_r = lane >> 2, co_j = lane & 3;
     uint32_t acc = 0, acc_phase = 0;
     uint32_t cc = 0;  // chunk counter: selects which half of the warp's staging area is current
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < total_tiles; tile += n_workers) {
       int m_blk, n_blk, bz;
       tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk, bz);
-      const int m_base = m_blk * BM + q * 32;
+      const int m_base = m_blk * TILE_M + (int)rank * BM + q * 32;
       const float* bias_b = p.bias ? p.bias + (size_t)bz * p.bias_bstride : nullptr;
       const __nv_bfloat16* res_b = RES ? p.residual + (size_t)bz * p.r_bstride : nullptr;
       __nv_bfloat16* out_b = p.out + (size_t)bz * p.o_bstride;
@@ -356,7 +384,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (TWO) mbar_arrive_cluster(&tempty_bar[acc], 0);   // the leader's MMA thread owns the wait
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
       if (STATS && m_base + lane < p.M)
@@ -367,9 +398,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 
   tc_fence_before();
   __syncthreads();
+  if (TWO) cluster_sync_all();   // neither CTA may leave (or free TMEM) while its peer still works
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (TWO) tmem_dealloc_2cta(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -459,20 +492,21 @@ int make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int
   return VZ_OK;
 }
 
-template <int BN, int ACT, bool RES, bool LN, bool STATS, bool F32>
+template <int BN, int ACT, bool RES, bool LN, bool STATS, bool F32, bool TWO>
 int launch_tc(const vz_gemm_args& a, const GemmDev& p, int num_sms, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, TWO>;
   CUtensorMap tmA, tmB;
   VZ_TRY(make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM, a.batch, a.a_bstride));
-  VZ_TRY(make_tmap(&tmB, a.W, a.N, a.K, a.ldw, BN, a.batch, a.w_bstride));
+  VZ_TRY(make_tmap(&tmB, a.W, a.N, a.K, a.ldw, TWO ? BN / 2 : BN, a.batch, a.w_bstride));
   static bool attr_done = false;  // idempotent attribute; benign race
   if (!attr_done) {
-    VZ_CUDA_CHECK(cudaFuncSetAttribute((gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32>),
+    VZ_CUDA_CHECK(cudaFuncSetAttribute((gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO>),
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_done = true;
   }
   const long tiles = (long)p.num_m * p.num_n * p.batch;
-  const int grid = tiles < num_sms ? (int)tiles : num_sms;
+  const int workers = TWO ? num_sms / 2 : num_sms;
+  const int grid = (tiles < workers ? (int)tiles : workers) * (TWO ? 2 : 1);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof.on) {
     std::lock_guard<std::mutex> lk(g_prof.mu);
@@ -488,18 +522,33 @@ int launch_tc(const vz_gemm_args& a, const GemmDev& p, int num_sms, cudaStream_t
     g_prof.flops.push_back(2.0 * a.M * (double)a.N * a.K * p.batch);
     VZ_CUDA_CHECK(cudaEventRecord(e0, st));
   }
-  gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32><<<grid, kThreads, C::SMEM_BYTES, st>>>(tmA, tmB, p);
-  VZ_LAUNCH_CHECK();
+  if (TWO) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VZ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO>, tmA, tmB, p));
+    count_launch();
+  } else {
+    gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO><<<grid, kThreads, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+    VZ_LAUNCH_CHECK();
+  }
   if (e1) VZ_CUDA_CHECK(cudaEventRecord(e1, st));
   return VZ_OK;
 }
 
 // pick the epilogue instantiation for the requested feature combination
-template <int BN>
+template <int BN, bool TWO = false>
 int launch_bn(const vz_gemm_args& a, const GemmDev& p, int num_sms, cudaStream_t st) {
   const int act = a.act;
   const bool res = a.residual != nullptr, ln = a.ln_stats != nullptr, stt = a.stats_out != nullptr, f32 = a.out_f32 != 0;
-#define VZ_GO(ACT, RES, LN, ST, F32) return launch_tc<BN, ACT, RES, LN, ST, F32>(a, p, num_sms, st)
+#define VZ_GO(ACT, RES, LN, ST, F32) return launch_tc<BN, ACT, RES, LN, ST, F32, TWO>(a, p, num_sms, st)
   if (f32) { if (act || res || ln || stt) return VZ_ERR_UNSUPPORTED; VZ_GO(0, false, false, false, true); }
   if (stt) { if (!res || act || ln) return VZ_ERR_UNSUPPORTED; VZ_GO(0, true, false, true, false); }
   if (ln) {
@@ -624,6 +673,13 @@ int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
   const int bn = pick_tile_n(a.M, a.N, batch, num_sms);
   if (bn == 256) {
     p.num_n = a.N / 256;
+    // 2-CTA (cta_group::2) form for the large problems: 256-row pair tiles, a third less smem traffic
+    static const int two_cta = []() { const char* e = getenv("VZ_GEMM_2CTA"); return e ? atoi(e) : 1; }();
+    const long pair_tiles = (long)((a.M + 255) / 256) * p.num_n * batch;
+    if (two_cta && a.M >= 256 && pair_tiles >= 2 * (num_sms / 2)) {
+      p.num_m = (a.M + 255) / 256;
+      return launch_bn<256, true>(a, p, num_sms, st);
+    }
     return launch_bn<256>(a, p, num_sms, st);
   }
   if (bn == 192) {
