@@ -54,6 +54,7 @@ class ClockSampler:
         self.index, self.rows, self.stop_flag, self.thread = index, [], False, None
         self.t0 = self.t1 = None
         self.max_mhz = None
+        self.power_limit_w = None
 
     def start(self):
         try:
@@ -63,6 +64,10 @@ class ClockSampler:
             idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
             h = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            try:
+                self.power_limit_w = pynvml.nvmlDeviceGetEnforcedPowerLimit(h) / 1000.0
+            except Exception:
+                self.power_limit_w = None
         except Exception:
             return
 
@@ -104,7 +109,7 @@ class ClockSampler:
         sm = [r[1] for r in rows]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(reasons), "samples": len(sm),
-                "power_w_max": max((r[3] for r in rows), default=None)}
+                "power_w_max": max((r[3] for r in rows), default=None), "power_limit_w": self.power_limit_w}
 
 
 def make_inputs(rank, n_local=IMAGES_PER_GPU):

@@ -600,7 +600,10 @@ int pick_tile_n(int M, int N, int batch, int num_sms) {
   const double cost256 = (double)((tiles256 + num_sms - 1) / num_sms);
   const double cost192 = 0.78 * (double)((tiles192 + num_sms - 1) / num_sms);
   int bn = 128;
-  if (N % 256 == 0 && tiles256 >= num_sms) bn = (cost192 < 0.9 * cost256 && tiles256 < 8 * num_sms) ? 192 : 256;
+  // (measured: with the 2-CTA form available, 256-wide tiles beat 128x192 on every shape of the path,
+  //  so 192 is only reachable through VZ_GEMM_BN)
+  (void)cost256; (void)cost192;
+  if (N % 256 == 0 && tiles256 >= num_sms) bn = 256;
   if (forced_bn == 256 && N % 256 == 0) bn = 256;
   if (forced_bn == 192 && N >= 192) bn = 192;
   if (forced_bn == 128) bn = 128;
@@ -676,7 +679,8 @@ int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
     // 2-CTA (cta_group::2) form for the large problems: 256-row pair tiles, a third less smem traffic
     static const int two_cta = []() { const char* e = getenv("VZ_GEMM_2CTA"); return e ? atoi(e) : 1; }();
     const long pair_tiles = (long)((a.M + 255) / 256) * p.num_n * batch;
-    if (two_cta && a.M >= 256 && pair_tiles >= 2 * (num_sms / 2)) {
+    static const long two_min = []() { const char* e = getenv("VZ_GEMM_2CTA_MIN"); return e ? atol(e) : 74L; }();
+    if (two_cta && a.M >= 256 && pair_tiles >= two_min) {
       p.num_m = (a.M + 255) / 256;
       return launch_bn<256, true>(a, p, num_sms, st);
     }
