@@ -323,8 +323,8 @@ def main():
         "roofline": {"kernel": "gemm_bf16_tcgen05_kernel", "bound": "tensor", "achieved": gemm_tflops, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf if peak_tf else None,
                      # dram__bytes_read+write per launch, ncu --set full, mean over the four ViT GEMM shapes
-                     # (profiles/r1_v5_gemm_full.md); algorithmic bytes of the same launches: 219 MB
-                     "traffic": 2.10e8, "traffic_source": "profiles/r1_v5_gemm_full.md",
+                     # (profiles/r1_v8_2cta_final.md); algorithmic bytes of the same launches: 219 MB
+                     "traffic": 2.175e8, "traffic_source": "profiles/r1_v8_2cta_final.md",
                      "peak_source": f"{pk_kind} bf16_tflops_sustained", "launches": int(n_g.value),
                      "gemm_ms_per_step": g_ms.value / args.steps,
                      "gemm_share_of_step": (g_ms.value / args.steps) / ms_step if ms_step else None},
