@@ -3,15 +3,20 @@
 // Q / K / V tiles arrive by TMA (128-byte swizzle) straight from the packed qkv activation.
 // Replaces HF CLIPAttention as called from vision_encoder/vision_encoder.py:101-105.
 //
-// One CTA = 128 query rows of one (tile, head); two CTAs are resident per SM.  Warps 0-3: softmax
-// (thread = query row = TMEM lane); warp 4: one thread issues the MMAs; warp 5: one thread issues TMA.
-// The 577 keys are walked in 10 blocks of 64 (the last one masked) with EVERYTHING double buffered --
-// two S accumulators in TMEM, two P tiles in smem, a 3-stage K/V ring -- so Q K_{j+1}^T is issued
-// before the softmax of block j starts and P_j V_j runs while the softmax of block j+1 computes:
+// PERSISTENT kernel, two CTAs per SM; a work item = 128 query rows of one (tile, head), items are
+// walked round-robin.  Warps 0-3: softmax (thread = query row = TMEM lane); warp 4: one thread
+// issues the MMAs; warp 5: one thread issues TMA.  The TMA and MMA threads run ahead ACROSS items
+// (Q is double buffered, the K/V ring and the S buffers never drain), so the load latency of an
+// item and the epilogue of the previous one overlap with softmax work instead of idling the SM.
+// The 577 keys are walked in 10 blocks of 64 -- the last one holds a single valid key and is computed
+// as a 16-key block -- with EVERYTHING double buffered -- two S accumulators in TMEM, two P tiles in
+// smem, a 3-stage K/V ring -- so Q K_{j+1}^T is issued before the softmax of block j starts and
+// P_j V_j runs while the softmax of block j+1 computes:
 //   S_j = Q K_j^T -> registers -> P_j = exp2((S_j - m) * scale) as bf16 in swizzled smem -> O += P_j V_j
 // The online softmax rescales the accumulator LAZILY: O (in TMEM) is only multiplied by
 // exp2(m_old - m_new) when the running maximum grew by more than 2^8, which is rare after the first
-// block, so O normally stays untouched in TMEM until the epilogue divides by the row sum.
+// block, so O normally stays untouched in TMEM until the epilogue divides by the row sum.  Softmax
+// warps without a valid query row (rows >= 577 of the last query block) only keep the barriers going.
 #include "vz_common.cuh"
 
 namespace vz {
@@ -21,12 +26,16 @@ constexpr int TOK = VZ_VIT_TOKENS;          // 577
 constexpr int HD = 64;                      // head dim
 constexpr int BQ = 128, BKV = 64;           // query rows per CTA, keys per block
 constexpr int NKB = (TOK + BKV - 1) / BKV;  // 10 key blocks (the last one holds a single valid key)
+constexpr int LAST_VALID = TOK - (NKB - 1) * BKV;  // 1 valid key in the last block ...
+constexpr int LAST_N = 16;                          // ... which is computed as a 16-key block
+static_assert(LAST_VALID >= 1 && LAST_VALID <= LAST_N, "last key block");
 constexpr int Q_BYTES = BQ * 128;           // 128 rows x 64 bf16
 constexpr int KV_BYTES = BKV * 128;         // 64 rows x 64 bf16
 constexpr int P_BYTES = BQ * 128;           // 128 rows x 64 keys bf16 (one swizzle atom wide)
 constexpr int KV_STAGES = 3;
-constexpr int SMEM_Q = 0;
-constexpr int SMEM_P = Q_BYTES;                               // 2 buffers
+constexpr int NQB = (TOK + BQ - 1) / BQ;    // 5 query blocks per (tile, head)
+constexpr int SMEM_Q = 0;                                     // 2 buffers (the next item's Q is prefetched)
+constexpr int SMEM_P = 2 * Q_BYTES;                           // 2 buffers
 constexpr int SMEM_RING = SMEM_P + 2 * P_BYTES;               // 3 x (K, V)
 constexpr int SMEM_BARS = SMEM_RING + KV_STAGES * 2 * KV_BYTES;
 constexpr int SMEM_TOTAL = SMEM_BARS + 256;
@@ -46,31 +55,143 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // accumulator is rescaled (FA-4 style lazy rescaling): keeps O untouched in TMEM most of the time.
 constexpr float kRescaleLog2 = 8.0f;
 
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+struct SoftmaxState {
+  float m_used = -INFINITY;   // maximum the exponentials are currently taken against
+  float l = 0.f;              // running row sum
+  float sl2;                  // softmax scale * log2(e)
+};
+
+// One key block of the online softmax for query row r: NCOL score columns are read from TMEM, the
+// first NVALID are real keys (the rest of the tile's last block belongs to the next tile).
+// g = this CTA's running key-block counter (across work items): buffer b = g & 1, use = g >> 1;
+// j = block index inside the item (the accumulator is only touched when j > 0).
+template <int NCOL, int NVALID>
+__device__ __forceinline__ void softmax_block(SoftmaxState& s, uint32_t g, int j, int r, uint32_t t_lane,
+                                              uint32_t tmem_base, uint32_t tmem_o, uint8_t* sP, uint64_t* bar_s_full,
+                                              uint64_t* bar_s_free, uint64_t* bar_p_full, uint64_t* bar_pv_done) {
+  static_assert(NCOL == 64 || NCOL == 16, "score columns per block");
+  const int lane = threadIdx.x & 31;
+  const uint32_t b = g & 1, use = g >> 1;
+  mbar_wait(&bar_s_full[b], use & 1, 600 + b);
+  tc_fence_after();
+  uint32_t v[NCOL];
+  if constexpr (NCOL == 64) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+      tmem_ld_32x32b_x32(tmem_base + t_lane + b * BKV + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+  } else {
+    tmem_ld_32x32b_x16(tmem_base + t_lane + b * BKV, v);
+  }
+  tmem_ld_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&bar_s_free[b]);
+  constexpr int NCH = NVALID >= 4 ? 4 : NVALID;   // independent max / sum chains
+  float bm4[NCH];
+#pragma unroll
+  for (int u = 0; u < NCH; ++u) bm4[u] = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NVALID; ++i) bm4[i % NCH] = fmaxf(bm4[i % NCH], __uint_as_float(v[i]));
+  float bm = bm4[0];
+#pragma unroll
+  for (int u = 1; u < NCH; ++u) bm = fmaxf(bm, bm4[u]);
+  // lazy rescale: only when the running maximum grows by more than 2^kRescaleLog2
+  float alpha = 1.f;
+  const bool need = (bm - s.m_used) * s.sl2 > kRescaleLog2;   // true on the first block (m_used = -inf)
+  if (need) {
+    alpha = ex2_approx((s.m_used - bm) * s.sl2);               // 0 on the first block
+    s.m_used = bm;
+    s.l *= alpha;
+  }
+  const bool any_need = __any_sync(0xffffffffu, need) && j > 0;
+  const float m_sl2 = s.m_used * s.sl2;
+  uint32_t pk[NCOL / 2];
+  float ls4[NCH];
+#pragma unroll
+  for (int u = 0; u < NCH; ++u) ls4[u] = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCOL; i += 2) {
+    // keys beyond NVALID are masked: probability 0 without spending an exponential on them
+    const float p0 = i < NVALID ? ex2_approx(fmaf(__uint_as_float(v[i]), s.sl2, -m_sl2)) : 0.f;
+    const float p1 = i + 1 < NVALID ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), s.sl2, -m_sl2)) : 0.f;
+    ls4[(i >> 1) % NCH] += p0 + p1;
+    pk[i >> 1] = pack_bf16x2(p0, p1);
+  }
+  float ls = ls4[0];
+#pragma unroll
+  for (int u = 1; u < NCH; ++u) ls += ls4[u];
+  s.l += ls;
+  if (any_need) {
+    // every earlier P V must have retired before O is touched (MMAs retire in order)
+    mbar_wait(&bar_pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1, 620);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tmem_o + t_lane + c * 32, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+      tmem_st_32x32b_x32(tmem_o + t_lane + c * 32, o);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  if (use > 0) mbar_wait(&bar_pv_done[b], (use - 1) & 1, 630 + b);   // P buffer b: previous tenant consumed
+  // P[r][0..NCOL) in the K-major 128B-swizzled UMMA layout (one atom): 16-byte chunks of row r
+  uint8_t* pb = sP + b * P_BYTES;
+#pragma unroll
+  for (int c = 0; c < NCOL / 8; ++c) {
+    uint4 w = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+    *reinterpret_cast<uint4*>(pb + r * 128 + ((c ^ (r & 7)) << 4)) = w;
+  }
+  fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&bar_p_full[b]);
+}
+
+// work item -> (query block, head, tile); consecutive items share K/V (L2 locality between co-resident CTAs)
+__device__ __forceinline__ void item_coords(int item, int& qb, int& h, int& t) {
+  qb = item % NQB;
+  const int th = item / NQB;
+  h = th % VZ_VIT_HEADS;
+  t = th / VZ_VIT_HEADS;
+}
+
 __global__ void __launch_bounds__(THREADS, 2)
 vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                   __nv_bfloat16* __restrict__ out, float scale) {
+                   __nv_bfloat16* __restrict__ out, float scale, int n_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem + SMEM_Q;
   uint8_t* sP = smem + SMEM_P;
   uint8_t* sRing = smem + SMEM_RING;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BARS);
-  uint64_t* bar_q = bars;              // Q landed
-  uint64_t* bar_kv_full = bars + 1;    // [3] K_j, V_j landed
-  uint64_t* bar_kv_empty = bars + 4;   // [3] P V_j retired -> slot reusable
-  uint64_t* bar_s_full = bars + 7;     // [2] S buffer written by Q K^T
-  uint64_t* bar_s_free = bars + 9;     // [2] S buffer copied to registers (4 warp arrivals)
-  uint64_t* bar_p_full = bars + 11;    // [2] P buffer written (and O rescaled if needed) (4 warp arrivals)
-  uint64_t* bar_pv_done = bars + 13;   // [2] P V retired -> P buffer reusable, O up to date
-  uint64_t* bar_o_full = bars + 15;    // all MMAs retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* bar_q_full = bars;         // [2] Q of an item landed
+  uint64_t* bar_q_empty = bars + 2;    // [2] every Q K^T of the item retired -> Q buffer reusable
+  uint64_t* bar_kv_full = bars + 4;    // [3] K_j, V_j landed
+  uint64_t* bar_kv_empty = bars + 7;   // [3] P V_j retired -> slot reusable
+  uint64_t* bar_s_full = bars + 10;    // [2] S buffer written by Q K^T
+  uint64_t* bar_s_free = bars + 12;    // [2] S buffer copied to registers (4 warp arrivals)
+  uint64_t* bar_p_full = bars + 14;    // [2] P buffer written (and O rescaled if needed) (4 warp arrivals)
+  uint64_t* bar_pv_done = bars + 16;   // [2] P V retired -> P buffer reusable, O up to date
+  uint64_t* bar_o_full = bars + 18;    // every MMA of the item retired
+  uint64_t* bar_o_free = bars + 19;    // O copied to registers (4 warp arrivals) -> next item may overwrite it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
-  const int qb = blockIdx.x, h = blockIdx.y, t = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row_base = t * TOK;  // first qkv row of this tile
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // the swizzled layouts need a 1024-byte aligned base
   if (threadIdx.x == 0) {
-    mbar_init(bar_q, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_q_full[i], 1); mbar_init(&bar_q_empty[i], 1); }
     for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&bar_kv_full[i], 1); mbar_init(&bar_kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_s_full[i], 1);
@@ -79,6 +200,7 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&bar_pv_done[i], 1);
     }
     mbar_init(bar_o_full, 1);
+    mbar_init(bar_o_free, 4);
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -89,164 +211,128 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_o = tmem_base + 128;
 
   if (warp == 5) {
-    // ======================= TMA producer =======================
+    // ======================= TMA producer: runs ahead across work items =======================
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmKV);
-      const int qcol = h * HD, kcol = VZ_VIT_WIDTH + h * HD, vcol = 2 * VZ_VIT_WIDTH + h * HD;
-      mbar_arrive_expect_tx(bar_q, Q_BYTES);
-      tma_load_2d(&tmQ, bar_q, sQ, qcol, row_base + qb * BQ);
-      for (int j = 0; j < NKB; ++j) {
-        const uint32_t st = j % KV_STAGES, ph = (j / KV_STAGES) & 1;
-        mbar_wait(&bar_kv_empty[st], ph ^ 1, 500 + st);
-        uint8_t* dK = sRing + st * 2 * KV_BYTES;
-        mbar_arrive_expect_tx(&bar_kv_full[st], 2 * KV_BYTES);
-        tma_load_2d(&tmKV, &bar_kv_full[st], dK, kcol, row_base + j * BKV);
-        tma_load_2d(&tmKV, &bar_kv_full[st], dK + KV_BYTES, vcol, row_base + j * BKV);
+      uint32_t g = 0, n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        int qb, h, t;
+        item_coords(item, qb, h, t);
+        const int row_base = t * TOK;
+        const int qcol = h * HD, kcol = VZ_VIT_WIDTH + h * HD, vcol = 2 * VZ_VIT_WIDTH + h * HD;
+        const uint32_t qs = n & 1;
+        mbar_wait(&bar_q_empty[qs], ((n >> 1) & 1) ^ 1, 490 + qs);
+        mbar_arrive_expect_tx(&bar_q_full[qs], Q_BYTES);
+        tma_load_2d(&tmQ, &bar_q_full[qs], sQ + qs * Q_BYTES, qcol, row_base + qb * BQ);
+        for (int j = 0; j < NKB; ++j, ++g) {
+          const uint32_t st = g % KV_STAGES, ph = (g / KV_STAGES) & 1;
+          mbar_wait(&bar_kv_empty[st], ph ^ 1, 500 + st);
+          uint8_t* dK = sRing + st * 2 * KV_BYTES;
+          mbar_arrive_expect_tx(&bar_kv_full[st], 2 * KV_BYTES);
+          tma_load_2d(&tmKV, &bar_kv_full[st], dK, kcol, row_base + j * BKV);
+          tma_load_2d(&tmKV, &bar_kv_full[st], dK + KV_BYTES, vcol, row_base + j * BKV);
+        }
       }
     }
   } else if (warp == 4) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16_ex(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_qk_last = umma_idesc_bf16_ex(BQ, LAST_N, 0, 0);   // last block: 1 valid key
       constexpr uint32_t idesc_pv = umma_idesc_bf16_ex(BQ, HD, 0, 1);   // B = V is MN-major (dims contiguous)
-      mbar_wait(bar_q, 0, 510);
-      const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(sQ));
-      auto issue_qk = [&](int j) {          // S[j & 1] = Q K_j^T
-        const uint32_t st = j % KV_STAGES, b = j & 1, use = j >> 1;
-        mbar_wait(&bar_kv_full[st], (j / KV_STAGES) & 1, 520 + st);
+      const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const uint32_t total = (uint32_t)my_items * NKB;   // key blocks this CTA walks, over all its items
+      // S[g & 1] = Q K_j^T for the CTA's g-th key block (item n = g / NKB, block j = g % NKB)
+      auto issue_qk = [&](uint32_t g) {
+        const uint32_t n = g / NKB, j = g - n * NKB;
+        const uint32_t st = g % KV_STAGES, b = g & 1, use = g >> 1, qs = n & 1;
+        if (j == 0) mbar_wait(&bar_q_full[qs], (n >> 1) & 1, 510 + qs);
+        mbar_wait(&bar_kv_full[st], (g / KV_STAGES) & 1, 520 + st);
         if (use > 0) mbar_wait(&bar_s_free[b], (use - 1) & 1, 530 + b);   // previous tenant is in registers
         tc_fence_after();
+        const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(sQ + qs * Q_BYTES));
         const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(sRing + st * 2 * KV_BYTES));
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_bf16(tmem_base + b * BKV, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc_qk,
-                    k != 0 ? 1u : 0u);
+          umma_bf16(tmem_base + b * BKV, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2),
+                    j == NKB - 1 ? idesc_qk_last : idesc_qk, k != 0 ? 1u : 0u);
         umma_commit(&bar_s_full[b]);
+        if (j == NKB - 1) umma_commit(&bar_q_empty[qs]);   // the item's last use of Q
       };
-      issue_qk(0);
-      for (int j = 0; j < NKB; ++j) {
-        if (j + 1 < NKB) issue_qk(j + 1);   // runs ahead of the softmax of block j
-        const uint32_t st = j % KV_STAGES, b = j & 1, use = j >> 1;
+      if (total > 0) issue_qk(0);
+      for (uint32_t g = 0; g < total; ++g) {
+        if (g + 1 < total) issue_qk(g + 1);   // runs ahead of the softmax of block g (also across items)
+        const uint32_t n = g / NKB, j = g - n * NKB;
+        const uint32_t st = g % KV_STAGES, b = g & 1, use = g >> 1;
         mbar_wait(&bar_p_full[b], use & 1, 540 + b);
+        if (j == 0 && n > 0) mbar_wait(bar_o_free, (n - 1) & 1, 550);   // previous item's O is in registers
         tc_fence_after();
         const uint32_t p_addr = smem_u32(sP + b * P_BYTES);
         const uint32_t v_addr = smem_u32(sRing + st * 2 * KV_BYTES + KV_BYTES);
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
+          if (j == NKB - 1 && kk * 16 >= LAST_N) break;   // the last block only holds LAST_VALID keys
           const uint64_t a_desc = umma_smem_desc_sw128(p_addr + kk * 32);
           const uint64_t b_desc = umma_smem_desc_sw128(v_addr + kk * 2048);  // 16 keys = 2 x (8 rows x 128 B)
           umma_bf16(tmem_o, a_desc, b_desc, idesc_pv, (j > 0 || kk != 0) ? 1u : 0u);
         }
         umma_commit(&bar_pv_done[b]);
         umma_commit(&bar_kv_empty[st]);
+        if (j == NKB - 1) umma_commit(bar_o_full);
       }
-      umma_commit(bar_o_full);
     }
   } else {
     // ======================= softmax warps: thread = query row = TMEM lane =======================
     const int r = warp * 32 + lane;
     const uint32_t t_lane = ((uint32_t)(warp * 32)) << 16;
-    const float sl2 = scale * kLog2e;
-    float m_used = -INFINITY, l = 0.f;
-    for (int j = 0; j < NKB; ++j) {
-      const uint32_t b = j & 1, use = j >> 1;
-      mbar_wait(&bar_s_full[b], use & 1, 600 + b);
+    uint32_t g = 0, n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      int qb, h, t;
+      item_coords(item, qb, h, t);
+      float l = 1.f;
+      if (qb * BQ + warp * 32 >= TOK) {
+        // no valid query row in this warp (last query block): keep the barrier protocol going, skip the math
+        for (int j = 0; j < NKB; ++j, ++g) {
+          const uint32_t b = g & 1, use = g >> 1;
+          mbar_wait(&bar_s_full[b], use & 1, 600 + b);
+          if (lane == 0) { mbar_arrive(&bar_s_free[b]); mbar_arrive(&bar_p_full[b]); }
+          __syncwarp();
+        }
+      } else {
+        SoftmaxState stt;
+        stt.sl2 = scale * kLog2e;
+        for (int j = 0; j < NKB - 1; ++j, ++g)
+          softmax_block<BKV, BKV>(stt, g, j, r, t_lane, tmem_base, tmem_o, sP, bar_s_full, bar_s_free, bar_p_full,
+                                  bar_pv_done);
+        softmax_block<LAST_N, LAST_VALID>(stt, g, NKB - 1, r, t_lane, tmem_base, tmem_o, sP, bar_s_full,
+                                          bar_s_free, bar_p_full, bar_pv_done);
+        ++g;
+        l = stt.l;
+      }
+      // ---- epilogue: O / l ----
+      mbar_wait(bar_o_full, n & 1, 640);
       tc_fence_after();
-      uint32_t v[64];
+      uint32_t o[64];
 #pragma unroll
       for (int c = 0; c < 2; ++c)
-        tmem_ld_32x32b_x32(tmem_base + t_lane + b * BKV + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+        tmem_ld_32x32b_x32(tmem_o + t_lane + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&o[c * 32]));
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_s_free[b]);
-      // keys of the last block beyond the tile's 577 tokens belong to the next tile: mask them
-      if (j == NKB - 1) {
-        constexpr int nvalid = TOK - (NKB - 1) * BKV;   // 1 valid key in the last block
-#pragma unroll
-        for (int i = nvalid; i < 64; ++i) v[i] = 0xff800000u;  // -inf
-      }
-      float bm4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int i = 0; i < 64; i += 4) {
-        bm4[0] = fmaxf(bm4[0], __uint_as_float(v[i]));
-        bm4[1] = fmaxf(bm4[1], __uint_as_float(v[i + 1]));
-        bm4[2] = fmaxf(bm4[2], __uint_as_float(v[i + 2]));
-        bm4[3] = fmaxf(bm4[3], __uint_as_float(v[i + 3]));
-      }
-      const float bm = fmaxf(fmaxf(bm4[0], bm4[1]), fmaxf(bm4[2], bm4[3]));
-      // lazy rescale: only when the running maximum grows by more than 2^kRescaleLog2
-      float alpha = 1.f;
-      const bool need = (bm - m_used) * sl2 > kRescaleLog2;   // true on the first block (m_used = -inf)
-      if (need) {
-        alpha = ex2_approx((m_used - bm) * sl2);               // 0 on the first block
-        m_used = bm;
-        l *= alpha;
-      }
-      const bool any_need = __any_sync(0xffffffffu, need) && j > 0;
-      const float m_sl2 = m_used * sl2;
-      uint32_t pk[32];
-      float ls4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int i = 0; i < 64; i += 8) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(v[i + 2 * u]), sl2, -m_sl2));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 2 * u + 1]), sl2, -m_sl2));
-          ls4[u] += p0 + p1;
-          pk[(i >> 1) + u] = pack_bf16x2(p0, p1);
-        }
-      }
-      l += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
-      if (any_need) {
-        // every earlier P V must have retired before O is touched (MMAs retire in order)
-        mbar_wait(&bar_pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1, 620);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t o[32];
-          tmem_ld_32x32b_x32(tmem_o + t_lane + c * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32b_x32(tmem_o + t_lane + c * 32, o);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-      }
-      if (use > 0) mbar_wait(&bar_pv_done[b], (use - 1) & 1, 630 + b);   // P buffer b: previous tenant consumed
-      // P[r][0..63] in the K-major 128B-swizzled UMMA layout (one atom): 8 chunks of row r
-      uint8_t* pb = sP + b * P_BYTES;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 w = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
-        *reinterpret_cast<uint4*>(pb + r * 128 + ((c ^ (r & 7)) << 4)) = w;
-      }
-      fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_p_full[b]);
-    }
-    // ---- epilogue: O / l ----
-    mbar_wait(bar_o_full, 0, 640);
-    tc_fence_after();
-    const int qrow = qb * BQ + r;
-    const float inv = 1.0f / l;
-    __nv_bfloat16* orow = out + (size_t)(row_base + qrow) * VZ_VIT_WIDTH + h * HD;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tmem_ld_32x32b_x32(tmem_o + t_lane + c * 32, o);
-      tmem_ld_wait();
+      if (lane == 0) mbar_arrive(bar_o_free);   // the next item's first P V may overwrite O now
+      const int qrow = qb * BQ + r;
       if (qrow < TOK) {
+        const float inv = 1.0f / l;
+        __nv_bfloat16* orow = out + (size_t)(t * TOK + qrow) * VZ_VIT_WIDTH + h * HD;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 8; ++i) {
           uint4 w;
           w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
           w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
           w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
           w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = w;
+          *reinterpret_cast<uint4*>(orow + i * 8) = w;
         }
       }
     }
@@ -270,8 +356,14 @@ int vit_attn_tc_launch(const void* qkv, void* out, int T, cudaStream_t st) {
     VZ_CUDA_CHECK(cudaFuncSetAttribute(vit_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     attr_done = true;
   }
-  dim3 grid((TOK + BQ - 1) / BQ, VZ_VIT_HEADS, T);
-  vit_attn_tc_kernel<<<grid, THREADS, SMEM_TOTAL, st>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out), 0.125f);
+  int dev = 0, num_sms = 0;
+  VZ_CUDA_CHECK(cudaGetDevice(&dev));
+  VZ_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  // persistent: two CTAs per SM walk the (tile, head, query block) items round-robin
+  const int n_items = NQB * VZ_VIT_HEADS * T;
+  const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
+  vit_attn_tc_kernel<<<grid, THREADS, SMEM_TOTAL, st>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out), 0.125f,
+                                                        n_items);
   VZ_LAUNCH_CHECK();
   return VZ_OK;
 }
