@@ -9,10 +9,11 @@
 // (Q is double buffered, the K/V ring and the S buffers never drain), so the load latency of an
 // item and the epilogue of the previous one overlap with softmax work instead of idling the SM.
 // The 577 keys are walked in 10 blocks of 64 -- the last one holds a single valid key and is computed
-// as a 16-key block -- with EVERYTHING double buffered -- two S accumulators in TMEM, two P tiles in
-// smem, a 3-stage K/V ring -- so Q K_{j+1}^T is issued before the softmax of block j starts and
+// as a 16-key block -- with EVERYTHING double buffered -- two S accumulators and two P tiles in
+// TMEM, a 4-stage K/V ring -- so Q K_{j+1}^T is issued before the softmax of block j starts and
 // P_j V_j runs while the softmax of block j+1 computes:
-//   S_j = Q K_j^T -> registers -> P_j = exp2((S_j - m) * scale) as bf16 in swizzled smem -> O += P_j V_j
+//   S_j = Q K_j^T -> registers -> P_j = exp2((S_j - m) * scale) as bf16 back into TMEM -> O += P_j V_j
+// (P is the TMEM A operand of the second MMA: it never touches shared memory)
 // The online softmax rescales the accumulator LAZILY: O (in TMEM) is only multiplied by
 // exp2(m_old - m_new) when the running maximum grew by more than 2^8, which is rare after the first
 // block, so O normally stays untouched in TMEM until the epilogue divides by the row sum.  Softmax
@@ -31,17 +32,16 @@ constexpr int LAST_N = 16;                          // ... which is computed as 
 static_assert(LAST_VALID >= 1 && LAST_VALID <= LAST_N, "last key block");
 constexpr int Q_BYTES = BQ * 128;           // 128 rows x 64 bf16
 constexpr int KV_BYTES = BKV * 128;         // 64 rows x 64 bf16
-constexpr int P_BYTES = BQ * 128;           // 128 rows x 64 keys bf16 (one swizzle atom wide)
-constexpr int KV_STAGES = 3;
+constexpr int KV_STAGES = 4;
 constexpr int NQB = (TOK + BQ - 1) / BQ;    // 5 query blocks per (tile, head)
 constexpr int SMEM_Q = 0;                                     // 2 buffers (the next item's Q is prefetched)
-constexpr int SMEM_P = 2 * Q_BYTES;                           // 2 buffers
-constexpr int SMEM_RING = SMEM_P + 2 * P_BYTES;               // 3 x (K, V)
+constexpr int SMEM_RING = 2 * Q_BYTES;                        // KV_STAGES x (K, V)
 constexpr int SMEM_BARS = SMEM_RING + KV_STAGES * 2 * KV_BYTES;
 constexpr int SMEM_TOTAL = SMEM_BARS + 256;
 static_assert(2 * (SMEM_TOTAL + 1024) <= 228 * 1024, "attention kernel must keep 2 CTAs per SM");
 constexpr int THREADS = 192;                // 4 softmax warps + MMA warp + TMA warp
-constexpr uint32_t TMEM_COLS = 256;         // S0: 0..63, S1: 64..127, O: 128..191
+constexpr uint32_t TMEM_COLS = 256;         // S0: 0..63, S1: 64..127, O: 128..191, P0: 192..223, P1: 224..255
+constexpr uint32_t TMEM_O = 128, TMEM_P = 192, P_COLS = BKV / 2;   // P: bf16 pairs, 32 columns per buffer
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -76,7 +76,7 @@ struct SoftmaxState {
 // j = block index inside the item (the accumulator is only touched when j > 0).
 template <int NCOL, int NVALID>
 __device__ __forceinline__ void softmax_block(SoftmaxState& s, uint32_t g, int j, int r, uint32_t t_lane,
-                                              uint32_t tmem_base, uint32_t tmem_o, uint8_t* sP, uint64_t* bar_s_full,
+                                              uint32_t tmem_base, uint32_t tmem_o, uint64_t* bar_s_full,
                                               uint64_t* bar_s_free, uint64_t* bar_p_full, uint64_t* bar_pv_done) {
   static_assert(NCOL == 64 || NCOL == 16, "score columns per block");
   const int lane = threadIdx.x & 31;
@@ -147,14 +147,11 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& s, uint32_t g, int j
     tc_fence_before();
   }
   if (use > 0) mbar_wait(&bar_pv_done[b], (use - 1) & 1, 630 + b);   // P buffer b: previous tenant consumed
-  // P[r][0..NCOL) in the K-major 128B-swizzled UMMA layout (one atom): 16-byte chunks of row r
-  uint8_t* pb = sP + b * P_BYTES;
-#pragma unroll
-  for (int c = 0; c < NCOL / 8; ++c) {
-    uint4 w = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
-    *reinterpret_cast<uint4*>(pb + r * 128 + ((c ^ (r & 7)) << 4)) = w;
-  }
-  fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+  // P[r][0..NCOL) stays in tensor memory: the A operand of P V (lane = row, two bf16 per 32-bit column)
+  if constexpr (NCOL == 64) tmem_st_32x32b_x32(tmem_base + t_lane + TMEM_P + b * P_COLS, pk);
+  else tmem_st_32x32b_x8(tmem_base + t_lane + TMEM_P + b * P_COLS, pk);
+  tmem_st_wait();
+  tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(&bar_p_full[b]);
 }
@@ -172,20 +169,19 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    __nv_bfloat16* __restrict__ out, float scale, int n_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem + SMEM_Q;
-  uint8_t* sP = smem + SMEM_P;
   uint8_t* sRing = smem + SMEM_RING;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BARS);
   uint64_t* bar_q_full = bars;         // [2] Q of an item landed
   uint64_t* bar_q_empty = bars + 2;    // [2] every Q K^T of the item retired -> Q buffer reusable
-  uint64_t* bar_kv_full = bars + 4;    // [3] K_j, V_j landed
-  uint64_t* bar_kv_empty = bars + 7;   // [3] P V_j retired -> slot reusable
-  uint64_t* bar_s_full = bars + 10;    // [2] S buffer written by Q K^T
-  uint64_t* bar_s_free = bars + 12;    // [2] S buffer copied to registers (4 warp arrivals)
-  uint64_t* bar_p_full = bars + 14;    // [2] P buffer written (and O rescaled if needed) (4 warp arrivals)
-  uint64_t* bar_pv_done = bars + 16;   // [2] P V retired -> P buffer reusable, O up to date
-  uint64_t* bar_o_full = bars + 18;    // every MMA of the item retired
-  uint64_t* bar_o_free = bars + 19;    // O copied to registers (4 warp arrivals) -> next item may overwrite it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* bar_kv_full = bars + 4;    // [KV_STAGES] K_j, V_j landed
+  uint64_t* bar_kv_empty = bar_kv_full + KV_STAGES;   // [KV_STAGES] P V_j retired -> slot reusable
+  uint64_t* bar_s_full = bar_kv_empty + KV_STAGES;    // [2] S buffer written by Q K^T
+  uint64_t* bar_s_free = bar_s_full + 2;    // [2] S buffer copied to registers (4 warp arrivals)
+  uint64_t* bar_p_full = bar_s_free + 2;    // [2] P buffer written (and O rescaled if needed) (4 warp arrivals)
+  uint64_t* bar_pv_done = bar_p_full + 2;   // [2] P V retired -> P buffer reusable, O up to date
+  uint64_t* bar_o_full = bar_pv_done + 2;   // every MMA of the item retired
+  uint64_t* bar_o_free = bar_o_full + 1;    // O copied to registers (4 warp arrivals) -> next item may overwrite it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -208,7 +204,7 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 128;
+  const uint32_t tmem_o = tmem_base + TMEM_O;
 
   if (warp == 5) {
     // ======================= TMA producer: runs ahead across work items =======================
@@ -268,14 +264,13 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(&bar_p_full[b], use & 1, 540 + b);
         if (j == 0 && n > 0) mbar_wait(bar_o_free, (n - 1) & 1, 550);   // previous item's O is in registers
         tc_fence_after();
-        const uint32_t p_addr = smem_u32(sP + b * P_BYTES);
+        const uint32_t p_tmem = tmem_base + TMEM_P + b * P_COLS;
         const uint32_t v_addr = smem_u32(sRing + st * 2 * KV_BYTES + KV_BYTES);
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
           if (j == NKB - 1 && kk * 16 >= LAST_N) break;   // the last block only holds LAST_VALID keys
-          const uint64_t a_desc = umma_smem_desc_sw128(p_addr + kk * 32);
           const uint64_t b_desc = umma_smem_desc_sw128(v_addr + kk * 2048);  // 16 keys = 2 x (8 rows x 128 B)
-          umma_bf16(tmem_o, a_desc, b_desc, idesc_pv, (j > 0 || kk != 0) ? 1u : 0u);
+          umma_bf16_ts(tmem_o, p_tmem + kk * 8, b_desc, idesc_pv, (j > 0 || kk != 0) ? 1u : 0u);   // 16 keys = 8 columns
         }
         umma_commit(&bar_pv_done[b]);
         umma_commit(&bar_kv_empty[st]);
@@ -303,10 +298,10 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         SoftmaxState stt;
         stt.sl2 = scale * kLog2e;
         for (int j = 0; j < NKB - 1; ++j, ++g)
-          softmax_block<BKV, BKV>(stt, g, j, r, t_lane, tmem_base, tmem_o, sP, bar_s_full, bar_s_free, bar_p_full,
+          softmax_block<BKV, BKV>(stt, g, j, r, t_lane, tmem_base, tmem_o, bar_s_full, bar_s_free, bar_p_full,
                                   bar_pv_done);
-        softmax_block<LAST_N, LAST_VALID>(stt, g, NKB - 1, r, t_lane, tmem_base, tmem_o, sP, bar_s_full,
-                                          bar_s_free, bar_p_full, bar_pv_done);
+        softmax_block<LAST_N, LAST_VALID>(stt, g, NKB - 1, r, t_lane, tmem_base, tmem_o, bar_s_full, bar_s_free,
+                                          bar_p_full, bar_pv_done);
         ++g;
         l = stt.l;
       }
