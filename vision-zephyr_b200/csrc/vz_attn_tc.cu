@@ -208,74 +208,96 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == 5) {
     // ======================= TMA producer: runs ahead across work items =======================
-    if (lane == 0) {
+    // (warp-uniform like the MMA warp: every lane walks the loop, one elected lane issues)
+    if (elect_one()) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmKV);
-      uint32_t g = 0, n = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
-        int qb, h, t;
-        item_coords(item, qb, h, t);
-        const int row_base = t * TOK;
-        const int qcol = h * HD, kcol = VZ_VIT_WIDTH + h * HD, vcol = 2 * VZ_VIT_WIDTH + h * HD;
-        const uint32_t qs = n & 1;
-        mbar_wait(&bar_q_empty[qs], ((n >> 1) & 1) ^ 1, 490 + qs);
+    }
+    uint32_t g = 0, n = 0, st = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      int qb, h, t;
+      item_coords(item, qb, h, t);
+      const int row_base = t * TOK;
+      const int qcol = h * HD, kcol = VZ_VIT_WIDTH + h * HD, vcol = 2 * VZ_VIT_WIDTH + h * HD;
+      const uint32_t qs = n & 1;
+      mbar_wait(&bar_q_empty[qs], ((n >> 1) & 1) ^ 1, 490 + qs);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&bar_q_full[qs], Q_BYTES);
         tma_load_2d(&tmQ, &bar_q_full[qs], sQ + qs * Q_BYTES, qcol, row_base + qb * BQ);
-        for (int j = 0; j < NKB; ++j, ++g) {
-          const uint32_t st = g % KV_STAGES, ph = (g / KV_STAGES) & 1;
-          mbar_wait(&bar_kv_empty[st], ph ^ 1, 500 + st);
+      }
+      __syncwarp();
+      for (int j = 0; j < NKB; ++j, ++g) {
+        mbar_wait(&bar_kv_empty[st], ((g / KV_STAGES) & 1) ^ 1, 500 + st);
+        if (elect_one()) {
           uint8_t* dK = sRing + st * 2 * KV_BYTES;
           mbar_arrive_expect_tx(&bar_kv_full[st], 2 * KV_BYTES);
           tma_load_2d(&tmKV, &bar_kv_full[st], dK, kcol, row_base + j * BKV);
           tma_load_2d(&tmKV, &bar_kv_full[st], dK + KV_BYTES, vcol, row_base + j * BKV);
         }
+        __syncwarp();
+        if (++st == KV_STAGES) st = 0;
       }
     }
   } else if (warp == 4) {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16_ex(BQ, BKV, 0, 0);
-      constexpr uint32_t idesc_qk_last = umma_idesc_bf16_ex(BQ, LAST_N, 0, 0);   // last block: 1 valid key
-      constexpr uint32_t idesc_pv = umma_idesc_bf16_ex(BQ, HD, 0, 1);   // B = V is MN-major (dims contiguous)
-      const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-      const uint32_t total = (uint32_t)my_items * NKB;   // key blocks this CTA walks, over all its items
-      // S[g & 1] = Q K_j^T for the CTA's g-th key block (item n = g / NKB, block j = g % NKB)
-      auto issue_qk = [&](uint32_t g) {
-        const uint32_t n = g / NKB, j = g - n * NKB;
-        const uint32_t st = g % KV_STAGES, b = g & 1, use = g >> 1, qs = n & 1;
-        if (j == 0) mbar_wait(&bar_q_full[qs], (n >> 1) & 1, 510 + qs);
-        mbar_wait(&bar_kv_full[st], (g / KV_STAGES) & 1, 520 + st);
-        if (use > 0) mbar_wait(&bar_s_free[b], (use - 1) & 1, 530 + b);   // previous tenant is in registers
-        tc_fence_after();
-        const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(sQ + qs * Q_BYTES));
-        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(sRing + st * 2 * KV_BYTES));
+    // All 32 lanes walk the loop and the waits (warp-uniform control flow keeps the descriptors in
+    // uniform registers and the instruction stream short -- the MMAs of one key block are only ~260
+    // tensor-pipe cycles, so a slow issuing thread would be the critical path); one elected lane issues.
+    constexpr uint32_t idesc_qk = umma_idesc_bf16_ex(BQ, BKV, 0, 0);
+    constexpr uint32_t idesc_qk_last = umma_idesc_bf16_ex(BQ, LAST_N, 0, 0);   // last block: 1 valid key
+    constexpr uint32_t idesc_pv = umma_idesc_bf16_ex(BQ, HD, 0, 1);   // B = V is MN-major (dims contiguous)
+    const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t total = (uint32_t)my_items * NKB;   // key blocks this CTA walks, over all its items
+    const uint64_t q_desc0 = umma_smem_desc_sw128(smem_u32(sQ));
+    const uint64_t ring_desc0 = umma_smem_desc_sw128(smem_u32(sRing));
+    // S[g & 1] = Q K_j^T for the CTA's g-th key block (item n, block j of it; ring slot st)
+    auto issue_qk = [&](uint32_t g, uint32_t n, uint32_t j, uint32_t st) {
+      const uint32_t b = g & 1, use = g >> 1, qs = n & 1;
+      if (j == 0) mbar_wait(&bar_q_full[qs], (n >> 1) & 1, 510 + qs);
+      mbar_wait(&bar_kv_full[st], (g / KV_STAGES) & 1, 520 + st);
+      if (use > 0) mbar_wait(&bar_s_free[b], (use - 1) & 1, 530 + b);   // previous tenant is in registers
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t q_desc = q_desc0 + (uint64_t)(qs * (Q_BYTES >> 4));
+        const uint64_t k_desc = ring_desc0 + (uint64_t)(st * (2 * KV_BYTES >> 4));
+        const uint32_t idesc = j == NKB - 1 ? idesc_qk_last : idesc_qk;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_bf16(tmem_base + b * BKV, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2),
-                    j == NKB - 1 ? idesc_qk_last : idesc_qk, k != 0 ? 1u : 0u);
+          umma_bf16(tmem_base + b * BKV, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc,
+                    k != 0 ? 1u : 0u);
         umma_commit(&bar_s_full[b]);
         if (j == NKB - 1) umma_commit(&bar_q_empty[qs]);   // the item's last use of Q
-      };
-      if (total > 0) issue_qk(0);
-      for (uint32_t g = 0; g < total; ++g) {
-        if (g + 1 < total) issue_qk(g + 1);   // runs ahead of the softmax of block g (also across items)
-        const uint32_t n = g / NKB, j = g - n * NKB;
-        const uint32_t st = g % KV_STAGES, b = g & 1, use = g >> 1;
-        mbar_wait(&bar_p_full[b], use & 1, 540 + b);
-        if (j == 0 && n > 0) mbar_wait(bar_o_free, (n - 1) & 1, 550);   // previous item's O is in registers
-        tc_fence_after();
+      }
+      __syncwarp();
+    };
+    if (total > 0) issue_qk(0, 0, 0, 0);
+    uint32_t n = 0, j = 0, st = 0;          // coordinates of block g
+    uint32_t n1 = 0, j1 = 0, st1 = 0;       // ... and of block g + 1
+    for (uint32_t g = 0; g < total; ++g) {
+      if (++j1 == NKB) { j1 = 0; ++n1; }
+      if (++st1 == KV_STAGES) st1 = 0;
+      if (g + 1 < total) issue_qk(g + 1, n1, j1, st1);   // runs ahead of the softmax of block g (also across items)
+      const uint32_t b = g & 1, use = g >> 1;
+      mbar_wait(&bar_p_full[b], use & 1, 540 + b);
+      if (j == 0 && n > 0) mbar_wait(bar_o_free, (n - 1) & 1, 550);   // previous item's O is in registers
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t p_tmem = tmem_base + TMEM_P + b * P_COLS;
-        const uint32_t v_addr = smem_u32(sRing + st * 2 * KV_BYTES + KV_BYTES);
+        const uint64_t v_desc = ring_desc0 + (uint64_t)((st * 2 * KV_BYTES + KV_BYTES) >> 4);
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
           if (j == NKB - 1 && kk * 16 >= LAST_N) break;   // the last block only holds LAST_VALID keys
-          const uint64_t b_desc = umma_smem_desc_sw128(v_addr + kk * 2048);  // 16 keys = 2 x (8 rows x 128 B)
-          umma_bf16_ts(tmem_o, p_tmem + kk * 8, b_desc, idesc_pv, (j > 0 || kk != 0) ? 1u : 0u);   // 16 keys = 8 columns
+          // 16 keys = 2 x (8 rows x 128 B) of V, 8 columns of P
+          umma_bf16_ts(tmem_o, p_tmem + kk * 8, v_desc + (uint64_t)(kk * (2048 >> 4)), idesc_pv,
+                       (j > 0 || kk != 0) ? 1u : 0u);
         }
         umma_commit(&bar_pv_done[b]);
         umma_commit(&bar_kv_empty[st]);
         if (j == NKB - 1) umma_commit(bar_o_full);
       }
+      __syncwarp();
+      if (++j == NKB) { j = 0; ++n; }
+      if (++st == KV_STAGES) st = 0;
     }
   } else {
     // ======================= softmax warps: thread = query row = TMEM lane =======================
