@@ -32,11 +32,14 @@ constexpr int LAST_N = 16;                          // ... which is computed as 
 static_assert(LAST_VALID >= 1 && LAST_VALID <= LAST_N, "last key block");
 constexpr int Q_BYTES = BQ * 128;           // 128 rows x 64 bf16
 constexpr int KV_BYTES = BKV * 128;         // 64 rows x 64 bf16
-constexpr int KV_STAGES = 4;
+constexpr int KV_STAGES = 4;                // per ring: K and V have their own rings (K is consumed ~2 blocks before V)
 constexpr int NQB = (TOK + BQ - 1) / BQ;    // 5 query blocks per (tile, head)
+constexpr int OUT_SLAB = 32 * 128;          // per softmax warp: 32 output rows x 64 bf16, staged for the TMA store
 constexpr int SMEM_Q = 0;                                     // 2 buffers (the next item's Q is prefetched)
-constexpr int SMEM_RING = 2 * Q_BYTES;                        // KV_STAGES x (K, V)
-constexpr int SMEM_BARS = SMEM_RING + KV_STAGES * 2 * KV_BYTES;
+constexpr int SMEM_K = 2 * Q_BYTES;                           // KV_STAGES x K
+constexpr int SMEM_V = SMEM_K + KV_STAGES * KV_BYTES;         // KV_STAGES x V
+constexpr int SMEM_OUT = SMEM_V + KV_STAGES * KV_BYTES;       // 4 x OUT_SLAB
+constexpr int SMEM_BARS = SMEM_OUT + 4 * OUT_SLAB;
 constexpr int SMEM_TOTAL = SMEM_BARS + 256;
 static_assert(2 * (SMEM_TOTAL + 1024) <= 228 * 1024, "attention kernel must keep 2 CTAs per SM");
 constexpr int THREADS = 192;                // 4 softmax warps + MMA warp + TMA warp
@@ -166,29 +169,36 @@ __device__ __forceinline__ void item_coords(int item, int& qb, int& h, int& t) {
 
 __global__ void __launch_bounds__(THREADS, 2)
 vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                   __nv_bfloat16* __restrict__ out, float scale, int n_items) {
+                   const __grid_constant__ CUtensorMap tmO, float scale, int n_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem + SMEM_Q;
-  uint8_t* sRing = smem + SMEM_RING;
+  uint8_t* sK = smem + SMEM_K;
+  uint8_t* sV = smem + SMEM_V;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BARS);
   uint64_t* bar_q_full = bars;         // [2] Q of an item landed
   uint64_t* bar_q_empty = bars + 2;    // [2] every Q K^T of the item retired -> Q buffer reusable
-  uint64_t* bar_kv_full = bars + 4;    // [KV_STAGES] K_j, V_j landed
-  uint64_t* bar_kv_empty = bar_kv_full + KV_STAGES;   // [KV_STAGES] P V_j retired -> slot reusable
-  uint64_t* bar_s_full = bar_kv_empty + KV_STAGES;    // [2] S buffer written by Q K^T
+  uint64_t* bar_k_full = bars + 4;                    // [KV_STAGES] K_j landed
+  uint64_t* bar_k_empty = bar_k_full + KV_STAGES;     // [KV_STAGES] Q K_j^T retired -> slot reusable
+  uint64_t* bar_v_full = bar_k_empty + KV_STAGES;     // [KV_STAGES] V_j landed
+  uint64_t* bar_v_empty = bar_v_full + KV_STAGES;     // [KV_STAGES] P V_j retired -> slot reusable
+  uint64_t* bar_s_full = bar_v_empty + KV_STAGES;     // [2] S buffer written by Q K^T
   uint64_t* bar_s_free = bar_s_full + 2;    // [2] S buffer copied to registers (4 warp arrivals)
   uint64_t* bar_p_full = bar_s_free + 2;    // [2] P buffer written (and O rescaled if needed) (4 warp arrivals)
   uint64_t* bar_pv_done = bar_p_full + 2;   // [2] P V retired -> P buffer reusable, O up to date
   uint64_t* bar_o_full = bar_pv_done + 2;   // every MMA of the item retired
   uint64_t* bar_o_free = bar_o_full + 1;    // O copied to registers (4 warp arrivals) -> next item may overwrite it
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o_free + 1);
+  static_assert((4 + 4 * KV_STAGES + 10) * 8 + 4 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // the swizzled layouts need a 1024-byte aligned base
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_q_full[i], 1); mbar_init(&bar_q_empty[i], 1); }
-    for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&bar_kv_full[i], 1); mbar_init(&bar_kv_empty[i], 1); }
+    for (int i = 0; i < KV_STAGES; ++i) {
+      mbar_init(&bar_k_full[i], 1); mbar_init(&bar_k_empty[i], 1);
+      mbar_init(&bar_v_full[i], 1); mbar_init(&bar_v_empty[i], 1);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_s_full[i], 1);
       mbar_init(&bar_s_free[i], 4);
@@ -205,37 +215,52 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + TMEM_O;
+  const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t total = (uint32_t)my_items * NKB;   // key blocks this CTA walks, over all its items
 
   if (warp == 5) {
     // ======================= TMA producer: runs ahead across work items =======================
-    // (warp-uniform like the MMA warp: every lane walks the loop, one elected lane issues)
+    // (warp-uniform like the MMA warp: every lane walks the loop, one elected lane issues.)
+    // K and V travel through separate rings: a K slot is free again as soon as its Q K^T retired, long
+    // before the V of the same block is consumed, so both streams keep their full prefetch distance.
     if (elect_one()) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmKV);
     }
-    uint32_t g = 0, n = 0, st = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
-      int qb, h, t;
-      item_coords(item, qb, h, t);
-      const int row_base = t * TOK;
-      const int qcol = h * HD, kcol = VZ_VIT_WIDTH + h * HD, vcol = 2 * VZ_VIT_WIDTH + h * HD;
-      const uint32_t qs = n & 1;
-      mbar_wait(&bar_q_empty[qs], ((n >> 1) & 1) ^ 1, 490 + qs);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&bar_q_full[qs], Q_BYTES);
-        tma_load_2d(&tmQ, &bar_q_full[qs], sQ + qs * Q_BYTES, qcol, row_base + qb * BQ);
-      }
-      __syncwarp();
-      for (int j = 0; j < NKB; ++j, ++g) {
-        mbar_wait(&bar_kv_empty[st], ((g / KV_STAGES) & 1) ^ 1, 500 + st);
+    uint32_t kg = 0, kj = 0, kst = 0, kn = 0; int kitem = blockIdx.x;   // next K block: index, block in item, slot, item
+    uint32_t vg = 0, vj = 0, vst = 0;         int vitem = blockIdx.x;   // next V block
+    while (kg < total || vg < total) {
+      if (kg < total && __shfl_sync(0xffffffffu, (int)mbar_try_wait(&bar_k_empty[kst], ((kg / KV_STAGES) & 1) ^ 1), 0)) {
+        int qb, h, t;
+        item_coords(kitem, qb, h, t);
+        if (kj == 0) {
+          const uint32_t qs = kn & 1;
+          mbar_wait(&bar_q_empty[qs], ((kn >> 1) & 1) ^ 1, 490 + qs);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&bar_q_full[qs], Q_BYTES);
+            tma_load_2d(&tmQ, &bar_q_full[qs], sQ + qs * Q_BYTES, h * HD, t * TOK + qb * BQ);
+          }
+        }
         if (elect_one()) {
-          uint8_t* dK = sRing + st * 2 * KV_BYTES;
-          mbar_arrive_expect_tx(&bar_kv_full[st], 2 * KV_BYTES);
-          tma_load_2d(&tmKV, &bar_kv_full[st], dK, kcol, row_base + j * BKV);
-          tma_load_2d(&tmKV, &bar_kv_full[st], dK + KV_BYTES, vcol, row_base + j * BKV);
+          mbar_arrive_expect_tx(&bar_k_full[kst], KV_BYTES);
+          tma_load_2d(&tmKV, &bar_k_full[kst], sK + kst * KV_BYTES, VZ_VIT_WIDTH + h * HD, t * TOK + kj * BKV);
         }
         __syncwarp();
-        if (++st == KV_STAGES) st = 0;
+        ++kg;
+        if (++kst == KV_STAGES) kst = 0;
+        if (++kj == NKB) { kj = 0; ++kn; kitem += gridDim.x; }
+      }
+      if (vg < total && __shfl_sync(0xffffffffu, (int)mbar_try_wait(&bar_v_empty[vst], ((vg / KV_STAGES) & 1) ^ 1), 0)) {
+        int qb, h, t;
+        item_coords(vitem, qb, h, t);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bar_v_full[vst], KV_BYTES);
+          tma_load_2d(&tmKV, &bar_v_full[vst], sV + vst * KV_BYTES, 2 * VZ_VIT_WIDTH + h * HD, t * TOK + vj * BKV);
+        }
+        __syncwarp();
+        ++vg;
+        if (++vst == KV_STAGES) vst = 0;
+        if (++vj == NKB) { vj = 0; vitem += gridDim.x; }
       }
     }
   } else if (warp == 4) {
@@ -246,26 +271,26 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     constexpr uint32_t idesc_qk = umma_idesc_bf16_ex(BQ, BKV, 0, 0);
     constexpr uint32_t idesc_qk_last = umma_idesc_bf16_ex(BQ, LAST_N, 0, 0);   // last block: 1 valid key
     constexpr uint32_t idesc_pv = umma_idesc_bf16_ex(BQ, HD, 0, 1);   // B = V is MN-major (dims contiguous)
-    const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const uint32_t total = (uint32_t)my_items * NKB;   // key blocks this CTA walks, over all its items
     const uint64_t q_desc0 = umma_smem_desc_sw128(smem_u32(sQ));
-    const uint64_t ring_desc0 = umma_smem_desc_sw128(smem_u32(sRing));
+    const uint64_t k_desc0 = umma_smem_desc_sw128(smem_u32(sK));
+    const uint64_t v_desc0 = umma_smem_desc_sw128(smem_u32(sV));
     // S[g & 1] = Q K_j^T for the CTA's g-th key block (item n, block j of it; ring slot st)
     auto issue_qk = [&](uint32_t g, uint32_t n, uint32_t j, uint32_t st) {
       const uint32_t b = g & 1, use = g >> 1, qs = n & 1;
       if (j == 0) mbar_wait(&bar_q_full[qs], (n >> 1) & 1, 510 + qs);
-      mbar_wait(&bar_kv_full[st], (g / KV_STAGES) & 1, 520 + st);
+      mbar_wait(&bar_k_full[st], (g / KV_STAGES) & 1, 520 + st);
       if (use > 0) mbar_wait(&bar_s_free[b], (use - 1) & 1, 530 + b);   // previous tenant is in registers
       tc_fence_after();
       if (elect_one()) {
         const uint64_t q_desc = q_desc0 + (uint64_t)(qs * (Q_BYTES >> 4));
-        const uint64_t k_desc = ring_desc0 + (uint64_t)(st * (2 * KV_BYTES >> 4));
+        const uint64_t k_desc = k_desc0 + (uint64_t)(st * (KV_BYTES >> 4));
         const uint32_t idesc = j == NKB - 1 ? idesc_qk_last : idesc_qk;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
           umma_bf16(tmem_base + b * BKV, q_desc + (uint64_t)(k * 2), k_desc + (uint64_t)(k * 2), idesc,
                     k != 0 ? 1u : 0u);
         umma_commit(&bar_s_full[b]);
+        umma_commit(&bar_k_empty[st]);
         if (j == NKB - 1) umma_commit(&bar_q_empty[qs]);   // the item's last use of Q
       }
       __syncwarp();
@@ -278,12 +303,13 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (++st1 == KV_STAGES) st1 = 0;
       if (g + 1 < total) issue_qk(g + 1, n1, j1, st1);   // runs ahead of the softmax of block g (also across items)
       const uint32_t b = g & 1, use = g >> 1;
+      mbar_wait(&bar_v_full[st], (g / KV_STAGES) & 1, 535 + st);
       mbar_wait(&bar_p_full[b], use & 1, 540 + b);
       if (j == 0 && n > 0) mbar_wait(bar_o_free, (n - 1) & 1, 550);   // previous item's O is in registers
       tc_fence_after();
       if (elect_one()) {
         const uint32_t p_tmem = tmem_base + TMEM_P + b * P_COLS;
-        const uint64_t v_desc = ring_desc0 + (uint64_t)((st * 2 * KV_BYTES + KV_BYTES) >> 4);
+        const uint64_t v_desc = v_desc0 + (uint64_t)(st * (KV_BYTES >> 4));
 #pragma unroll
         for (int kk = 0; kk < BKV / 16; ++kk) {
           if (j == NKB - 1 && kk * 16 >= LAST_N) break;   // the last block only holds LAST_VALID keys
@@ -292,7 +318,7 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                        (j > 0 || kk != 0) ? 1u : 0u);
         }
         umma_commit(&bar_pv_done[b]);
-        umma_commit(&bar_kv_empty[st]);
+        umma_commit(&bar_v_empty[st]);
         if (j == NKB - 1) umma_commit(bar_o_full);
       }
       __syncwarp();
@@ -303,12 +329,14 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ======================= softmax warps: thread = query row = TMEM lane =======================
     const int r = warp * 32 + lane;
     const uint32_t t_lane = ((uint32_t)(warp * 32)) << 16;
+    uint8_t* slab = smem + SMEM_OUT + warp * OUT_SLAB;   // this warp's 32 output rows, 128B-swizzled for the TMA store
     uint32_t g = 0, n = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
       int qb, h, t;
       item_coords(item, qb, h, t);
       float l = 1.f;
-      if (qb * BQ + warp * 32 >= TOK) {
+      const bool active = qb * BQ + warp * 32 < TOK;
+      if (!active) {
         // no valid query row in this warp (last query block): keep the barrier protocol going, skip the math
         for (int j = 0; j < NKB; ++j, ++g) {
           const uint32_t b = g & 1, use = g >> 1;
@@ -327,7 +355,7 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         ++g;
         l = stt.l;
       }
-      // ---- epilogue: O / l ----
+      // ---- epilogue: O / l -> bf16 -> swizzled smem slab -> TMA store (rows beyond the tile's 577 are clipped) ----
       mbar_wait(bar_o_full, n & 1, 640);
       tc_fence_after();
       uint32_t o[64];
@@ -337,11 +365,13 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_o_free);   // the next item's first P V may overwrite O now
-      const int qrow = qb * BQ + r;
-      if (qrow < TOK) {
+      if (lane == 0) {
+        mbar_arrive(bar_o_free);   // the next item's first P V may overwrite O now
+        tma_store_wait_read();     // the previous item's store has drained this warp's slab
+      }
+      __syncwarp();
+      if (active) {
         const float inv = 1.0f / l;
-        __nv_bfloat16* orow = out + (size_t)(t * TOK + qrow) * VZ_VIT_WIDTH + h * HD;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           uint4 w;
@@ -349,10 +379,17 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
           w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
           w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + i * 8) = w;
+          *reinterpret_cast<uint4*>(slab + lane * 128 + ((i ^ (lane & 7)) << 4)) = w;
+        }
+        fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmO, slab, h * HD, qb * BQ + warp * 32, t);
+          tma_store_commit();
         }
       }
     }
+    if (lane == 0) tma_store_wait_read();   // shared memory must outlive the last store's read
   }
   tc_fence_before();
   __syncthreads();
@@ -365,9 +402,11 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }  // namespace
 
 int vit_attn_tc_launch(const void* qkv, void* out, int T, cudaStream_t st) {
-  CUtensorMap tmQ, tmKV;
+  CUtensorMap tmQ, tmKV, tmO;
   VZ_TRY(encode_tmap_2d_bf16(&tmQ, qkv, (long long)T * TOK, 3 * VZ_VIT_WIDTH, 3 * VZ_VIT_WIDTH, HD, BQ));
   VZ_TRY(encode_tmap_2d_bf16(&tmKV, qkv, (long long)T * TOK, 3 * VZ_VIT_WIDTH, 3 * VZ_VIT_WIDTH, HD, BKV));
+  // output as [tile][577 rows][1024]: a 32-row store box that runs past a tile's last row is clipped by the TMA
+  VZ_TRY(encode_tmap_3d_bf16(&tmO, out, TOK, VZ_VIT_WIDTH, VZ_VIT_WIDTH, 32, T, (long long)TOK * VZ_VIT_WIDTH));
   static bool attr_done = false;
   if (!attr_done) {
     VZ_CUDA_CHECK(cudaFuncSetAttribute(vit_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
@@ -379,8 +418,7 @@ int vit_attn_tc_launch(const void* qkv, void* out, int T, cudaStream_t st) {
   // persistent: two CTAs per SM walk the (tile, head, query block) items round-robin
   const int n_items = NQB * VZ_VIT_HEADS * T;
   const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
-  vit_attn_tc_kernel<<<grid, THREADS, SMEM_TOTAL, st>>>(tmQ, tmKV, reinterpret_cast<__nv_bfloat16*>(out), 0.125f,
-                                                        n_items);
+  vit_attn_tc_kernel<<<grid, THREADS, SMEM_TOTAL, st>>>(tmQ, tmKV, tmO, 0.125f, n_items);
   VZ_LAUNCH_CHECK();
   return VZ_OK;
 }

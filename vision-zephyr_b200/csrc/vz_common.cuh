@@ -57,6 +57,7 @@ int softmax_rows_launch(const float* s, void* p, int rows, int n, float scale, c
 int vit_attn_launch(const void* qkv, void* out, int T, cudaStream_t st);
 int vit_attn_tc_launch(const void* qkv, void* out, int T, cudaStream_t st);
 int encode_tmap_2d_bf16(CUtensorMap* tm, const void* base, long long rows, int cols, int ld, int box_cols, int box_rows);
+int encode_tmap_3d_bf16(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows, int batch, long long bstride);
 int qattn_launch(int mode, const void* q, int q_rs, int q_zrows, const void* k0, const void* v0,
                  int rs0, int zrows0, int count0, const void* k1, const void* v1, int rs1,
                  const int32_t* off1, const void* kpad, const void* vpad, int L, void* out, int ldo,
@@ -154,6 +155,18 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar,
         "r"(c1), "r"(c2)
       : "memory");
 }
+
+// smem -> global tensor store (bulk async group of the issuing thread); out-of-bounds box elements are clipped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int32_t c0, int32_t c1,
+                                             int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // ---- tcgen05 ----------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() {

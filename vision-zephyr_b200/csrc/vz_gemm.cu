@@ -589,6 +589,13 @@ int encode_tmap_2d_bf16(CUtensorMap* tm, const void* base, long long rows, int c
   return VZ_OK;
 }
 
+// 3-D bf16 tensor map {64 columns, box_rows rows, 1 batch} with 128-byte swizzle (the GEMM's operand map; the
+// attention kernel stores its output tiles through one)
+int encode_tmap_3d_bf16(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows, int batch,
+                        long long bstride) {
+  return make_tmap(tm, base, rows, cols, ld, box_rows, batch, bstride);
+}
+
 namespace {
 // tile width the launcher will use for a problem (shared with the orchestration, which sizes the
 // LayerNorm partial-statistics buffers from it)
