@@ -295,14 +295,24 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       __syncwarp();
     };
-    if (total > 0) issue_qk(0, 0, 0, 0);
+    // Q K^T runs TWO blocks ahead of the softmax: S[g & 1] is rewritten with block g + 2 as soon as the
+    // softmax has copied block g to registers, so the issue -> commit -> mbarrier -> waiter latency of a
+    // block (~1000 cycles measured) hides behind almost two softmax blocks.  The events the loop waits
+    // for alternate strictly (s_free(g), p_full(g), s_free(g + 1), ...), so blocking waits suffice.
     uint32_t n = 0, j = 0, st = 0;          // coordinates of block g
-    uint32_t n1 = 0, j1 = 0, st1 = 0;       // ... and of block g + 1
+    uint32_t n2 = 0, j2 = 0, st2 = 0;       // ... and of the next block whose Q K^T is to be issued
+    for (uint32_t a = 0; a < 2 && a < total; ++a) {
+      issue_qk(a, n2, j2, st2);
+      if (++j2 == NKB) { j2 = 0; ++n2; }
+      if (++st2 == KV_STAGES) st2 = 0;
+    }
     for (uint32_t g = 0; g < total; ++g) {
-      if (++j1 == NKB) { j1 = 0; ++n1; }
-      if (++st1 == KV_STAGES) st1 = 0;
-      if (g + 1 < total) issue_qk(g + 1, n1, j1, st1);   // runs ahead of the softmax of block g (also across items)
       const uint32_t b = g & 1, use = g >> 1;
+      if (g + 2 < total) {
+        issue_qk(g + 2, n2, j2, st2);   // waits until the softmax holds S_g in registers (s_free)
+        if (++j2 == NKB) { j2 = 0; ++n2; }
+        if (++st2 == KV_STAGES) st2 = 0;
+      }
       mbar_wait(&bar_v_full[st], (g / KV_STAGES) & 1, 535 + st);
       mbar_wait(&bar_p_full[b], use & 1, 540 + b);
       if (j == 0 && n > 0) mbar_wait(bar_o_free, (n - 1) & 1, 550);   // previous item's O is in registers
@@ -330,33 +340,10 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int r = warp * 32 + lane;
     const uint32_t t_lane = ((uint32_t)(warp * 32)) << 16;
     uint8_t* slab = smem + SMEM_OUT + warp * OUT_SLAB;   // this warp's 32 output rows, 128B-swizzled for the TMA store
-    uint32_t g = 0, n = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
-      int qb, h, t;
-      item_coords(item, qb, h, t);
-      float l = 1.f;
-      const bool active = qb * BQ + warp * 32 < TOK;
-      if (!active) {
-        // no valid query row in this warp (last query block): keep the barrier protocol going, skip the math
-        for (int j = 0; j < NKB; ++j, ++g) {
-          const uint32_t b = g & 1, use = g >> 1;
-          mbar_wait(&bar_s_full[b], use & 1, 600 + b);
-          if (lane == 0) { mbar_arrive(&bar_s_free[b]); mbar_arrive(&bar_p_full[b]); }
-          __syncwarp();
-        }
-      } else {
-        SoftmaxState stt;
-        stt.sl2 = scale * kLog2e;
-        for (int j = 0; j < NKB - 1; ++j, ++g)
-          softmax_block<BKV, BKV>(stt, g, j, r, t_lane, tmem_base, tmem_o, bar_s_full, bar_s_free, bar_p_full,
-                                  bar_pv_done);
-        softmax_block<LAST_N, LAST_VALID>(stt, g, NKB - 1, r, t_lane, tmem_base, tmem_o, bar_s_full, bar_s_free,
-                                          bar_p_full, bar_pv_done);
-        ++g;
-        l = stt.l;
-      }
-      // ---- epilogue: O / l -> bf16 -> swizzled smem slab -> TMA store (rows beyond the tile's 577 are clipped) ----
-      mbar_wait(bar_o_full, n & 1, 640);
+    // epilogue of item (eq, eh, et) = the CTA's en-th: O / l -> bf16 -> swizzled smem slab -> TMA store (rows
+    // beyond the tile's 577 are clipped by the tensor map)
+    auto epilogue = [&](int eq, int eh, int et, uint32_t en, float l, bool active) {
+      mbar_wait(bar_o_full, en & 1, 640);
       tc_fence_after();
       uint32_t o[64];
 #pragma unroll
@@ -367,7 +354,7 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar_o_free);   // the next item's first P V may overwrite O now
-        tma_store_wait_read();     // the previous item's store has drained this warp's slab
+        tma_store_wait_read();     // the previous store has drained this warp's slab
       }
       __syncwarp();
       if (active) {
@@ -384,11 +371,51 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA (async proxy)
         __syncwarp();
         if (lane == 0) {
-          tma_store_3d(&tmO, slab, h * HD, qb * BQ + warp * 32, t);
+          tma_store_3d(&tmO, slab, eh * HD, eq * BQ + warp * 32, et);
           tma_store_commit();
         }
       }
+    };
+    // The epilogue of an item is DEFERRED until the first key block of the next item has been handed to
+    // the MMA warp: by then the item's last P V has long retired, so nobody waits for it (the next item's
+    // first P V, the only instruction that needs O to be drained, waits on o_free instead).
+    bool pend = false, pact = false;
+    int pq = 0, ph = 0, pt = 0;
+    float pl = 1.f;
+    uint32_t g = 0, n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      int qb, h, t;
+      item_coords(item, qb, h, t);
+      const bool active = qb * BQ + warp * 32 < TOK;
+      SoftmaxState stt;
+      stt.sl2 = scale * kLog2e;
+      // no valid query row in this warp (last query block): keep the barrier protocol going, skip the math
+      auto idle_block = [&]() {
+        const uint32_t b = g & 1, use = g >> 1;
+        mbar_wait(&bar_s_full[b], use & 1, 600 + b);
+        // same gate as the working warps: an arrival for block g must not land in p_full[b]'s previous phase
+        if (use > 0) mbar_wait(&bar_pv_done[b], (use - 1) & 1, 610 + b);
+        if (lane == 0) { mbar_arrive(&bar_s_free[b]); mbar_arrive(&bar_p_full[b]); }
+        __syncwarp();
+      };
+      if (active) softmax_block<BKV, BKV>(stt, g, 0, r, t_lane, tmem_base, tmem_o, bar_s_full, bar_s_free, bar_p_full,
+                                          bar_pv_done);
+      else idle_block();
+      ++g;
+      if (pend) epilogue(pq, ph, pt, n - 1, pl, pact);
+      if (active) {
+        for (int j = 1; j < NKB - 1; ++j, ++g)
+          softmax_block<BKV, BKV>(stt, g, j, r, t_lane, tmem_base, tmem_o, bar_s_full, bar_s_free, bar_p_full,
+                                  bar_pv_done);
+        softmax_block<LAST_N, LAST_VALID>(stt, g, NKB - 1, r, t_lane, tmem_base, tmem_o, bar_s_full, bar_s_free,
+                                          bar_p_full, bar_pv_done);
+        ++g;
+      } else {
+        for (int j = 1; j < NKB; ++j, ++g) idle_block();
+      }
+      pend = true; pact = active; pq = qb; ph = h; pt = t; pl = stt.l;
     }
+    if (pend) epilogue(pq, ph, pt, n - 1, pl, pact);
     if (lane == 0) tma_store_wait_read();   // shared memory must outlive the last store's read
   }
   tc_fence_before();
