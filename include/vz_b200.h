@@ -88,7 +88,14 @@ typedef struct {
   float ln_eps;
   float* stats_out;
   int stats_np;
+  /* Optional stream-K scratch (device memory, >= vz_gemm_sk_workspace_bytes(), 16-byte aligned, exclusive
+   * to one stream at a time): lets the launcher split the k-blocks of the last, partially filled round of
+   * tiles evenly over all SMs (fp32 partial sums handed over through this buffer and added in a fixed
+   * order, so results stay deterministic).  NULL = whole tiles only.                                    */
+  void* sk_ws;
+  size_t sk_ws_bytes;
 } vz_gemm_args;
+size_t vz_gemm_sk_workspace_bytes(void);
 
 int vz_gemm_bf16(const vz_gemm_args* args, void* stream);
 /* number of partial-statistics slots per row that a stats_out GEMM of this shape writes */

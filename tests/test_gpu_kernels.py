@@ -243,3 +243,88 @@ def test_gemm_two_cta_form(M, N, K, act, res):
     R = _rand((M, N), 1.0, 53) if res else None
     out = run_gemm(A, W, bias=bias, act=act, residual=R)
     _check(out, ref_gemm(A, W, bias, act, R), f"2-CTA gemm {M}x{N}x{K} act={act} res={res}")
+
+
+_CANARY = 1 << 20
+
+
+def _sk_ws():
+    """scratch of exactly the advertised size, followed by a canary that must never be written"""
+    L, lib = _lib()
+    n = lib.vz_gemm_sk_workspace_bytes()
+    buf = torch.zeros(n + _CANARY, dtype=torch.uint8, device="cuda")
+    buf[n:] = 0xA5
+    return buf[:n], buf
+
+
+def _canary_intact(buf):
+    return bool((buf[-_CANARY:] == 0xA5).all().item())
+
+
+@pytest.mark.parametrize("M,N,K,act,res", [
+    (1280, 4096, 4096, 0, True),     # Q-Former out-proj: 80 pair tiles on 74 CTA pairs (2-CTA form)
+    (1280, 8192, 4096, 2, False),    # FFN1: 160 pair tiles
+    (1280, 4096, 8192, 0, True),     # FFN2: 128 k-blocks
+    (1280, 512, 5120, 0, False),     # fewer tiles than SMs: every tile is shared by several CTAs (1-CTA form)
+    (1154, 3072, 1024, 1, False),    # ragged M, quick-GELU
+    (23080, 3072, 1024, 0, False),   # ViT qkv at the bench size: 1092 pair tiles, 14.76 rounds
+    (577, 1024, 4096, 0, True),      # one tile: 40 tiles of 128x128 shared by all 148 SMs
+    (24, 8192, 4096, 0, False),      # text K/V rows of a short prompt
+])
+def test_gemm_stream_k_tail(M, N, K, act, res):
+    """With a stream-K scratch buffer the last, partially filled round of tiles is split along K over all
+    SMs; partial sums are added in a fixed order, so two runs agree bit for bit and the result matches
+    the whole-tile schedule within bf16 rounding."""
+    L, lib = _lib()
+    A, W = _rand((M, K), 1.0, 61), _rand((N, K), K ** -0.5, 62)
+    bias = torch.randn(N, device="cuda") * 0.3
+    R = _rand((M, N), 1.0, 63) if res else None
+    ws, ws_all = _sk_ws()
+
+    def run(use_sk):
+        out = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
+        g = L.GemmArgs()
+        g.A, g.W, g.out, g.bias = A.data_ptr(), W.data_ptr(), out.data_ptr(), bias.data_ptr()
+        g.residual = R.data_ptr() if R is not None else None
+        g.M, g.N, g.K, g.lda, g.ldw, g.ldo, g.ldr = M, N, K, K, K, N, (N if R is not None else 0)
+        g.act = act
+        if use_sk:
+            g.sk_ws, g.sk_ws_bytes = ws.data_ptr(), ws.numel()
+        L.check(lib.vz_gemm_bf16(C.byref(g), L.stream_ptr()), "vz_gemm_bf16")
+        torch.cuda.synchronize()
+        return out
+
+    ref = ref_gemm(A, W, bias, act, R)
+    o_sk, o_sk2, o_dp = run(True), run(True), run(False)
+    _check(o_sk, ref, f"stream-K gemm {M}x{N}x{K}")
+    assert torch.equal(o_sk, o_sk2), "stream-K result must be deterministic"
+    assert _canary_intact(ws_all), "stream-K scratch overrun"
+    d = (o_sk.float() - o_dp.float()).abs().max().item()
+    print("stream-K vs whole-tile max diff", d)
+    assert d <= 2.0 ** -6 * max(ref.abs().max().item(), 1.0)
+
+
+def test_gemm_stream_k_batched_f32():
+    """batched fp32-output form (cross-attention scores): 120 tiles of 128x128... split along K = 5120"""
+    L, lib = _lib()
+    T, Mq, Kf, Np = 40, 256, 5120, 576
+    a = _rand((T, Mq, Kf), 1.0, 71)
+    f = _rand((T, Np, Kf), Kf ** -0.5, 72)
+    ws, ws_all = _sk_ws()
+    outs = []
+    for use_sk in (True, False):
+        s = torch.full((T, Mq, Np), float("nan"), dtype=torch.float32, device="cuda")
+        g = L.GemmArgs()
+        g.A, g.W, g.out = a.data_ptr(), f.data_ptr(), s.data_ptr()
+        g.M, g.N, g.K, g.lda, g.ldw, g.ldo = Mq, Np, Kf, Kf, Kf, Np
+        g.batch, g.out_f32 = T, 1
+        g.a_bstride, g.w_bstride, g.o_bstride = Mq * Kf, Np * Kf, Mq * Np
+        if use_sk:
+            g.sk_ws, g.sk_ws_bytes = ws.data_ptr(), ws.numel()
+        L.check(lib.vz_gemm_bf16(C.byref(g), L.stream_ptr()), "batched f32 stream-K")
+        torch.cuda.synchronize()
+        outs.append(s)
+    ref = torch.einsum("tmk,tnk->tmn", a.float(), f.float())
+    for s in outs:
+        assert (s - ref).abs().max().item() < 2e-3
+    assert _canary_intact(ws_all), "stream-K scratch overrun"

@@ -18,7 +18,10 @@ SHAPES = [("qkv", M, 3072, 1024, 0, 0, 1), ("o", M, 1024, 1024, 0, 1, 1), ("fc1"
           ("ffn1", 1280, 8192, 4096, 2, 0, 1), ("ffn2", 1280, 4096, 8192, 0, 1, 1), ("ca_q", 1280, 4096, 4096, 0, 0, 1)]
 
 
-def run(name, M, N, K, act, res, reps=20, ln=False, stats=False):
+SK_WS = torch.zeros(lib.vz_gemm_sk_workspace_bytes(), dtype=torch.uint8, device="cuda")
+
+
+def run(name, M, N, K, act, res, reps=20, ln=False, stats=False, sk=False):
     A = torch.randn((M, K), device="cuda").to(torch.bfloat16)
     W = (torch.randn((N, K), device="cuda") * K ** -0.5).to(torch.bfloat16)
     bias = torch.randn(N, device="cuda")
@@ -29,6 +32,8 @@ def run(name, M, N, K, act, res, reps=20, ln=False, stats=False):
     g.residual = R.data_ptr() if res else None
     g.M, g.N, g.K, g.lda, g.ldw, g.ldo, g.ldr = M, N, K, K, K, N, N
     g.act = act
+    if sk:
+        g.sk_ws, g.sk_ws_bytes = SK_WS.data_ptr(), SK_WS.numel()
     keep = []
     if ln:
         npp = 8
@@ -55,7 +60,7 @@ def run(name, M, N, K, act, res, reps=20, ln=False, stats=False):
             ts.append(e0.elapsed_time(e1))
     ts.sort()
     med = ts[len(ts) // 2]
-    name = name + ("+ln" if ln else "") + ("+st" if stats else "")
+    name = name + ("+ln" if ln else "") + ("+st" if stats else "") + ("+sk" if sk else "")
     print(f"{name:10s} M={M:6d} N={N:6d} K={K:5d} act={act} res={res}: {med * 1e3:8.1f} us  {2.0 * M * N * K / med / 1e9:7.1f} TFLOP/s")
 
 
@@ -69,3 +74,4 @@ if os.environ.get("VZ_BENCH_LN") == "1":
 else:
     for s in SHAPES:
         run(*s[:6])
+        run(*s[:6], sk=True)

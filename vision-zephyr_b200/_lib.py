@@ -31,6 +31,7 @@ class GemmArgs(C.Structure):
         ("r_bstride", C.c_longlong), ("bias_bstride", C.c_longlong),
         ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_np", C.c_int), ("ln_eps", C.c_float),
         ("stats_out", C.c_void_p), ("stats_np", C.c_int),
+        ("sk_ws", C.c_void_p), ("sk_ws_bytes", C.c_size_t),
     ]
 
 
@@ -92,6 +93,7 @@ SYMBOLS = {
     "vz_version": (_i, []),
     "vz_gemm_bf16": (_i, [C.POINTER(GemmArgs), _vp]),
     "vz_gemm_stats_partials": (_i, [_i, _i]),
+    "vz_gemm_sk_workspace_bytes": (_sz, []),
     "vz_kernel_launches": (C.c_longlong, []),
     "vz_gemm_profile": (_i, [_i]),
     "vz_gemm_profile_read": (_i, [C.POINTER(C.c_longlong), C.POINTER(C.c_double), C.POINTER(C.c_double)]),

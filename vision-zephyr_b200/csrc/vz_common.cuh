@@ -43,6 +43,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // internal launchers shared between translation units
 int gemm_launch(const vz_gemm_args& a, cudaStream_t st);
 int gemm_stats_partials(int M, int N);
+size_t gemm_sk_workspace_bytes();
 int row_stats_launch(const void* x, int ldx, int M, int D, float* stats, cudaStream_t st);
 int layernorm_launch(const void* x, int ldx, const float* g, const float* b, void* out, int ldo,
                      int M, int D, float eps, const int32_t* row_map, int rows_per_map,

@@ -19,6 +19,8 @@ namespace vz {
 thread_local int g_last_cuda_error = 0;
 
 static std::atomic<long long> g_launches{0};
+static std::atomic<uint32_t> g_sk_epoch{0};   // stream-K hand-over flags carry the epoch of the launch that wrote them
+constexpr size_t kSkFlagBytes = 8192;         // >= SMs * epilogue warps * 4 bytes
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // Optional measurement hook (bench.py): CUDA events around every tcgen05 GEMM launch, on the
@@ -74,7 +76,51 @@ struct GemmDev {
   // ... and producer side: partial row statistics of THIS GEMM's output
   float* stats_out;        // [M][stats_np][2] or NULL
   int stats_np;
+  // stream-K tail (see WorkIter): the first dp_tiles tiles are walked whole, round-robin; the k-blocks of
+  // the last sk_tiles tiles are cut into one contiguous range per worker
+  int dp_tiles, sk_tiles;
+  float4* sk_ws;           // per (worker, CTA rank): one 128 x BN fp32 partial accumulator
+  uint32_t* sk_flags;      // per (worker, CTA rank, epilogue warp): epoch of the partial it holds
+  uint32_t sk_epoch;
 };
+
+// The work list of one worker (a CTA, or a CTA pair in the 2-CTA form).  Data-parallel part: tiles
+// worker, worker + W, ... < dp_tiles, all k-blocks each.  Stream-K part: the sk_tiles * num_k k-blocks
+// of the remaining tiles are split evenly; worker w owns units [U w / W, U (w + 1) / W), which cover the
+// TAIL of one tile (k-blocks kb0 > 0: a partial sum, handed over through global memory), then whole
+// tiles, then the HEAD of one tile (kb0 == 0, kb1 < num_k: this worker finishes the tile by adding the
+// partial sums of the workers after it, in worker order -> deterministic).  Tails come first in every
+// worker's list and never wait, so the hand-over cannot deadlock.
+struct WorkItem { int tile, kb0, kb1; };
+struct WorkIter {
+  int W, dp_tiles, num_k, next_dp, u, u1;
+  __device__ __forceinline__ WorkIter(int w, int W_, int dp_tiles_, int sk_tiles, int num_k_)
+      : W(W_), dp_tiles(dp_tiles_), num_k(num_k_), next_dp(w) {
+    const int U = sk_tiles * num_k_;
+    u = (int)(((long long)U * w) / W_);
+    u1 = (int)(((long long)U * (w + 1)) / W_);
+  }
+  __device__ __forceinline__ bool next(WorkItem& it) {
+    if (next_dp < dp_tiles) { it.tile = next_dp; it.kb0 = 0; it.kb1 = num_k; next_dp += W; return true; }
+    if (u < u1) {
+      const int t = u / num_k, base = t * num_k;
+      const int end = u1 < base + num_k ? u1 : base + num_k;
+      it.tile = dp_tiles + t; it.kb0 = u - base; it.kb1 = end - base;
+      u = end;
+      return true;
+    }
+    return false;
+  }
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk, int& b) {
   const int per_batch = num_m * num_n;
@@ -131,7 +177,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.num_m * p.num_n * p.batch;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -162,10 +207,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     // ============================ TMA producer ============================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = worker; tile < total_tiles; tile += n_workers) {
+      WorkIter work(worker, n_workers, p.dp_tiles, p.sk_tiles, p.num_k);
+      WorkItem it;
+      while (work.next(it)) {
         int m_blk, n_blk, bz;
-        tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk, bz);
-        for (int kb = 0; kb < p.num_k; ++kb) {
+        tile_coords(it.tile, p.num_m, p.num_n, m_blk, n_blk, bz);
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
           if (TWO) {
             // both CTAs' bytes are counted on the leader's barrier
@@ -189,11 +236,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     if (lane == 0 && rank == 0) {   // 2-CTA: only the leader issues; the MMA spans both SMs
       constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = worker; tile < total_tiles; tile += n_workers) {
+      WorkIter work(worker, n_workers, p.dp_tiles, p.sk_tiles, p.num_k);
+      WorkItem it;
+      while (work.next(it)) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 200 + acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_k; ++kb) {
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase, 300 + stage);
           tc_fence_after();
           const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(sA + stage * C::A_BYTES));
@@ -202,9 +251,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 32 B (16 bf16) along K inside the swizzle atom: +2 in the (addr>>4) field
             if (TWO) umma_bf16_2cta(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                                    (kb | k) != 0 ? 1u : 0u);
+                                    (kb != it.kb0 || k != 0) ? 1u : 0u);
             else umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                           (kb | k) != 0 ? 1u : 0u);
+                           (kb != it.kb0 || k != 0) ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs) once these MMAs retire
           if (TWO) umma_commit_2cta(&empty_bar[stage], 3);
@@ -234,9 +283,54 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     const int co_r = lane >> 2, co_j = lane & 3;
     uint32_t acc = 0, acc_phase = 0;
     uint32_t cc = 0;  // chunk counter: selects which half of the warp's staging area is current
-    for (int tile = worker; tile < total_tiles; tile += n_workers) {
+    WorkIter work(worker, n_workers, p.dp_tiles, p.sk_tiles, p.num_k);
+    WorkItem it;
+    // stream-K hand-over slots: element (row 32 q + lane, column 32 c + 4 j .. + 3) of the CTA's partial
+    // tile is float4 [((q * BN/32 + c) * 8 + j) * 32 + lane] -- the register layout, fully coalesced
+    constexpr int SK_SLOT4 = BM * BN / 4;   // float4 per (worker, rank)
+    constexpr int NR = TWO ? 2 : 1;         // CTAs per worker: slot / flag index = worker * NR + rank < number of SMs
+    while (work.next(it)) {
       int m_blk, n_blk, bz;
-      tile_coords(tile, p.num_m, p.num_n, m_blk, n_blk, bz);
+      tile_coords(it.tile, p.num_m, p.num_n, m_blk, n_blk, bz);
+      if (it.kb0 > 0) {
+        // ---- tail of a tile that an earlier worker finishes: dump the raw accumulator, raise the flag ----
+        mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+        float4* slot = p.sk_ws + (size_t)(worker * NR + (int)rank) * SK_SLOT4;
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += 2) {
+          if (n_blk * BN + c * 32 >= p.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + c * 32, r);
+          tmem_ld_wait();
+          float4* dst = slot + (size_t)((q * (BN / 32) + c) * 8) * 32 + lane;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j * 32] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                      __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+        tc_fence_before();
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          st_release_u32(p.sk_flags + (worker * NR + (int)rank) * kEpiWarps + e, p.sk_epoch);
+          if (TWO) mbar_arrive_cluster(&tempty_bar[acc], 0);
+          else mbar_arrive(&tempty_bar[acc]);
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
+      // head of a stream-K tile: the workers after this one hold the rest of its k-blocks
+      int sk_first = 0, sk_last = -1;
+      if (it.kb1 < p.num_k) {
+        const long long U = (long long)p.sk_tiles * p.num_k;
+        const long long tile_end = (long long)(it.tile - p.dp_tiles + 1) * p.num_k;
+        sk_first = worker + 1;
+        sk_last = worker;
+        while (sk_last + 1 < n_workers && (U * (sk_last + 1)) / n_workers < tile_end) ++sk_last;
+      }
       const int m_base = m_blk * TILE_M + (int)rank * BM + q * 32;
       const float* bias_b = p.bias ? p.bias + (size_t)bz * p.bias_bstride : nullptr;
       const __nv_bfloat16* res_b = RES ? p.residual + (size_t)bz * p.r_bstride : nullptr;
@@ -304,6 +398,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        for (int sw = sk_first; sw <= sk_last; ++sw) {   // stream-K: add the later workers' partial sums, in order
+          const uint32_t* flag = p.sk_flags + (sw * NR + (int)rank) * kEpiWarps + e;
+          if (c == half) {   // first chunk of the tile: the partial may still be on its way
+            uint32_t polls = 0;
+            while (ld_acquire_u32(flag) != p.sk_epoch) {
+              if (++polls > (1u << 28)) { printf("vz: stream-K hand-over timeout worker=%d from=%d\n", worker, sw); __trap(); }
+            }
+          }
+          const float4* src = p.sk_ws + (size_t)(sw * NR + (int)rank) * SK_SLOT4 + (size_t)((q * (BN / 32) + c) * 8) * 32 + lane;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldcg(src + j * 32);
+            v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+          }
+        }
         if (LN) {
           // LN(x) W^T + b  ==  rstd * (x W'^T - mu * colsum(W')) + b'   (gamma folded into W', beta into b')
           const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + col0);
@@ -493,7 +602,7 @@ int make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int
 }
 
 template <int BN, int ACT, bool RES, bool LN, bool STATS, bool F32, bool TWO>
-int launch_tc(const vz_gemm_args& a, const GemmDev& p, int num_sms, cudaStream_t st) {
+int launch_tc(const vz_gemm_args& a, const GemmDev& p_in, int num_sms, cudaStream_t st) {
   using C = Cfg<BN, TWO>;
   CUtensorMap tmA, tmB;
   VZ_TRY(make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM, a.batch, a.a_bstride));
@@ -504,9 +613,32 @@ int launch_tc(const vz_gemm_args& a, const GemmDev& p, int num_sms, cudaStream_t
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_done = true;
   }
+  GemmDev p = p_in;
   const long tiles = (long)p.num_m * p.num_n * p.batch;
   const int workers = TWO ? num_sms / 2 : num_sms;
-  const int grid = (tiles < workers ? (int)tiles : workers) * (TWO ? 2 : 1);
+  p.dp_tiles = (int)tiles;
+  p.sk_tiles = 0;
+  p.sk_ws = nullptr; p.sk_flags = nullptr; p.sk_epoch = 0;
+  // Stream-K tail: when the tile count is not a multiple of the worker count, the last (partial) round
+  // leaves most SMs idle; instead the k-blocks of the last full round + the remainder are split evenly.
+  // Worth it when the balanced schedule beats the rounded one by more than the hand-over (~6 k-blocks).
+  static const int sk_on = []() { const char* e = getenv("VZ_GEMM_SK"); return e ? atoi(e) : 1; }();
+  const size_t sk_need = kSkFlagBytes + (size_t)num_sms * BM * BN * sizeof(float);
+  if (sk_on && a.sk_ws && a.sk_ws_bytes >= sk_need && aligned16(a.sk_ws) && tiles % workers != 0 && p.num_k >= 8 &&
+      tiles * p.num_k >= workers) {
+    const long full = tiles / workers;
+    const double t_dp = (double)(full + 1) * p.num_k;
+    const double t_sk = (double)tiles * p.num_k / workers + 6.0;
+    if (t_sk < 0.96 * t_dp) {
+      p.sk_tiles = full == 0 ? (int)tiles : (int)(workers + tiles % workers);
+      p.dp_tiles = (int)tiles - p.sk_tiles;
+      p.sk_flags = reinterpret_cast<uint32_t*>(a.sk_ws);
+      p.sk_ws = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(a.sk_ws) + kSkFlagBytes);
+      p.sk_epoch = g_sk_epoch.fetch_add(1, std::memory_order_relaxed) + 1;
+      if (p.sk_epoch == 0) p.sk_epoch = g_sk_epoch.fetch_add(1, std::memory_order_relaxed) + 1;
+    }
+  }
+  const int grid = (p.sk_tiles > 0 ? workers : (tiles < workers ? (int)tiles : workers)) * (TWO ? 2 : 1);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof.on) {
     std::lock_guard<std::mutex> lk(g_prof.mu);
@@ -617,6 +749,14 @@ int pick_tile_n(int M, int N, int batch, int num_sms) {
   return bn;
 }
 }  // namespace
+
+size_t gemm_sk_workspace_bytes() {
+  int dev = 0, num_sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (num_sms < 148) num_sms = 148;
+  return kSkFlagBytes + (size_t)num_sms * BM * 256 * sizeof(float);
+}
 
 int gemm_stats_partials(int M, int N) {
   int dev = 0, num_sms = 148;
@@ -733,6 +873,8 @@ extern "C" int vz_gemm_profile_read(long long* launches, double* total_ms, doubl
 }
 
 extern "C" int vz_gemm_stats_partials(int M, int N) { return vz::gemm_stats_partials(M, N); }
+
+extern "C" size_t vz_gemm_sk_workspace_bytes(void) { return vz::gemm_sk_workspace_bytes(); }
 
 extern "C" int vz_gemm_bf16(const vz_gemm_args* args, void* stream) {
   if (!args) return VZ_ERR_BAD_ARG;

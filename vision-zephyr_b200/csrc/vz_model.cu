@@ -22,9 +22,17 @@ struct Bump {
 
 constexpr size_t kB16 = 2;
 
+// stream + the module's stream-K scratch; converts to the stream for the plain launchers
+struct Ctx {
+  cudaStream_t st;
+  void* sk_ws;
+  size_t sk_bytes;
+  operator cudaStream_t() const { return st; }
+};
+
 int gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act,
          const void* residual, int ldr, void* out, int ldo, int row_mode, int rows_per, int simple,
-         cudaStream_t st) {
+         const Ctx& st) {
   vz_gemm_args g;
   g.A = A; g.W = W; g.out = out; g.bias = bias; g.residual = residual;
   g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldo = ldo; g.ldr = ldr;
@@ -32,13 +40,14 @@ int gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, co
   g.batch = 1; g.out_f32 = 0;
   g.a_bstride = g.w_bstride = g.o_bstride = g.r_bstride = g.bias_bstride = 0;
   g.ln_stats = nullptr; g.ln_colsum = nullptr; g.ln_np = 0; g.ln_eps = 0.f; g.stats_out = nullptr; g.stats_np = 0;
+  g.sk_ws = st.sk_ws; g.sk_ws_bytes = st.sk_bytes;
   return gemm_launch(g, st);
 }
 
 // GEMM with a LayerNorm folded in front (consumer) and/or partial row statistics behind (producer)
 int gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act,
             const void* residual, int ldr, void* out, int ldo, const float* ln_stats, int ln_np,
-            const float* ln_colsum, float* stats_out, int stats_np, int simple, cudaStream_t st) {
+            const float* ln_colsum, float* stats_out, int stats_np, int simple, const Ctx& st) {
   vz_gemm_args g;
   g.A = A; g.W = W; g.out = out; g.bias = bias; g.residual = residual;
   g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldo = ldo; g.ldr = ldr;
@@ -47,6 +56,7 @@ int gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
   g.a_bstride = g.w_bstride = g.o_bstride = g.r_bstride = g.bias_bstride = 0;
   g.ln_stats = ln_stats; g.ln_colsum = ln_colsum; g.ln_np = ln_np; g.ln_eps = 1e-5f;
   g.stats_out = simple ? nullptr : stats_out; g.stats_np = stats_np;
+  g.sk_ws = st.sk_ws; g.sk_ws_bytes = st.sk_bytes;
   VZ_TRY(gemm_launch(g, st));
   // the debug GEMM has no statistics epilogue: a row kernel produces the single partial instead
   if (simple && stats_out) VZ_TRY(row_stats_launch(out, ldo, M, N, stats_out, st));
@@ -56,7 +66,7 @@ int gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
 // batched tcgen05 GEMM (strides in elements); fp32 output when out_f32
 int gemm_batched(const void* A, int lda, long long sa, const void* W, int ldw, long long sw, int batch, int M,
                  int N, int K, const float* bias, long long sbias, void* out, int ldo, long long so, int out_f32,
-                 cudaStream_t st) {
+                 const Ctx& st) {
   vz_gemm_args g;
   g.A = A; g.W = W; g.out = out; g.bias = bias; g.residual = nullptr;
   g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldo = ldo; g.ldr = 0;
@@ -64,6 +74,7 @@ int gemm_batched(const void* A, int lda, long long sa, const void* W, int ldw, l
   g.batch = batch; g.out_f32 = out_f32;
   g.a_bstride = sa; g.w_bstride = sw; g.o_bstride = so; g.r_bstride = 0; g.bias_bstride = sbias;
   g.ln_stats = nullptr; g.ln_colsum = nullptr; g.ln_np = 0; g.ln_eps = 0.f; g.stats_out = nullptr; g.stats_np = 0;
+  g.sk_ws = st.sk_ws; g.sk_ws_bytes = st.sk_bytes;
   return gemm_launch(g, st);
 }
 
@@ -71,6 +82,8 @@ struct VitWs {
   void* hs[VZ_VIT_LAYERS + 1];
   void *xn, *qkv, *attn, *mid, *h;
   float *statsA, *statsB;  // [M][<=16][2] partial row statistics (LayerNorm fused into the GEMMs)
+  void* sk;                // stream-K scratch of the GEMMs
+  size_t sk_bytes;
   size_t total;
 };
 
@@ -88,12 +101,16 @@ VitWs vit_layout(void* base, int T) {
   w.h = b.take(M * VZ_VIT_MLP * kB16);
   w.statsA = reinterpret_cast<float*>(b.take(M * 16 * 2 * sizeof(float)));
   w.statsB = reinterpret_cast<float*>(b.take(M * 16 * 2 * sizeof(float)));
+  w.sk_bytes = gemm_sk_workspace_bytes();
+  w.sk = b.take(w.sk_bytes);
   w.total = b.off + 256;
   return w;
 }
 
 struct QfWs {
   void *featsN, *fT, *qk, *S, *Pm, *PF, *x, *xn, *qkv, *attn, *q, *hbuf, *q0n, *qkv0, *tn, *kv_text, *attn0, *x1;
+  void* sk;                // stream-K scratch of the GEMMs
+  size_t sk_bytes;
   size_t total;
 };
 
@@ -121,6 +138,8 @@ QfWs qf_layout(void* base, int T, int n_samples, int text_rows) {
   w.kv_text = b.take(R1 * 2 * VZ_QF_WIDTH * kB16);
   w.attn0 = b.take(Bs * VZ_QF_WIDTH * kB16);
   w.x1 = b.take(Bs * VZ_QF_WIDTH * kB16);
+  w.sk_bytes = gemm_sk_workspace_bytes();
+  w.sk = b.take(w.sk_bytes);
   w.total = b.off + 256;
   return w;
 }
@@ -157,7 +176,8 @@ extern "C" int vz_vit_forward(const vz_vit_weights* w, const void* patches, int 
   if (!aligned16(workspace) || !aligned16(patches) || !aligned16(fused_out)) return VZ_ERR_BAD_ARG;
   const VitWs ws = vit_layout(workspace, T);
   if (ws.total > workspace_bytes) return VZ_ERR_WORKSPACE;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const Ctx st{reinterpret_cast<cudaStream_t>(stream), ws.sk, ws.sk_bytes};
+  VZ_CUDA_CHECK(cudaMemsetAsync(ws.sk, 0, 8192, st));   // stream-K hand-over flags (epoch 0 = nothing there)
   const int M = T * VZ_VIT_TOKENS, MP = T * VZ_VIT_PATCHES, D = VZ_VIT_WIDTH;
 
   // embeddings: class token rows, then conv-as-GEMM (+ position embedding in the epilogue)
@@ -207,7 +227,8 @@ extern "C" int vz_qformer_forward(const vz_qf_weights* w, const void* feats, int
   if (!aligned16(workspace) || !aligned16(feats) || !aligned16(out)) return VZ_ERR_BAD_ARG;
   const QfWs ws = qf_layout(workspace, T, has_text ? n_samples : 1, has_text ? text_rows : 0);
   if (ws.total > workspace_bytes) return VZ_ERR_WORKSPACE;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const Ctx st{reinterpret_cast<cudaStream_t>(stream), ws.sk, ws.sk_bytes};
+  VZ_CUDA_CHECK(cudaMemsetAsync(ws.sk, 0, 8192, st));   // stream-K hand-over flags (epoch 0 = nothing there)
   const int P = T * VZ_VIT_PATCHES, M = T * VZ_QF_QUERIES, D = VZ_QF_WIDTH, D3 = 3 * VZ_QF_WIDTH;
   const int FW = VZ_FUSED_WIDTH, NP = VZ_VIT_PATCHES, HQ = VZ_QF_HEADS * VZ_QF_QUERIES, HD = VZ_QF_HEAD_DIM;
   const __nv_bfloat16* qkv0 = reinterpret_cast<const __nv_bfloat16*>(ws.qkv0);
