@@ -94,6 +94,9 @@ typedef struct {
    * order, so results stay deterministic).  NULL = whole tiles only.                                    */
   void* sk_ws;
   size_t sk_ws_bytes;
+  /* 1 = W is given as [K, ldw] row-major with N contiguous (out = A * W instead of A * W^T); N % 64 == 0,
+   * plain epilogue (bias only).  Used for P * f in the cross-attention: no transposed copy of f.        */
+  int w_is_kn;
 } vz_gemm_args;
 size_t vz_gemm_sk_workspace_bytes(void);
 

@@ -328,3 +328,23 @@ def test_gemm_stream_k_batched_f32():
     for s in outs:
         assert (s - ref).abs().max().item() < 2e-3
     assert _canary_intact(ws_all), "stream-K scratch overrun"
+
+
+@pytest.mark.parametrize("T,M,N,K", [(40, 256, 5120, 576), (1, 256, 5120, 576), (3, 200, 640, 192), (1, 1280, 512, 4096)])
+def test_gemm_weights_as_k_by_n(T, M, N, K):
+    """w_is_kn: the second operand is [K, N] row-major (out = A W), consumed as an MN-major tcgen05 operand --
+    the cross-attention's P f product reads the features in place instead of a transposed copy"""
+    L, lib = _lib()
+    A = _rand((T, M, K), 0.1, 81)
+    Wkn = _rand((T, K, N), 1.0, 82)
+    bias = torch.randn(N, device="cuda") * 0.2
+    out = torch.full((T, M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+    g = L.GemmArgs()
+    g.A, g.W, g.out, g.bias = A.data_ptr(), Wkn.data_ptr(), out.data_ptr(), bias.data_ptr()
+    g.M, g.N, g.K, g.lda, g.ldw, g.ldo = M, N, K, K, N, N
+    g.batch, g.a_bstride, g.w_bstride, g.o_bstride = T, M * K, K * N, M * N
+    g.w_is_kn = 1
+    L.check(lib.vz_gemm_bf16(C.byref(g), L.stream_ptr()), "w_is_kn gemm")
+    torch.cuda.synchronize()
+    ref = torch.einsum("tmk,tkn->tmn", A.float(), Wkn.float()) + bias
+    _check(out, ref, f"[K,N]-operand gemm T={T} {M}x{N}x{K}")

@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
         ("r_bstride", C.c_longlong), ("bias_bstride", C.c_longlong),
         ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_np", C.c_int), ("ln_eps", C.c_float),
         ("stats_out", C.c_void_p), ("stats_np", C.c_int),
-        ("sk_ws", C.c_void_p), ("sk_ws_bytes", C.c_size_t),
+        ("sk_ws", C.c_void_p), ("sk_ws_bytes", C.c_size_t), ("w_is_kn", C.c_int),
     ]
 
 

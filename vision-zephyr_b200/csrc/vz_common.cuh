@@ -53,7 +53,6 @@ int fuse_launch(const void* const* hs21, int T, const float* g, const float* b, 
 int cls_rows_launch(const void* cls, const void* pos, void* emb, int T, cudaStream_t st);
 int gather_rows_launch(const void* in, void* out, int M, int row_bytes, const int32_t* row_map,
                        int rows_per, cudaStream_t st);
-int transpose_launch(const void* in, void* out, int batch, int R, int C, cudaStream_t st);
 int softmax_rows_launch(const float* s, void* p, int rows, int n, float scale, cudaStream_t st);
 int vit_attn_launch(const void* qkv, void* out, int T, cudaStream_t st);
 int vit_attn_tc_launch(const void* qkv, void* out, int T, cudaStream_t st);

@@ -151,7 +151,9 @@ __device__ __forceinline__ float act_apply(float x, int act) {
 // Epilogue features are template parameters (ACT activation, RES residual, LN fused LayerNorm
 // consumer, STATS fused LayerNorm producer, F32 fp32 output): the epilogue sits at the register
 // limit of a 384-thread CTA, so each instantiation only carries the state it needs.
-template <int BN, int ACT, bool RES, bool LN, bool STATS, bool F32, bool TWO>
+// BKN: the B operand is given as [K, N] row-major (N contiguous, "MN-major" for the tensor core): its
+// stage is BN/64 TMA boxes of 64 k-rows x 64 columns (8 KB each, 128-byte rows, 8-row groups 1 KB apart).
+template <int BN, int ACT, bool RES, bool LN, bool STATS, bool F32, bool TWO, bool BKN = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                          const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
@@ -220,12 +222,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             else mbar_arrive_cluster(&full_bar[stage], 0);
             tma_load_3d_2cta(&tmA, &full_bar[stage], sA + stage * C::A_BYTES, kb * BK,
                              m_blk * TILE_M + (int)rank * BM, bz);
-            tma_load_3d_2cta(&tmB, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK,
-                             n_blk * BN + (int)rank * (BN / 2), bz);
+            if (BKN) {
+#pragma unroll
+              for (int i = 0; i < BN / 2 / 64; ++i)
+                tma_load_3d_2cta(&tmB, &full_bar[stage], sB + stage * C::B_BYTES + i * 8192,
+                                 n_blk * BN + (int)rank * (BN / 2) + i * 64, kb * BK, bz);
+            } else {
+              tma_load_3d_2cta(&tmB, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK,
+                               n_blk * BN + (int)rank * (BN / 2), bz);
+            }
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
             tma_load_3d(&tmA, &full_bar[stage], sA + stage * C::A_BYTES, kb * BK, m_blk * BM, bz);
-            tma_load_3d(&tmB, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK, n_blk * BN, bz);
+            if (BKN) {
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_3d(&tmB, &full_bar[stage], sB + stage * C::B_BYTES + i * 8192, n_blk * BN + i * 64,
+                            kb * BK, bz);
+            } else {
+              tma_load_3d(&tmB, &full_bar[stage], sB + stage * C::B_BYTES, kb * BK, n_blk * BN, bz);
+            }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -234,7 +250,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   } else if (warp == 1) {
     // ============================ MMA issuer ==============================
     if (lane == 0 && rank == 0) {   // 2-CTA: only the leader issues; the MMA spans both SMs
-      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
+      constexpr uint32_t idesc = umma_idesc_bf16_ex(TILE_M, BN, 0, BKN ? 1 : 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       WorkIter work(worker, n_workers, p.dp_tiles, p.sk_tiles, p.num_k);
       WorkItem it;
@@ -246,13 +262,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           mbar_wait(&full_bar[stage], phase, 300 + stage);
           tc_fence_after();
           const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(sA + stage * C::A_BYTES));
-          const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(sB + stage * C::B_BYTES));
+          // [K, N] operand: 64-column atoms 8 KB apart (LBO); one UMMA_K step = 16 k-rows = 2 KB
+          const uint64_t b_desc = BKN ? (umma_smem_desc_sw128(smem_u32(sB + stage * C::B_BYTES)) +
+                                         ((uint64_t)((8192 >> 4) - 1) << 16))
+                                      : umma_smem_desc_sw128(smem_u32(sB + stage * C::B_BYTES));
+          constexpr uint64_t b_step = BKN ? (2048 >> 4) : 2;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 32 B (16 bf16) along K inside the swizzle atom: +2 in the (addr>>4) field
-            if (TWO) umma_bf16_2cta(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+            if (TWO) umma_bf16_2cta(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)k * b_step, idesc,
                                     (kb != it.kb0 || k != 0) ? 1u : 0u);
-            else umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+            else umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)k * b_step, idesc,
                            (kb != it.kb0 || k != 0) ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs) once these MMAs retire
@@ -601,15 +621,16 @@ int make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int
   return VZ_OK;
 }
 
-template <int BN, int ACT, bool RES, bool LN, bool STATS, bool F32, bool TWO>
+template <int BN, int ACT, bool RES, bool LN, bool STATS, bool F32, bool TWO, bool BKN = false>
 int launch_tc(const vz_gemm_args& a, const GemmDev& p_in, int num_sms, cudaStream_t st) {
   using C = Cfg<BN, TWO>;
   CUtensorMap tmA, tmB;
   VZ_TRY(make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM, a.batch, a.a_bstride));
-  VZ_TRY(make_tmap(&tmB, a.W, a.N, a.K, a.ldw, TWO ? BN / 2 : BN, a.batch, a.w_bstride));
+  if (BKN) VZ_TRY(make_tmap(&tmB, a.W, a.K, a.N, a.ldw, 64, a.batch, a.w_bstride));   // [K, N]: 64 x 64 boxes
+  else VZ_TRY(make_tmap(&tmB, a.W, a.N, a.K, a.ldw, TWO ? BN / 2 : BN, a.batch, a.w_bstride));
   static bool attr_done = false;  // idempotent attribute; benign race
   if (!attr_done) {
-    VZ_CUDA_CHECK(cudaFuncSetAttribute((gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO>),
+    VZ_CUDA_CHECK(cudaFuncSetAttribute((gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO, BKN>),
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_done = true;
   }
@@ -665,10 +686,10 @@ int launch_tc(const vz_gemm_args& a, const GemmDev& p_in, int num_sms, cudaStrea
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VZ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO>, tmA, tmB, p));
+    VZ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO, BKN>, tmA, tmB, p));
     count_launch();
   } else {
-    gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO><<<grid, kThreads, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+    gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO, BKN><<<grid, kThreads, C::SMEM_BYTES, st>>>(tmA, tmB, p);
     VZ_LAUNCH_CHECK();
   }
   if (e1) VZ_CUDA_CHECK(cudaEventRecord(e1, st));
@@ -680,6 +701,10 @@ template <int BN, bool TWO = false>
 int launch_bn(const vz_gemm_args& a, const GemmDev& p, int num_sms, cudaStream_t st) {
   const int act = a.act;
   const bool res = a.residual != nullptr, ln = a.ln_stats != nullptr, stt = a.stats_out != nullptr, f32 = a.out_f32 != 0;
+  if (a.w_is_kn) {   // [K, N] weights: plain epilogue only (the cross-attention P f product)
+    if (act || res || ln || stt || f32 || BN == 192) return VZ_ERR_UNSUPPORTED;
+    if constexpr (BN != 192) return launch_tc<BN, 0, false, false, false, false, TWO, true>(a, p, num_sms, st);
+  }
 #define VZ_GO(ACT, RES, LN, ST, F32) return launch_tc<BN, ACT, RES, LN, ST, F32, TWO>(a, p, num_sms, st)
   if (f32) { if (act || res || ln || stt) return VZ_ERR_UNSUPPORTED; VZ_GO(0, false, false, false, true); }
   if (stt) { if (!res || act || ln) return VZ_ERR_UNSUPPORTED; VZ_GO(0, true, false, true, false); }
@@ -774,6 +799,7 @@ int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
       (a.bias && !aligned16(a.bias)))
     return VZ_ERR_BAD_ARG;
   if (a.N % 32 != 0 || a.K % 8 != 0) return VZ_ERR_UNSUPPORTED;
+  if (a.w_is_kn && (a.N % 64 != 0 || a.force_simple)) return VZ_ERR_UNSUPPORTED;
   if (a.row_mode != VZ_ROWS_PLAIN && a.rows_per <= 0) return VZ_ERR_BAD_ARG;
   const int batch = a.batch > 1 ? a.batch : 1;
   if (batch > 1 && ((a.a_bstride & 7) || (a.w_bstride & 7) || (a.o_bstride & 7) || (a.r_bstride & 7) ||

@@ -40,7 +40,7 @@ int gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, co
   g.batch = 1; g.out_f32 = 0;
   g.a_bstride = g.w_bstride = g.o_bstride = g.r_bstride = g.bias_bstride = 0;
   g.ln_stats = nullptr; g.ln_colsum = nullptr; g.ln_np = 0; g.ln_eps = 0.f; g.stats_out = nullptr; g.stats_np = 0;
-  g.sk_ws = st.sk_ws; g.sk_ws_bytes = st.sk_bytes;
+  g.sk_ws = st.sk_ws; g.sk_ws_bytes = st.sk_bytes; g.w_is_kn = 0;
   return gemm_launch(g, st);
 }
 
@@ -56,7 +56,7 @@ int gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
   g.a_bstride = g.w_bstride = g.o_bstride = g.r_bstride = g.bias_bstride = 0;
   g.ln_stats = ln_stats; g.ln_colsum = ln_colsum; g.ln_np = ln_np; g.ln_eps = 1e-5f;
   g.stats_out = simple ? nullptr : stats_out; g.stats_np = stats_np;
-  g.sk_ws = st.sk_ws; g.sk_ws_bytes = st.sk_bytes;
+  g.sk_ws = st.sk_ws; g.sk_ws_bytes = st.sk_bytes; g.w_is_kn = 0;
   VZ_TRY(gemm_launch(g, st));
   // the debug GEMM has no statistics epilogue: a row kernel produces the single partial instead
   if (simple && stats_out) VZ_TRY(row_stats_launch(out, ldo, M, N, stats_out, st));
@@ -66,7 +66,7 @@ int gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
 // batched tcgen05 GEMM (strides in elements); fp32 output when out_f32
 int gemm_batched(const void* A, int lda, long long sa, const void* W, int ldw, long long sw, int batch, int M,
                  int N, int K, const float* bias, long long sbias, void* out, int ldo, long long so, int out_f32,
-                 const Ctx& st) {
+                 const Ctx& st, int w_is_kn = 0) {
   vz_gemm_args g;
   g.A = A; g.W = W; g.out = out; g.bias = bias; g.residual = nullptr;
   g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldo = ldo; g.ldr = 0;
@@ -74,7 +74,7 @@ int gemm_batched(const void* A, int lda, long long sa, const void* W, int ldw, l
   g.batch = batch; g.out_f32 = out_f32;
   g.a_bstride = sa; g.w_bstride = sw; g.o_bstride = so; g.r_bstride = 0; g.bias_bstride = sbias;
   g.ln_stats = nullptr; g.ln_colsum = nullptr; g.ln_np = 0; g.ln_eps = 0.f; g.stats_out = nullptr; g.stats_np = 0;
-  g.sk_ws = st.sk_ws; g.sk_ws_bytes = st.sk_bytes;
+  g.sk_ws = st.sk_ws; g.sk_ws_bytes = st.sk_bytes; g.w_is_kn = w_is_kn;
   return gemm_launch(g, st);
 }
 
@@ -108,7 +108,7 @@ VitWs vit_layout(void* base, int T) {
 }
 
 struct QfWs {
-  void *featsN, *fT, *qk, *S, *Pm, *PF, *x, *xn, *qkv, *attn, *q, *hbuf, *q0n, *qkv0, *tn, *kv_text, *attn0, *x1;
+  void *featsN, *qk, *S, *Pm, *PF, *x, *xn, *qkv, *attn, *q, *hbuf, *q0n, *qkv0, *tn, *kv_text, *attn0, *x1;
   void* sk;                // stream-K scratch of the GEMMs
   size_t sk_bytes;
   size_t total;
@@ -121,7 +121,6 @@ QfWs qf_layout(void* base, int T, int n_samples, int text_rows) {
   QfWs w;
   w.featsN = b.take(P * VZ_FUSED_WIDTH * kB16);
   const size_t HQ = (size_t)VZ_QF_HEADS * VZ_QF_QUERIES;  // 256 (query, head) rows per tile
-  w.fT = b.take(P * VZ_FUSED_WIDTH * kB16);                          // [T][5120][576]
   w.qk = b.take((size_t)T * HQ * VZ_FUSED_WIDTH * kB16);              // [T][32][8][5120]
   w.S = b.take((size_t)T * HQ * VZ_VIT_PATCHES * 4);                  // [T][256][576] f32
   w.Pm = b.take((size_t)T * HQ * VZ_VIT_PATCHES * kB16);              // [T][256][576]
@@ -244,8 +243,7 @@ extern "C" int vz_qformer_forward(const vz_qf_weights* w, const void* feats, int
   // Cross-attention without materialising K and V (exact reassociation):
   //   scores_h = (q_h Wk_h) f^T            (the k bias adds a per-query constant: softmax-invariant)
   //   out_h    = (P_h f) Wv_h^T + bv_h     (rows of P sum to 1)
-  // f^T is shared by all 8 blocks: one transpose per forward.
-  VZ_TRY(transpose_launch(fn, ws.fT, T, NP, FW, st));
+  // (P_h f consumes f as a [K, N] operand, so no transposed copy of the features is ever made.)
 
   // ---- block 0 self-attention: queries are tile-invariant, text K/V are per sample --------------
   const vz_qf_block& B0 = w->blocks[0];
@@ -297,9 +295,9 @@ extern "C" int vz_qformer_forward(const vz_qf_weights* w, const void* feats, int
                         ws.S, NP, (long long)HQ * NP, 1, st));
     VZ_TRY(softmax_rows_launch(reinterpret_cast<const float*>(ws.S), ws.Pm, T * HQ, NP,
                                0.044194173824159216f /* 1/sqrt(512) */, st));
-    // PF[t] = P[t] (256 x 576) . f[t] (576 x 5120)                     batch = tiles, W = f^T
-    VZ_TRY(gemm_batched(ws.Pm, NP, (long long)HQ * NP, ws.fT, NP, (long long)FW * NP, T, HQ, FW, NP, nullptr, 0,
-                        ws.PF, FW, (long long)HQ * FW, 0, st));
+    // PF[t] = P[t] (256 x 576) . f[t] (576 x 5120)                     batch = tiles, W = f as [K, N]
+    VZ_TRY(gemm_batched(ws.Pm, NP, (long long)HQ * NP, fn, FW, (long long)NP * FW, T, HQ, FW, NP, nullptr, 0,
+                        ws.PF, FW, (long long)HQ * FW, 0, st, /*w_is_kn=*/1));
     // attn[(t,q), h*512:(h+1)*512] = PF[(t,q),h,:] . Wv_h^T + bv_h     batch = heads
     VZ_TRY(gemm_batched(ws.PF, VZ_QF_HEADS * FW, FW, Bk.ca_v_w, FW, (long long)HD * FW, VZ_QF_HEADS, M, HD, FW,
                         Bk.ca_in_b + 2 * D, HD, ws.attn, D, HD, 0, st));

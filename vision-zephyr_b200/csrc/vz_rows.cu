@@ -200,23 +200,6 @@ patchify_kernel(const void* __restrict__ pix, __nv_bfloat16* __restrict__ patche
   for (int i = threadIdx.x; i < 24 * VZ_PATCH_K * 2 / 16; i += blockDim.x) dst[i] = s4[i];
 }
 
-// in [batch][R][C] bf16 -> out [batch][C][R]; 64x64 tiles through padded shared memory.
-__global__ void __launch_bounds__(256)
-transpose_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int C) {
-  __shared__ __nv_bfloat16 tile[64][66];
-  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
-  const size_t boff = (size_t)blockIdx.z * R * C;
-  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
-    const int r = i >> 6, c = i & 63;
-    tile[r][c] = (r0 + r < R && c0 + c < C) ? in[boff + (size_t)(r0 + r) * C + c0 + c] : __float2bfloat16_rn(0.f);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
-    const int c = i >> 6, r = i & 63;
-    if (r0 + r < R && c0 + c < C) out[boff + (size_t)(c0 + c) * R + r0 + r] = tile[r][c];
-  }
-}
-
 // row softmax of fp32 scores (pre-scaled by `scale`) -> bf16 probabilities; one warp per row.
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int rows, int n, float scale_log2e) {
@@ -273,14 +256,6 @@ row_stats_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int M, int D, flo
 int row_stats_launch(const void* x, int ldx, int M, int D, float* stats, cudaStream_t st) {
   if (D % 8) return VZ_ERR_UNSUPPORTED;
   row_stats_kernel<<<(M + 7) / 8, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, M, D, stats);
-  VZ_LAUNCH_CHECK();
-  return VZ_OK;
-}
-
-int transpose_launch(const void* in, void* out, int batch, int R, int C, cudaStream_t st) {
-  dim3 grid((C + 63) / 64, (R + 63) / 64, batch);
-  transpose_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in),
-                                         reinterpret_cast<__nv_bfloat16*>(out), R, C);
   VZ_LAUNCH_CHECK();
   return VZ_OK;
 }
