@@ -414,6 +414,11 @@ __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem, bool p
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz)
                : "memory");
 }
+// 16-byte async copy of which only the first src_bytes (0..16) are read; the rest is zero-filled
+__device__ __forceinline__ void cp_async_16_partial(void* smem, const void* gmem, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes)
+               : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

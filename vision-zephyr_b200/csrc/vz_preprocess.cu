@@ -9,11 +9,15 @@
 //   CLIPImageProcessor.preprocess  multi_scale_process.py:178-181 (768-entry LUT from the oracle)
 //
 // One CTA = one 14-row band (one patch row) of one 336x336 output tile.  Source rows are streamed
-// through a double-buffered shared-memory row buffer (blended on the way in); every thread owns 4
-// of the band's 1008 byte-columns, runs the horizontal pass for them and folds the result straight
-// into 14 fixed-point vertical accumulators held in registers, so neither the blended image nor the
-// u8 intermediate ever touches HBM.  The band is then normalised through the LUT, transposed into
-// im2col order in shared memory and written with 128-bit stores.
+// through a double-buffered shared-memory row buffer (blended on the way in); every thread owns one
+// output PIXEL (3 channels) of the band's 336, runs the horizontal pass for it and folds the result
+// straight into 14 x 3 fixed-point vertical accumulators held in registers, so neither the blended
+// image nor the u8 intermediate ever touches HBM.  The band is then normalised through the LUT,
+// transposed into im2col order in shared memory and written with 128-bit stores.
+// The tap loops are bound by instruction issue, not by bytes (11-19 taps per axis): the horizontal
+// pass walks 4 taps = 12 interleaved RGB bytes at a time -- three aligned 32-bit shared-memory loads
+// re-aligned with funnel shifts, one 128-bit load for the four coefficients -- and the vertical pass
+// is an unconditional 14 x 3 multiply-add against a zero-padded per-source-row coefficient table.
 #include "vz_common.cuh"
 
 namespace vz {
@@ -21,9 +25,9 @@ namespace {
 
 constexpr int TILE = 336;
 constexpr int BAND = 14;
-constexpr int NCOL = TILE * 3;  // 1008 byte-columns per band row
-constexpr int PP_THREADS = 256;
-constexpr int COLS_PER_THREAD = 4;  // 4*256 >= 1008
+constexpr int PP_THREADS = 352;     // 11 warps: thread x < 336 owns output pixel x of the band
+constexpr int VT_STRIDE = 16;       // ints per row of the vertical coefficient table (14 used)
+constexpr int NBUF = 4;             // source-row ring: rows sy+1 .. sy+3 are in flight (cp.async) while row sy is filtered
 constexpr int PREC = 22;
 constexpr int MAX_PRIMS = 32;  // visual-prompt instances per image (the reference draws 1-4)
 
@@ -38,6 +42,10 @@ struct PreArgs {
   int row_buf_bytes;  // per row buffer (>= 3*max W, multiple of 16)
   int max_ksize;
 };
+
+// byte i of a 32-bit word, zero extended (one PRMT)
+template <int I>
+__device__ __forceinline__ int byte_of(uint32_t w) { return (int)__byte_perm(w, 0u, 0x4440u | I); }
 
 __device__ __forceinline__ int clip8(int v) {
   v >>= PREC;
@@ -65,7 +73,7 @@ __device__ __forceinline__ bool rect_covers(const vz_prim& p, int x, int y) {
   return hl || vl;
 }
 
-__global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PreArgs a) {
+__global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PreArgs a) {
   extern __shared__ __align__(16) uint8_t pp_smem[];
   const int band = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
   const vz_tile_desc td = a.tiles[t];
@@ -82,19 +90,21 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PreArgs a)
   const int32_t* v_kk = v_cnt + td.out_h;
 
   const int stage_bytes = (a.out_mode == VZ_OUT_CHW_F32) ? 3 * BAND * TILE * 4 : 24 * VZ_PATCH_K * 2;
+  const int ksh4 = (ksh + 3) >> 2;              // horizontal taps in groups of four
+  const int vt_rows = 4 * a.max_ksize + 16;     // capacity of the vertical table (source rows of one band)
   uint8_t* s_stage = pp_smem;
   uint8_t* s_row = pp_smem + stage_bytes;
-  int32_t* s_vkk = reinterpret_cast<int32_t*>(s_row + 2 * a.row_buf_bytes);  // [BAND][ksv]
-  int32_t* s_vmin = s_vkk + BAND * a.max_ksize;
+  int32_t* s_vtab = reinterpret_cast<int32_t*>(s_row + NBUF * a.row_buf_bytes);   // [vt_rows][16]: coefficient of source row i for band row y
+  int32_t* s_vmin = s_vtab + vt_rows * VT_STRIDE;
   int32_t* s_vcnt = s_vmin + BAND;
-  int32_t* s_hkk = s_vcnt + BAND + 4;  // [ksh][336]: tap k of output column x (zero outside the taps)
+  int4* s_hkk4 = reinterpret_cast<int4*>(s_vcnt + BAND + 4);  // [ksh4][336]: taps 4g..4g+3 of output column x (zero padded)
 
   // ---- instance list of this image (visual prompts) -> shared memory ---------------------------
   __shared__ vz_prim s_prims[MAX_PRIMS];
   const int n_prims = im.prim_count < MAX_PRIMS ? im.prim_count : MAX_PRIMS;
   for (int i = tid; i < n_prims; i += PP_THREADS) s_prims[i] = a.prims[im.prim_begin + i];
 
-  // ---- vertical taps of the band's 14 output rows ------------------------------------------
+  // ---- vertical windows of the band's 14 output rows ------------------------------------------
   const int ry0 = td.tile_y + band * BAND - td.off_y;  // resized-image row of band row 0
   if (tid < BAND) {
     const int ry = ry0 + tid;
@@ -102,29 +112,26 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PreArgs a)
     s_vmin[tid] = ok ? v_min[ry] : 0;
     s_vcnt[tid] = ok ? v_cnt[ry] : 0;
   }
-  for (int i = tid; i < BAND * ksv; i += PP_THREADS) {
-    const int y = i / ksv, k = i - y * ksv;
-    const int ry = ry0 + y;
-    s_vkk[y * a.max_ksize + k] = (ry >= 0 && ry < td.out_h) ? v_kk[ry * ksv + k] : 0;
-  }
-  // ---- horizontal coefficients of the tile's 336 columns, tap-major (conflict-free reads) ---------
-  for (int i = tid; i < ksh * TILE; i += PP_THREADS) {
-    const int k = i / TILE, x = i - k * TILE;
+  // ---- horizontal coefficients of the tile's 336 columns, four taps per 128-bit entry ----------
+  for (int i = tid; i < ksh4 * TILE; i += PP_THREADS) {
+    const int g = i / TILE, x = i - g * TILE;
     const int rx = td.tile_x + x - td.off_x;
-    s_hkk[i] = (rx >= 0 && rx < td.out_w) ? h_kk[rx * ksh + k] : 0;
-  }
-  // ---- this thread's columns ------------------------------------------------------------------
-  int hx_min[COLS_PER_THREAD], hx_cnt[COLS_PER_THREAD], hx_c[COLS_PER_THREAD], hx_x[COLS_PER_THREAD];
+    int c[4] = {0, 0, 0, 0};
+    if (rx >= 0 && rx < td.out_w) {
 #pragma unroll
-  for (int i = 0; i < COLS_PER_THREAD; ++i) {
-    const int j = tid + i * PP_THREADS;
-    const int x = (j < NCOL) ? j / 3 : 0;
-    hx_x[i] = x;
-    hx_c[i] = (j < NCOL) ? j - x * 3 : 0;
+      for (int k = 0; k < 4; ++k)
+        if (4 * g + k < ksh) c[k] = h_kk[rx * ksh + 4 * g + k];
+    }
+    s_hkk4[i] = make_int4(c[0], c[1], c[2], c[3]);
+  }
+  // ---- this thread's output pixel -----------------------------------------------------------------
+  const int x = tid < TILE ? tid : 0;
+  int hx_min, hx_cnt;
+  {
     const int rx = td.tile_x + x - td.off_x;
-    const bool ok = (j < NCOL) && rx >= 0 && rx < td.out_w;
-    hx_min[i] = ok ? h_min[rx] : -1;
-    hx_cnt[i] = ok ? h_cnt[rx] : 0;
+    const bool ok = tid < TILE && rx >= 0 && rx < td.out_w;
+    hx_min = ok ? h_min[rx] : -1;
+    hx_cnt = ok ? h_cnt[rx] : 0;
   }
   // source column window needed by this tile (uniform per CTA)
   int sx0, sx1;
@@ -135,9 +142,7 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PreArgs a)
     if (rxa <= rxb) { sx0 = h_min[rxa]; sx1 = h_min[rxb] + h_cnt[rxb]; }
     else { sx0 = 0; sx1 = 0; }
   }
-#pragma unroll
-  for (int i = 0; i < COLS_PER_THREAD; ++i)
-    if (hx_min[i] < 0) hx_min[i] = sx0;  // invalid column: all-zero taps, any in-buffer address will do
+  if (hx_min < 0) hx_min = sx0;  // invalid column: all-zero taps, any in-buffer address will do
   __syncthreads();
   // source row window of the band
   int sy0 = 0, sy1 = 0;
@@ -148,12 +153,23 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PreArgs a)
     if (ya <= yb) { sy0 = s_vmin[ya]; sy1 = s_vmin[yb] + s_vcnt[yb]; }
   }
   if (sx1 <= sx0) sy1 = sy0;  // tile lies completely in the padding
+  if (sy1 - sy0 > vt_rows) __trap();   // cannot happen: a band spans < 3.4 * ksize source rows (see vz_preprocess)
+  // ---- vertical coefficient table: entry [i][y] = tap of source row sy0 + i in band row y, else 0 ----
+  for (int i = tid; i < (sy1 - sy0) * VT_STRIDE; i += PP_THREADS) {
+    const int r = i / VT_STRIDE, y = i - r * VT_STRIDE;
+    int coef = 0;
+    if (y < BAND) {
+      const int k = sy0 + r - s_vmin[y];
+      if (k >= 0 && k < s_vcnt[y]) coef = v_kk[(ry0 + y) * ksv + k];
+    }
+    s_vtab[i] = coef;
+  }
 
-  int acc[BAND][COLS_PER_THREAD];
+  int acc[BAND][3];
 #pragma unroll
   for (int y = 0; y < BAND; ++y)
 #pragma unroll
-    for (int i = 0; i < COLS_PER_THREAD; ++i) acc[y][i] = 1 << (PREC - 1);
+    for (int c = 0; c < 3; ++c) acc[y][c] = 1 << (PREC - 1);
 
   const int nbytes = (sx1 - sx0) * 3;
   const uint8_t* img_end = im.src + (size_t)im.W * im.H * 3;
@@ -162,35 +178,37 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PreArgs a)
   auto row_phase = [&](int sy) -> int {
     return (int)(reinterpret_cast<uintptr_t>(im.src + ((size_t)sy * im.W + sx0) * 3) & 15);
   };
-  auto load_row = [&](int sy, uint8_t* dst) {
-    const uint8_t* srow = im.src + ((size_t)sy * im.W + sx0) * 3;
-    const int ph = (int)(reinterpret_cast<uintptr_t>(srow) & 15);
-    if (im.prim_count == 0) {
+  // asynchronous copy of the raw bytes of source row sy into a ring slot (one commit group per row)
+  auto issue_row = [&](int sy, uint8_t* dst) {
+    if (sy < sy1) {
+      const uint8_t* srow = im.src + ((size_t)sy * im.W + sx0) * 3;
+      const int ph = (int)(reinterpret_cast<uintptr_t>(srow) & 15);
       const uint8_t* g0 = srow - ph;
       const int nvec = (nbytes + ph + 15) >> 4;
       for (int i = tid; i < nvec; i += PP_THREADS) {
         const uint8_t* g = g0 + 16 * i;
-        if (g + 16 <= img_end) {
-          *reinterpret_cast<uint4*>(dst + 16 * i) = __ldg(reinterpret_cast<const uint4*>(g));
-        } else {
-          for (int b = 0; b < 16; ++b) dst[16 * i + b] = (g + b < img_end) ? g[b] : (uint8_t)0;
-        }
+        const long left = img_end - g;     // bytes of the image from g on
+        cp_async_16_partial(dst + 16 * i, g, left >= 16 ? 16 : (left > 0 ? (int)left : 0));
       }
-      return;
     }
-    // blend path: one thread per PIXEL; the instance list sits in shared memory and every RGBA
-    // overlay pixel is one aligned 32-bit load
+    cp_async_commit();
+  };
+  // visual prompts: blend the instances over the row in place (one thread per pixel; the instance list
+  // sits in shared memory and every RGBA overlay pixel is one aligned 32-bit load)
+  auto blend_row = [&](int sy, uint8_t* dst) {
+    const int ph = row_phase(sy);
     const int npx = sx1 - sx0;
     for (int px = tid; px < npx; px += PP_THREADS) {
-      const int x = sx0 + px;
-      int r = srow[px * 3], g = srow[px * 3 + 1], b = srow[px * 3 + 2];
+      const int xs = sx0 + px;
+      uint8_t* q = dst + ph + px * 3;
+      int r = q[0], g = q[1], b = q[2];
       for (int pi = 0; pi < n_prims; ++pi) {
         const vz_prim& p = s_prims[pi];
         uint32_t ov;
         if (p.type == VZ_PRIM_LAYER) {
-          ov = __ldg(reinterpret_cast<const uint32_t*>(im.layers) + ((size_t)p.layer * im.H + sy) * im.W + x);
+          ov = __ldg(reinterpret_cast<const uint32_t*>(im.layers) + ((size_t)p.layer * im.H + sy) * im.W + xs);
         } else {
-          if (!rect_covers(p, x, sy)) continue;
+          if (!rect_covers(p, xs, sy)) continue;
           ov = p.rgba;
         }
         const int al = (int)(ov >> 24);
@@ -198,67 +216,69 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PreArgs a)
         g = blend_over(g, (int)((ov >> 8) & 0xff), al);
         b = blend_over(b, (int)((ov >> 16) & 0xff), al);
       }
-      dst[ph + px * 3] = (uint8_t)r;
-      dst[ph + px * 3 + 1] = (uint8_t)g;
-      dst[ph + px * 3 + 2] = (uint8_t)b;
+      q[0] = (uint8_t)r; q[1] = (uint8_t)g; q[2] = (uint8_t)b;
     }
   };
 
-  if (sy1 > sy0) load_row(sy0, s_row);
-  __syncthreads();
+  for (int i = 0; i < NBUF - 1; ++i) issue_row(sy0 + i, s_row + i * a.row_buf_bytes);
+  const int4* hk = s_hkk4 + x;
   for (int sy = sy0; sy < sy1; ++sy) {
-    const uint8_t* cur = s_row + ((sy - sy0) & 1) * a.row_buf_bytes;
-    if (sy + 1 < sy1) load_row(sy + 1, s_row + ((sy + 1 - sy0) & 1) * a.row_buf_bytes);
-    // horizontal pass: uniform tap loop (taps beyond a column's count have zero coefficients), four
-    // independent accumulators per thread
-    int hv[COLS_PER_THREAD];
+    uint8_t* cur = s_row + ((sy - sy0) % NBUF) * a.row_buf_bytes;
+    cp_async_wait<NBUF - 2>();   // row sy has landed (for this thread's copies) ...
+    __syncthreads();             // ... and for everyone's; row sy - 1 is no longer read by anybody
+    issue_row(sy + NBUF - 1, s_row + ((sy + NBUF - 1 - sy0) % NBUF) * a.row_buf_bytes);
+    if (im.prim_count != 0) {
+      blend_row(sy, cur);
+      __syncthreads();
+    }
+    // horizontal pass for this thread's pixel: taps beyond the column's count have zero coefficients
+    int hv0, hv1, hv2;
     {
-      const uint8_t* base = cur + row_phase(sy);
-      const uint8_t* sp0 = base + (hx_min[0] - sx0) * 3 + hx_c[0];
-      const uint8_t* sp1 = base + (hx_min[1] - sx0) * 3 + hx_c[1];
-      const uint8_t* sp2 = base + (hx_min[2] - sx0) * 3 + hx_c[2];
-      const uint8_t* sp3 = base + (hx_min[3] - sx0) * 3 + hx_c[3];
-      const int32_t* c0 = s_hkk + hx_x[0];
-      const int32_t* c1 = s_hkk + hx_x[1];
-      const int32_t* c2 = s_hkk + hx_x[2];
-      const int32_t* c3 = s_hkk + hx_x[3];
-      int s0 = 1 << (PREC - 1), s1 = s0, s2 = s0, s3 = s0;
-#pragma unroll 4
-      for (int k = 0; k < ksh; ++k) {
-        s0 += (int)sp0[k * 3] * c0[k * TILE];
-        s1 += (int)sp1[k * 3] * c1[k * TILE];
-        s2 += (int)sp2[k * 3] * c2[k * TILE];
-        s3 += (int)sp3[k * 3] * c3[k * TILE];
+      const int b0 = row_phase(sy) + (hx_min - sx0) * 3;          // first byte of tap 0 in the row buffer
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(cur) + (b0 >> 2);
+      const uint32_t sh = (uint32_t)(b0 & 3) * 8u;
+      int s0 = 1 << (PREC - 1), s1 = s0, s2 = s0;
+      uint32_t w0 = wp[0];
+      for (int g = 0; g < ksh4; ++g) {
+        const uint32_t w1 = wp[3 * g + 1], w2 = wp[3 * g + 2], w3 = wp[3 * g + 3];
+        const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh),
+                       a2 = __funnelshift_r(w2, w3, sh);     // 12 bytes = 4 RGB pixels, byte-aligned to tap 4g
+        const int4 c = hk[g * TILE];
+        s0 += byte_of<0>(a0) * c.x + byte_of<3>(a0) * c.y + byte_of<2>(a1) * c.z + byte_of<1>(a2) * c.w;
+        s1 += byte_of<1>(a0) * c.x + byte_of<0>(a1) * c.y + byte_of<3>(a1) * c.z + byte_of<2>(a2) * c.w;
+        s2 += byte_of<2>(a0) * c.x + byte_of<1>(a1) * c.y + byte_of<0>(a2) * c.z + byte_of<3>(a2) * c.w;
+        w0 = w3;
       }
-      hv[0] = clip8(s0); hv[1] = clip8(s1); hv[2] = clip8(s2); hv[3] = clip8(s3);
+      hv0 = clip8(s0); hv1 = clip8(s1); hv2 = clip8(s2);
     }
+    // vertical pass: every band row takes this source row with its (possibly zero) coefficient
+    {
+      const int4* vt = reinterpret_cast<const int4*>(s_vtab + (sy - sy0) * VT_STRIDE);
+      const int4 v0 = vt[0], v1 = vt[1], v2 = vt[2], v3 = vt[3];
+      const int vk[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
 #pragma unroll
-    for (int y = 0; y < BAND; ++y) {
-      const int k = sy - s_vmin[y];
-      if (k >= 0 && k < s_vcnt[y]) {
-        const int coef = s_vkk[y * a.max_ksize + k];
-#pragma unroll
-        for (int i = 0; i < COLS_PER_THREAD; ++i) acc[y][i] += hv[i] * coef;
+      for (int y = 0; y < BAND; ++y) {
+        acc[y][0] += hv0 * vk[y];
+        acc[y][1] += hv1 * vk[y];
+        acc[y][2] += hv2 * vk[y];
       }
     }
-    __syncthreads();
   }
+  cp_async_wait<0>();
 
   // ---- normalise + transpose into the output layout -------------------------------------------
   if (a.out_mode == VZ_OUT_PATCHES_BF16) {
     __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(s_stage);
     for (int i = tid; i < 24 * 4; i += PP_THREADS) sp[(i >> 2) * VZ_PATCH_K + 588 + (i & 3)] = __float2bfloat16_rn(0.f);
-#pragma unroll
-    for (int i = 0; i < COLS_PER_THREAD; ++i) {
-      const int j = tid + i * PP_THREADS;
-      if (j >= NCOL) continue;
-      const int x = j / 3, c = hx_c[i];
+    if (tid < TILE) {
       const int px = x / 14, kx = x - px * 14;
 #pragma unroll
-      for (int y = 0; y < BAND; ++y) {
-        const int v = (hx_cnt[i] > 0 && s_vcnt[y] > 0) ? clip8(acc[y][i]) : 0;
-        sp[px * VZ_PATCH_K + c * 196 + y * 14 + kx] = __float2bfloat16_rn(a.lut[c * 256 + v]);
-      }
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int y = 0; y < BAND; ++y) {
+          const int v = (hx_cnt > 0 && s_vcnt[y] > 0) ? clip8(acc[y][c]) : 0;
+          sp[px * VZ_PATCH_K + c * 196 + y * 14 + kx] = __float2bfloat16_rn(a.lut[c * 256 + v]);
+        }
     }
     __syncthreads();
     uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) +
@@ -267,24 +287,22 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PreArgs a)
     for (int i = tid; i < 24 * VZ_PATCH_K * 2 / 16; i += PP_THREADS) dst[i] = s4[i];
   } else {
     float* sf = reinterpret_cast<float*>(s_stage);  // [3][BAND][336]
+    if (tid < TILE) {
 #pragma unroll
-    for (int i = 0; i < COLS_PER_THREAD; ++i) {
-      const int j = tid + i * PP_THREADS;
-      if (j >= NCOL) continue;
-      const int x = j / 3, c = hx_c[i];
+      for (int c = 0; c < 3; ++c)
 #pragma unroll
-      for (int y = 0; y < BAND; ++y) {
-        const int v = (hx_cnt[i] > 0 && s_vcnt[y] > 0) ? clip8(acc[y][i]) : 0;
-        sf[(c * BAND + y) * TILE + x] = a.lut[c * 256 + v];
-      }
+        for (int y = 0; y < BAND; ++y) {
+          const int v = (hx_cnt > 0 && s_vcnt[y] > 0) ? clip8(acc[y][c]) : 0;
+          sf[(c * BAND + y) * TILE + x] = a.lut[c * 256 + v];
+        }
     }
     __syncthreads();
     float* o = reinterpret_cast<float*>(a.out);
     for (int i = tid; i < 3 * BAND * TILE / 4; i += PP_THREADS) {
       const int e = i * 4;
       const int c = e / (BAND * TILE), rem = e - c * BAND * TILE;
-      const int y = rem / TILE, x = rem - y * TILE;
-      *reinterpret_cast<float4*>(o + (((size_t)t * 3 + c) * TILE + band * BAND + y) * TILE + x) =
+      const int y = rem / TILE, xx = rem - y * TILE;
+      *reinterpret_cast<float4*>(o + (((size_t)t * 3 + c) * TILE + band * BAND + y) * TILE + xx) =
           *reinterpret_cast<const float4*>(sf + e);
     }
   }
@@ -308,8 +326,10 @@ extern "C" int vz_preprocess(const vz_image_desc* images, int n_images, const vz
   a.row_buf_bytes = ((max_src_w * 3 + 3 * max_ksize + 32 + 15) / 16) * 16;  // + phase + tap overrun slack
   a.max_ksize = max_ksize;
   const int stage_bytes = (out_mode == VZ_OUT_CHW_F32) ? 3 * BAND * TILE * 4 : 24 * VZ_PATCH_K * 2;
-  const size_t smem = (size_t)stage_bytes + 2 * (size_t)a.row_buf_bytes + (size_t)BAND * max_ksize * 4 + 2 * BAND * 4 +
-                      16 + (size_t)max_ksize * TILE * 4;
+  // a band of 14 output rows spans at most 14 * scale + ksize <= 3.4 * ksize source rows (ksize = 2 ceil(3 scale) + 1)
+  const size_t vt_rows = 4 * (size_t)max_ksize + 16;
+  const size_t smem = (size_t)stage_bytes + NBUF * (size_t)a.row_buf_bytes + vt_rows * VT_STRIDE * 4 + 2 * BAND * 4 + 16 +
+                      (size_t)((max_ksize + 3) / 4) * TILE * 16;
   if (smem > 220 * 1024) return VZ_ERR_UNSUPPORTED;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static bool attr_done = false;
