@@ -236,20 +236,29 @@ int vz_vit_forward(const vz_vit_weights* w, const void* patches, int T, void* fu
 #define VZ_QF_HEAD_DIM 512
 #define VZ_QF_FFN 8192
 
+/* norm1 / norm2 / norm3 of every block are FOLDED into the Linear that follows them, like the ViT's
+ * layer norms (see vz_gemm_args): W' = W * gamma, b' = b + W beta, s[n] = sum_k W'[n,k]; the GEMM that
+ * writes the residual stream emits the row statistics.  Exception: block 0's self-attention input is
+ * the tile-invariant learned queries plus the per-sample text rows, a handful of rows that still go
+ * through the LayerNorm kernel (n1_g, n1_b), so block 0 keeps a PLAIN sa_in_w / sa_in_b and a NULL s_sa_in. */
 typedef struct {
-  const float *n1_g, *n1_b, *n2_g, *n2_b, *n3_g, *n3_b;
-  const void* sa_in_w;   /* bf16 [12288,4096] */
-  const float* sa_in_b;  /* f32 [12288] */
+  const float *n1_g, *n1_b; /* norm1 (used by block 0 only) */
+  const void* sa_in_w;   /* bf16 [12288,4096]: plain in block 0, norm1-folded in blocks 1..7 */
+  const float* sa_in_b;  /* f32 [12288] (beta-folded in blocks 1..7) */
+  const float* s_sa_in;  /* f32 [12288] column sums of the folded weight; NULL in block 0 */
   const void* sa_out_w;  /* bf16 [4096,4096] */
   const float* sa_out_b;
-  const void* ca_q_w;    /* bf16 [4096,4096] */
+  const void* ca_q_w;    /* bf16 [4096,4096] = q_proj_weight, norm2-folded */
+  const float* ca_q_b;   /* f32 [4096] = in_proj_bias[0:4096] + Wq norm2.bias */
+  const float* s_ca_q;   /* f32 [4096] column sums */
   const void* ca_kT_w;   /* bf16 [5120,4096] = k_proj_weight TRANSPOSED (row n, column h*512+d)   */
   const void* ca_v_w;    /* bf16 [4096,5120] = v_proj_weight                                        */
-  const float* ca_in_b;  /* f32 [12288] (q,k,v biases; the k bias cancels in the softmax)          */
+  const float* ca_in_b;  /* f32 [12288] (q,k,v biases; only the v part is read: the k bias cancels in the softmax) */
   const void* ca_out_w;  /* bf16 [4096,4096] */
   const float* ca_out_b;
-  const void* ffn1_w;    /* bf16 [8192,4096] */
-  const float* ffn1_b;
+  const void* ffn1_w;    /* bf16 [8192,4096], norm3-folded */
+  const float* ffn1_b;   /* f32 [8192] (beta-folded) */
+  const float* s_ffn1;   /* f32 [8192] column sums */
   const void* ffn2_w;    /* bf16 [4096,8192] */
   const float* ffn2_b;
 } vz_qf_block;

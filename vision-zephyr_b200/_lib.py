@@ -64,8 +64,9 @@ class VitWeights(C.Structure):
 
 class QfBlock(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
-        "n1_g", "n1_b", "n2_g", "n2_b", "n3_g", "n3_b", "sa_in_w", "sa_in_b", "sa_out_w", "sa_out_b",
-        "ca_q_w", "ca_kT_w", "ca_v_w", "ca_in_b", "ca_out_w", "ca_out_b", "ffn1_w", "ffn1_b", "ffn2_w", "ffn2_b")]
+        "n1_g", "n1_b", "sa_in_w", "sa_in_b", "s_sa_in", "sa_out_w", "sa_out_b",
+        "ca_q_w", "ca_q_b", "s_ca_q", "ca_kT_w", "ca_v_w", "ca_in_b", "ca_out_w", "ca_out_b",
+        "ffn1_w", "ffn1_b", "s_ffn1", "ffn2_w", "ffn2_b")]
 
 
 class QfWeights(C.Structure):

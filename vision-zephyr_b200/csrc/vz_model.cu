@@ -109,6 +109,7 @@ VitWs vit_layout(void* base, int T) {
 
 struct QfWs {
   void *featsN, *qk, *S, *Pm, *PF, *x, *xn, *qkv, *attn, *q, *hbuf, *q0n, *qkv0, *tn, *kv_text, *attn0, *x1;
+  float* stats;            // [M][<=64][2] partial row statistics of the residual stream (norms folded into GEMMs)
   void* sk;                // stream-K scratch of the GEMMs
   size_t sk_bytes;
   size_t total;
@@ -137,6 +138,7 @@ QfWs qf_layout(void* base, int T, int n_samples, int text_rows) {
   w.kv_text = b.take(R1 * 2 * VZ_QF_WIDTH * kB16);
   w.attn0 = b.take(Bs * VZ_QF_WIDTH * kB16);
   w.x1 = b.take(Bs * VZ_QF_WIDTH * kB16);
+  w.stats = reinterpret_cast<float*>(b.take(M * 64 * 2 * sizeof(float)));
   w.sk_bytes = gemm_sk_workspace_bytes();
   w.sk = b.take(w.sk_bytes);
   w.total = b.off + 256;
@@ -272,21 +274,28 @@ extern "C" int vz_qformer_forward(const vz_qf_weights* w, const void* feats, int
     VZ_TRY(gather_rows_launch(ws.x1, ws.x, M, D * (int)kB16, nullptr, VZ_QF_QUERIES, st));
   }
 
+  // norm1/2/3 never run as kernels from here on: every GEMM that writes the residual stream x also
+  // writes per-row partial (sum, sum of squares); the Linear that follows the norm has gamma / beta
+  // folded into its weights and finishes the normalisation in its epilogue.  x of block 0 comes out
+  // of a row gather, so its statistics come from a row kernel (one partial).
+  const int np_gemm = simple ? 1 : gemm_stats_partials(M, D);
+  if (np_gemm > 64) return VZ_ERR_UNSUPPORTED;
+  VZ_TRY(row_stats_launch(ws.x, D, M, D, ws.stats, st));
+  int np = 1;
   for (int i = 0; i < VZ_QF_BLOCKS; ++i) {
     const vz_qf_block& Bk = w->blocks[i];
     if (i > 0) {
-      VZ_TRY(layernorm_launch(ws.x, D, Bk.n1_g, Bk.n1_b, ws.xn, D, M, D, 1e-5f, nullptr, 1, st));
-      VZ_TRY(gemm(ws.xn, D, Bk.sa_in_w, D, M, D3, D, Bk.sa_in_b, VZ_ACT_NONE, nullptr, 0, ws.qkv, D3,
-                  VZ_ROWS_PLAIN, 0, simple, st));
+      VZ_TRY(gemm_ln(ws.x, D, Bk.sa_in_w, D, M, D3, D, Bk.sa_in_b, VZ_ACT_NONE, nullptr, 0, ws.qkv, D3, ws.stats, np,
+                     Bk.s_sa_in, nullptr, 0, simple, st));
       VZ_TRY(qattn_launch(1, qkv, D3, VZ_QF_QUERIES, qkv + D, qkv + 2 * D, D3, VZ_QF_QUERIES, VZ_QF_QUERIES,
                           nullptr, nullptr, D3, nullptr, nullptr, nullptr, 0, ws.attn, D, T, st));
-      VZ_TRY(gemm(ws.attn, D, Bk.sa_out_w, D, M, D, D, Bk.sa_out_b, VZ_ACT_NONE, ws.x, D, ws.x, D,
-                  VZ_ROWS_PLAIN, 0, simple, st));
+      VZ_TRY(gemm_ln(ws.attn, D, Bk.sa_out_w, D, M, D, D, Bk.sa_out_b, VZ_ACT_NONE, ws.x, D, ws.x, D, nullptr, 0,
+                     nullptr, ws.stats, np_gemm, simple, st));
+      np = np_gemm;
     }
-    // cross-attention over the tile's 576 patch rows
-    VZ_TRY(layernorm_launch(ws.x, D, Bk.n2_g, Bk.n2_b, ws.xn, D, M, D, 1e-5f, nullptr, 1, st));
-    VZ_TRY(gemm(ws.xn, D, Bk.ca_q_w, D, M, D, D, Bk.ca_in_b, VZ_ACT_NONE, nullptr, 0, ws.q, D, VZ_ROWS_PLAIN,
-                0, simple, st));
+    // cross-attention over the tile's 576 patch rows (norm2 folded into the query projection)
+    VZ_TRY(gemm_ln(ws.x, D, Bk.ca_q_w, D, M, D, D, Bk.ca_q_b, VZ_ACT_NONE, nullptr, 0, ws.q, D, ws.stats, np,
+                   Bk.s_ca_q, nullptr, 0, simple, st));
     // qk[(t,q),h,:] = q[(t,q), h*512:(h+1)*512] . Wk_h            batch = heads, K = 512
     VZ_TRY(gemm_batched(ws.q, D, HD, Bk.ca_kT_w, D, HD, VZ_QF_HEADS, M, FW, HD, nullptr, 0, ws.qk,
                         VZ_QF_HEADS * FW, FW, 0, st));
@@ -301,14 +310,14 @@ extern "C" int vz_qformer_forward(const vz_qf_weights* w, const void* feats, int
     // attn[(t,q), h*512:(h+1)*512] = PF[(t,q),h,:] . Wv_h^T + bv_h     batch = heads
     VZ_TRY(gemm_batched(ws.PF, VZ_QF_HEADS * FW, FW, Bk.ca_v_w, FW, (long long)HD * FW, VZ_QF_HEADS, M, HD, FW,
                         Bk.ca_in_b + 2 * D, HD, ws.attn, D, HD, 0, st));
-    VZ_TRY(gemm(ws.attn, D, Bk.ca_out_w, D, M, D, D, Bk.ca_out_b, VZ_ACT_NONE, ws.x, D, ws.x, D, VZ_ROWS_PLAIN,
-                0, simple, st));
-    // FFN, exact (erf) GELU
-    VZ_TRY(layernorm_launch(ws.x, D, Bk.n3_g, Bk.n3_b, ws.xn, D, M, D, 1e-5f, nullptr, 1, st));
-    VZ_TRY(gemm(ws.xn, D, Bk.ffn1_w, D, M, VZ_QF_FFN, D, Bk.ffn1_b, VZ_ACT_GELU_ERF, nullptr, 0, ws.hbuf,
-                VZ_QF_FFN, VZ_ROWS_PLAIN, 0, simple, st));
-    VZ_TRY(gemm(ws.hbuf, VZ_QF_FFN, Bk.ffn2_w, VZ_QF_FFN, M, D, VZ_QF_FFN, Bk.ffn2_b, VZ_ACT_NONE, ws.x, D,
-                ws.x, D, VZ_ROWS_PLAIN, 0, simple, st));
+    VZ_TRY(gemm_ln(ws.attn, D, Bk.ca_out_w, D, M, D, D, Bk.ca_out_b, VZ_ACT_NONE, ws.x, D, ws.x, D, nullptr, 0,
+                   nullptr, ws.stats, np_gemm, simple, st));
+    np = np_gemm;
+    // FFN, exact (erf) GELU (norm3 folded into the first Linear)
+    VZ_TRY(gemm_ln(ws.x, D, Bk.ffn1_w, D, M, VZ_QF_FFN, D, Bk.ffn1_b, VZ_ACT_GELU_ERF, nullptr, 0, ws.hbuf,
+                   VZ_QF_FFN, ws.stats, np, Bk.s_ffn1, nullptr, 0, simple, st));
+    VZ_TRY(gemm_ln(ws.hbuf, VZ_QF_FFN, Bk.ffn2_w, VZ_QF_FFN, M, D, VZ_QF_FFN, Bk.ffn2_b, VZ_ACT_NONE, ws.x, D,
+                   ws.x, D, nullptr, 0, nullptr, ws.stats, np_gemm, simple, st));
   }
   VZ_TRY(layernorm_launch(ws.x, D, w->norm_g, w->norm_b, out, ldo, M, D, 1e-5f, nullptr, 1, st));
   return VZ_OK;

@@ -134,22 +134,31 @@ class QFormerB200(nn.Module):
         w = _lib.QfWeights()
         for i, blk in enumerate(self.blocks):
             ca, sa = blk.cross_attn, blk.self_attn
+            # LayerNorm folding (csrc/vz_gemm.cu): LN(x) W^T + b = rstd (x W'^T - mu colsum(W')) + b'
+            def fold(W, b, norm):
+                W32, g32, beta32 = W.detach().float(), norm.weight.detach().float(), norm.bias.detach().float()
+                Wf = (W32 * g32[None, :]).to(torch.bfloat16).contiguous()
+                return Wf, (b.detach().float() + W32 @ beta32).contiguous(), Wf.float().sum(1).contiguous()
+            if i == 0:   # block 0: the (few) query / text rows go through the LayerNorm kernel
+                sa_w, sa_b, sa_s = bf(sa.in_proj_weight), f32(sa.in_proj_bias), None
+            else:
+                sa_w, sa_b, sa_s = fold(sa.in_proj_weight, sa.in_proj_bias, blk.norm1)
+            q_w, q_b, q_s = fold(ca.q_proj_weight, ca.in_proj_bias[:WIDTH], blk.norm2)
+            f1_w, f1_b, f1_s = fold(blk.ffn["0"].weight, blk.ffn["0"].bias, blk.norm3)
             ent = {
                 "n1_g": f32(blk.norm1.weight), "n1_b": f32(blk.norm1.bias),
-                "n2_g": f32(blk.norm2.weight), "n2_b": f32(blk.norm2.bias),
-                "n3_g": f32(blk.norm3.weight), "n3_b": f32(blk.norm3.bias),
-                "sa_in_w": bf(sa.in_proj_weight), "sa_in_b": f32(sa.in_proj_bias),
+                "sa_in_w": sa_w, "sa_in_b": sa_b, "s_sa_in": sa_s,
                 "sa_out_w": bf(sa.out_proj.weight), "sa_out_b": f32(sa.out_proj.bias),
-                "ca_q_w": bf(ca.q_proj_weight), "ca_in_b": f32(ca.in_proj_bias),
+                "ca_q_w": q_w, "ca_q_b": q_b, "s_ca_q": q_s, "ca_in_b": f32(ca.in_proj_bias),
                 # K is never materialised: scores = (q Wk) f^T needs Wk^T with the head dim contiguous
                 "ca_kT_w": bf(ca.k_proj_weight).t().contiguous(), "ca_v_w": bf(ca.v_proj_weight),
                 "ca_out_w": bf(ca.out_proj.weight), "ca_out_b": f32(ca.out_proj.bias),
-                "ffn1_w": bf(blk.ffn["0"].weight), "ffn1_b": f32(blk.ffn["0"].bias),
+                "ffn1_w": f1_w, "ffn1_b": f1_b, "s_ffn1": f1_s,
                 "ffn2_w": bf(blk.ffn["2"].weight), "ffn2_b": f32(blk.ffn["2"].bias),
             }
             for name, t in ent.items():
                 P[f"{i}.{name}"] = t
-                setattr(w.blocks[i], name, t.data_ptr())
+                setattr(w.blocks[i], name, t.data_ptr() if t is not None else None)
         w.learned_queries = P["lq"].data_ptr()
         w.pre_g, w.pre_b = P["pre_g"].data_ptr(), P["pre_b"].data_ptr()
         w.norm_g, w.norm_b = P["norm_g"].data_ptr(), P["norm_b"].data_ptr()
