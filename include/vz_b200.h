@@ -132,6 +132,13 @@ typedef struct {
   const uint8_t* layers; /* RGBA u8 [n_layers, H, W, 4] host-rasterised overlays, or NULL         */
   int W, H;
   int prim_begin, prim_count; /* range into the primitive array, applied in order              */
+  /* The resampling tables of the image's views address a virtual CANVAS in which the image sits at
+   * (pad_x, pad_y): 0,0 = the image itself; > 0 = expand2square padding (mm_utils.py:16-35), canvas
+   * pixels outside the image have the colour bg; < 0 = centre crop (mm_utils.py:65-74).
+   * Visual prompts stay in image coordinates.                                                   */
+  int pad_x, pad_y;
+  uint32_t bg;         /* r | g<<8 | b<<16 */
+  int reserved;
 } vz_image_desc;
 
 enum { VZ_PRIM_LAYER = 0, VZ_PRIM_RECT = 1 };

@@ -60,17 +60,32 @@ def _lanczos(x):
     return _sinc(x) * _sinc(x / 3) if -3.0 <= x < 3.0 else 0.0
 
 
-def coeff_matrix(in_size, out_size):
-    """Dense int64 [out,in] fixed-point LANCZOS matrix of one axis (zeros outside the taps)."""
+def _bicubic(x):
+    """Pillow Resample.c bicubic_filter (a = -0.5)."""
+    a = -0.5
+    x = -x if x < 0.0 else x
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+_FILTERS = {"lanczos": (_lanczos, 3.0), "bicubic": (_bicubic, 2.0)}
+
+
+def coeff_matrix(in_size, out_size, filt="lanczos"):
+    """Dense int64 [out,in] fixed-point matrix of one axis for a Pillow filter (zeros outside the taps)."""
+    fn, fsupport = _FILTERS[filt]
     scale = in_size / out_size
     fs = max(scale, 1.0)
-    support = 3.0 * fs
+    support = fsupport * fs
     K = np.zeros((out_size, in_size), np.int64)
     for xx in range(out_size):
         center = (xx + 0.5) * scale
         xmin = max(int(center - support + 0.5), 0)
         xmax = min(int(center + support + 0.5), in_size)
-        w = [_lanczos((x + xmin - center + 0.5) / fs) for x in range(xmax - xmin)]
+        w = [fn((x + xmin - center + 0.5) / fs) for x in range(xmax - xmin)]
         ww = 0.0
         for v in w:
             ww += v
@@ -87,17 +102,22 @@ def _clip8(acc):
 
 def lanczos_resize(img, size):
     """img u8 [H,W,C] -> u8 [h,w,C] for size=(w,h), like PIL.Image.resize(size, LANCZOS)."""
+    return pil_resize(img, size, "lanczos")
+
+
+def pil_resize(img, size, filt="lanczos"):
+    """img u8 [H,W,C] -> u8 [h,w,C] for size=(w,h), like PIL.Image.resize(size, LANCZOS | BICUBIC)."""
     H, W = img.shape[:2]
     w, h = size
     out = img
     if w != W:  # horizontal pass first
-        Kh = coeff_matrix(W, w)
+        Kh = coeff_matrix(W, w, filt)
         # float64 BLAS is exact here: |sum| < 2**53
         acc = np.einsum("ox,yxc->yoc", Kh.astype(np.float64), out.astype(np.float64), optimize=True).astype(np.int64)
         acc += 1 << (PRECISION_BITS - 1)
         out = _clip8(acc)
     if h != H:
-        Kv = coeff_matrix(H, h)
+        Kv = coeff_matrix(H, h, filt)
         acc = np.einsum("oy,yxc->oxc", Kv.astype(np.float64), out.astype(np.float64), optimize=True).astype(np.int64)
         acc += 1 << (PRECISION_BITS - 1)
         out = _clip8(acc)
@@ -132,6 +152,52 @@ def anyres_tiles_u8(img, pinpoints):
         for j in range(0, bw, TILE):
             tiles.append(canvas[i:i + TILE, j:j + TILE])
     return np.stack(tiles)
+
+
+def expand2square(img, bg):
+    """mm_utils.expand2square (mm_utils.py:16-35) on a u8 [H,W,3] array."""
+    H, W = img.shape[:2]
+    if W == H:
+        return img
+    m = max(W, H)
+    out = np.empty((m, m, 3), np.uint8)
+    out[:] = np.asarray(bg, np.uint8)
+    if W > H:
+        y = (W - H) // 2
+        out[y:y + H] = img
+    else:
+        x = (H - W) // 2
+        out[:, x:x + W] = img
+    return out
+
+
+def clip_processor_u8(img):
+    """The geometric part of CLIPImageProcessor.preprocess with size={'shortest_edge': 336}, crop 336
+    (transformers 4.52.4, the version the reference pins: PIL BICUBIC resize of the short side to 336,
+    long side int(336 * long / short), then centre crop with floor-divided offsets)."""
+    H, W = img.shape[:2]
+    if W <= H:
+        nw, nh = TILE, int(TILE * H / W)
+    else:
+        nw, nh = int(TILE * W / H), TILE
+    r = pil_resize(img, (nw, nh), "bicubic")
+    top, left = (nh - TILE) // 2, (nw - TILE) // 2
+    return r[top:top + TILE, left:left + TILE]
+
+
+def process_images_u8(img, mode, image_mean=(0.48145466, 0.4578275, 0.40821073)):
+    """mm_utils.process_images (mm_utils.py:38-87) / train.py:570-590 up to the u8 336x336 tile:
+    'pad' | 'resize' | 'square' | anything else ('plain')."""
+    if mode == "pad":
+        img = expand2square(img, tuple(int(x * 255) for x in image_mean))
+    elif mode == "resize":
+        img = pil_resize(img, (TILE, TILE), "lanczos")
+    elif mode == "square":
+        H, W = img.shape[:2]
+        m = min(W, H)
+        left, top = int((W - m) / 2), int((H - m) / 2)
+        img = img[top:top + m, left:left + m]
+    return clip_processor_u8(img)
 
 
 def normalize_lut(tiles_u8, lut):

@@ -44,7 +44,7 @@ def test_bad_arguments_are_rejected_without_a_gpu():
 def test_struct_layouts_match_the_header():
     from vision_zephyr_b200 import _lib
     assert ctypes.sizeof(_lib.GemmArgs) == 5 * 8 + 13 * 4 + 4 + 5 * 8 + 2 * 8 + 2 * 4 + 8 + 4 + 4 + 2 * 8 + 8
-    assert ctypes.sizeof(_lib.ImageDesc) == 32
+    assert ctypes.sizeof(_lib.ImageDesc) == 48
     assert ctypes.sizeof(_lib.Prim) == 32
     assert ctypes.sizeof(_lib.TileDesc) == 36
     assert ctypes.sizeof(_lib.SlotDesc) == 48

@@ -114,3 +114,30 @@ def test_blend_then_resize_on_large_image(golden_dir):
     got = vz.process_any_resolution_images([torch.from_numpy(img).cuda()], PINPOINTS_C3, lut,
                                            prompts=[[vz.VisualPrompt("layer", layer=layer)]], out_mode="chw")[0]
     assert np.array_equal(got.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("mode", ["pad", "square", "resize", "plain"])
+def test_process_images_modes_bit_exact(mode, golden_dir):
+    """mm_utils.process_images / the training loader's 'pad' and plain branches (expand2square, centre crop,
+    LANCZOS squash, CLIP processor BICUBIC resize + centre crop): kernel == oracle, with a visual prompt on
+    one image (prompts stay in image coordinates under padding / cropping)"""
+    import vision_zephyr_b200 as vz
+    from oracle import pil_ops as P
+    lut = _lut(golden_dir)
+    sizes = [(700, 500), (420, 901), (336, 336), (1000, 1000), (301, 640)]
+    imgs = [synth_image(20 + i, w, h) for i, (w, h) in enumerate(sizes)]
+    layer = np.zeros((500, 700, 4), np.uint8)
+    layer[50:450, 100:650] = (250, 20, 30, 99)
+    prompts = [[vz.VisualPrompt("layer", layer=layer),
+                vz.VisualPrompt("rectangle", rgba=(0, 0, 255, 200), bbox=(5, 5, 690, 480), width=4)]] + [[]] * 4
+    got = vz.process_fixed_images([torch.from_numpy(x).cuda() for x in imgs], lut, prompts, out_mode="chw", mode=mode)
+    for i, img in enumerate(imgs):
+        src = img
+        if i == 0:
+            src = P.alpha_composite_rgb(img, layer)
+            m = P.draw_rectangle_mask(500, 700, (5, 5, 690, 480), 4)
+            ov = np.zeros((500, 700, 4), np.uint8)
+            ov[m] = (0, 0, 255, 200)
+            src = P.alpha_composite_rgb(src, ov)
+        ref = P.normalize_lut(P.process_images_u8(src, mode)[None], lut)[0]
+        assert np.array_equal(got[i][0].cpu().numpy(), ref), (mode, i)

@@ -42,6 +42,32 @@ def test_lanczos_table_equals_oracle_matrix(n_in, n_out):
     assert np.array_equal(K, ref)
 
 
+@pytest.mark.parametrize("n_in,n_out", [(700, 470), (500, 336), (200, 448), (1300, 336), (336, 336)])
+def test_bicubic_table_equals_oracle_matrix(n_in, n_out):
+    t = anyres.resample_table(n_in, n_out, "bicubic")
+    ks, n = int(t[0]), int(t[1])
+    xmin, cnt, kk = t[2:2 + n], t[2 + n:2 + 2 * n], t[2 + 2 * n:].reshape(n, ks)
+    K = np.zeros((n_out, n_in), np.int64)
+    for x in range(n):
+        K[x, xmin[x]:xmin[x] + cnt[x]] = kk[x, :cnt[x]]
+    ref = P.coeff_matrix(n_in, n_out, "bicubic") if n_in != n_out else np.eye(n_in, dtype=np.int64) * (1 << 22)
+    assert np.array_equal(K, ref)
+
+
+def test_fixed_view_geometry():
+    """canvas / view geometry of the process_images modes (mm_utils.py:16-87, train.py:570-590)"""
+    v, c = anyres.fixed_view((700, 500), "pad")
+    assert (c["W"], c["H"], c["pad_x"], c["pad_y"], c["bg"]) == (700, 700, 0, 100, (122, 116, 104))
+    assert (v[0]["out_w"], v[0]["out_h"], v[0]["tile_x"], v[0]["tile_y"], v[0]["filt"]) == (336, 336, 0, 0, "bicubic")
+    v, c = anyres.fixed_view((420, 901), "square")
+    assert (c["W"], c["H"], c["pad_x"], c["pad_y"]) == (420, 420, 0, -240)
+    v, c = anyres.fixed_view((700, 500), "plain")
+    assert (v[0]["out_w"], v[0]["out_h"], v[0]["tile_x"], v[0]["tile_y"]) == (470, 336, 67, 0)
+    assert anyres.single_view((336, 336)) == [dict(out_w=336, out_h=336, off_x=0, off_y=0, tile_x=0, tile_y=0)]
+    with pytest.raises(ValueError):
+        anyres.fixed_view((10, 10), "identity")
+
+
 def test_merged_row_counts_match_reference(golden_dir):
     g = np.load(f"{golden_dir}/golden_merge.npz")
     for c in range(10):

@@ -75,3 +75,45 @@ def test_patchify_is_conv_im2col():
     ref = torch.nn.functional.conv2d(torch.from_numpy(px), torch.from_numpy(w), stride=14).flatten(2).transpose(1, 2)
     got = P.patchify(px) @ w.reshape(8, 588).T
     assert np.allclose(ref.reshape(-1, 8).numpy(), got, atol=1e-3)
+
+
+def test_bicubic_resize_matches_pillow():
+    """the oracle's bicubic pass (what CLIPImageProcessor.resize asks Pillow for) is bit-exact"""
+    from PIL import Image
+    rng = np.random.default_rng(11)
+    for (W, H), (w, h) in [((700, 500), (470, 336)), ((336, 900), (336, 900)), ((500, 333), (504, 336)),
+                           ((1300, 1300), (336, 336)), ((200, 150), (448, 336)), ((337, 336), (337, 336))]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(img).resize((w, h), Image.BICUBIC))
+        assert np.array_equal(P.pil_resize(img, (w, h), "bicubic"), ref), ((W, H), (w, h))
+
+
+def test_process_images_modes_match_pillow_flow():
+    """mm_utils.process_images / train.py:570-590 geometry (expand2square, centre crop, LANCZOS squash, then the
+    CLIP processor's BICUBIC short-side resize + centre crop) restated on arrays == the same steps in Pillow"""
+    from PIL import Image
+    rng = np.random.default_rng(12)
+    mean = (0.48145466, 0.4578275, 0.40821073)
+    for (W, H) in [(700, 500), (420, 901), (336, 336), (1000, 1000), (301, 640)]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        pil = Image.fromarray(img)
+        for mode in ("pad", "square", "resize", "plain"):
+            im = pil
+            if mode == "pad":
+                bg = tuple(int(x * 255) for x in mean)
+                m = max(W, H)
+                if W != H:
+                    im = Image.new("RGB", (m, m), bg)
+                    im.paste(pil, (0, (W - H) // 2) if W > H else ((H - W) // 2, 0))
+            elif mode == "resize":
+                im = pil.resize((336, 336), Image.Resampling.LANCZOS)
+            elif mode == "square":
+                m = min(W, H)
+                left, top = int((W - m) / 2), int((H - m) / 2)
+                im = pil.crop((left, top, left + m, top + m))
+            w, h = im.size
+            nw, nh = (336, int(336 * h / w)) if w <= h else (int(336 * w / h), 336)
+            r = im.resize((nw, nh), Image.BICUBIC)
+            left, top = (nw - 336) // 2, (nh - 336) // 2
+            ref = np.asarray(r.crop((left, top, left + 336, top + 336)))
+            assert np.array_equal(P.process_images_u8(img, mode, mean), ref), (W, H, mode)

@@ -37,7 +37,8 @@ class GemmArgs(C.Structure):
 
 class ImageDesc(C.Structure):
     _fields_ = [("src", C.c_void_p), ("layers", C.c_void_p), ("W", C.c_int), ("H", C.c_int),
-                ("prim_begin", C.c_int), ("prim_count", C.c_int)]
+                ("prim_begin", C.c_int), ("prim_count", C.c_int),
+                ("pad_x", C.c_int), ("pad_y", C.c_int), ("bg", C.c_uint32), ("reserved", C.c_int)]
 
 
 class Prim(C.Structure):

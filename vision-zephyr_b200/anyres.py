@@ -105,11 +105,32 @@ def _lanczos(x: float) -> float:
     return 0.0
 
 
-@lru_cache(maxsize=512)
+def _bicubic(x: float) -> float:
+    """Pillow Resample.c bicubic_filter (a = -0.5, support 2)."""
+    a = -0.5
+    if x < 0.0:
+        x = -x
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+_FILTERS = {"lanczos": (_lanczos, 3.0), "bicubic": (_bicubic, 2.0)}
+
+
 def lanczos_table(in_size: int, out_size: int) -> np.ndarray:
-    """int32 table [ksize, out_size, xmin[out], count[out], kk[out*ksize]] for one axis.
+    return resample_table(in_size, out_size, "lanczos")
+
+
+@lru_cache(maxsize=512)
+def resample_table(in_size: int, out_size: int, filt: str = "lanczos") -> np.ndarray:
+    """int32 table [ksize, out_size, xmin[out], count[out], kk[out*ksize]] for one axis and one Pillow
+    filter ('lanczos': Image.resize(LANCZOS); 'bicubic': what CLIPImageProcessor.resize asks for).
     in_size == out_size yields the identity table (Image.resize returns a copy in that case,
     and Resample.c skips the pass)."""
+    fn, fsupport = _FILTERS[filt]
     if in_size == out_size:
         ksize = 1
         xmin = np.arange(out_size, dtype=np.int32)
@@ -118,7 +139,7 @@ def lanczos_table(in_size: int, out_size: int) -> np.ndarray:
         return np.concatenate([np.array([ksize, out_size], np.int32), xmin, cnt, kk])
     scale = float(np.float32(in_size) - np.float32(0)) / out_size
     filterscale = max(scale, 1.0)
-    support = 3.0 * filterscale
+    support = fsupport * filterscale
     ksize = int(math.ceil(support)) * 2 + 1
     xmin = np.zeros(out_size, np.int32)
     cnt = np.zeros(out_size, np.int32)
@@ -133,7 +154,7 @@ def lanczos_table(in_size: int, out_size: int) -> np.ndarray:
         if hi > in_size:
             hi = in_size
         n = hi - lo
-        w = [_lanczos((x + lo - center + 0.5) * ss) for x in range(n)]
+        w = [fn((x + lo - center + 0.5) * ss) for x in range(n)]
         ww = 0.0
         for v in w:
             ww += v
@@ -155,10 +176,10 @@ class TablePool:
         self._words = 0
         self.max_ksize = 1
 
-    def offset(self, in_size: int, out_size: int) -> int:
-        key = (in_size, out_size)
+    def offset(self, in_size: int, out_size: int, filt: str = "lanczos") -> int:
+        key = (in_size, out_size, filt)
         if key not in self._off:
-            t = lanczos_table(in_size, out_size)
+            t = resample_table(in_size, out_size, filt)
             self._off[key] = self._words
             self._chunks.append(t)
             self._words += t.size
@@ -185,16 +206,52 @@ def anyres_views(image_size: Tuple[int, int], grid_pinpoints) -> Tuple[List[dict
 
 
 def single_view(image_size: Tuple[int, int], mode: str = "identity") -> List[dict]:
-    """Fixed-336 path (mm_utils.process_images, mm_utils.py:38-87) for an image that is already
-    336x336 ('identity'), or 'resize' = LANCZOS squash to 336x336."""
+    """Fixed-336 path for an image that is already 336x336 ('identity'), or 'resize' = LANCZOS squash
+    to 336x336 (mm_utils.py:59-63).  See fixed_view for the other modes of mm_utils.process_images."""
+    return fixed_view(image_size, mode)[0]
+
+
+def hf_resize_size(image_size: Tuple[int, int], short: int = TILE) -> Tuple[int, int]:
+    """CLIPImageProcessor.resize with size={'shortest_edge': 336}: the short side becomes 336, the long
+    side int(336 * long / short) (transformers get_resize_output_image_size, default_to_square=False)."""
     w, h = image_size
+    if w <= h:
+        return short, int(short * h / w)
+    return int(short * w / h), short
+
+
+def fixed_view(image_size: Tuple[int, int], mode: str = "identity", image_mean=None):
+    """One 336x336 view per image, as mm_utils.process_images (mm_utils.py:38-87) and the 'pad' / plain
+    branches of the training loader (train/train.py:570-590) produce it.  Returns (views, canvas) where
+    canvas = dict(W, H, pad_x, pad_y, bg) is the virtual source the tables address:
+      'identity'  336x336 input, nothing to do
+      'resize'    LANCZOS squash to 336x336
+      'plain'     CLIPImageProcessor.preprocess: BICUBIC resize of the short side to 336, centre crop
+      'square'    centre crop to min(w, h) (mm_utils.py:65-74), then 'plain'
+      'pad'       expand2square with the mean colour (mm_utils.py:16-35), then 'plain'"""
+    w, h = image_size
+    canvas = dict(W=w, H=h, pad_x=0, pad_y=0, bg=(0, 0, 0))
     if mode == "identity":
         if (w, h) != (TILE, TILE):
             raise ValueError("identity view needs a 336x336 image")
-        return [dict(out_w=TILE, out_h=TILE, off_x=0, off_y=0, tile_x=0, tile_y=0)]
+        return [dict(out_w=TILE, out_h=TILE, off_x=0, off_y=0, tile_x=0, tile_y=0)], canvas
     if mode == "resize":
-        return [dict(out_w=TILE, out_h=TILE, off_x=0, off_y=0, tile_x=0, tile_y=0)]
-    raise ValueError(f"unknown mode {mode}")
+        return [dict(out_w=TILE, out_h=TILE, off_x=0, off_y=0, tile_x=0, tile_y=0)], canvas
+    if mode == "square":
+        m = min(w, h)
+        left, top = int((w - m) / 2), int((h - m) / 2)
+        canvas = dict(W=m, H=m, pad_x=-left, pad_y=-top, bg=(0, 0, 0))
+    elif mode == "pad":
+        m = max(w, h)
+        mean = image_mean if image_mean is not None else (0.48145466, 0.4578275, 0.40821073)
+        bg = tuple(int(x * 255) for x in mean)
+        canvas = dict(W=m, H=m, pad_x=(m - w) // 2 if h > w else 0, pad_y=(m - h) // 2 if w > h else 0, bg=bg)
+    elif mode != "plain":
+        raise ValueError(f"unknown mode {mode}")
+    nw, nh = hf_resize_size((canvas["W"], canvas["H"]))
+    # transformers center_crop: top = (h - 336) // 2, left = (w - 336) // 2
+    view = dict(out_w=nw, out_h=nh, off_x=0, off_y=0, tile_x=(nw - TILE) // 2, tile_y=(nh - TILE) // 2, filt="bicubic")
+    return [view], canvas
 
 
 # ---------------------------------------------------------------------------------------------

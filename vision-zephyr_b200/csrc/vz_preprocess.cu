@@ -171,44 +171,69 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PreArgs
 #pragma unroll
     for (int c = 0; c < 3; ++c) acc[y][c] = 1 << (PREC - 1);
 
-  const int nbytes = (sx1 - sx0) * 3;
   const uint8_t* img_end = im.src + (size_t)im.W * im.H * 3;
+  // The tables address a virtual CANVAS; the image sits at (pad_x, pad_y) inside it (expand2square
+  // padding: pad >= 0 and the rest of the canvas has the colour `bg`; centre crop: pad <= 0).
+  // Real columns of this tile's window, in image coordinates:
+  const int rx0 = max(sx0 - im.pad_x, 0), rx1 = min(sx1 - im.pad_x, im.W);
+  const bool needs_fill = (sx0 - im.pad_x < 0) || (sx1 - im.pad_x > im.W) || (sy0 - im.pad_y < 0) ||
+                          (sy1 - im.pad_y > im.H);
   // Rows land in smem at the same 16-byte phase they have in global memory, so the copy is made of
-  // aligned 128-bit loads; `row_phase(sy)` is where the first needed byte sits in the buffer.
+  // aligned 16-byte chunks; `row_phase(sy)` is where canvas column sx0 sits in the row's buffer.
   auto row_phase = [&](int sy) -> int {
-    return (int)(reinterpret_cast<uintptr_t>(im.src + ((size_t)sy * im.W + sx0) * 3) & 15);
+    const int yr = sy - im.pad_y;
+    if (yr < 0 || yr >= im.H || rx1 <= rx0) return 0;
+    const uintptr_t g = reinterpret_cast<uintptr_t>(im.src + ((size_t)yr * im.W + rx0) * 3);
+    return (int)((g - (uintptr_t)((rx0 + im.pad_x - sx0) * 3)) & 15);
   };
-  // asynchronous copy of the raw bytes of source row sy into a ring slot (one commit group per row)
+  // asynchronous copy of the raw bytes of canvas row sy into a ring slot (one commit group per row)
   auto issue_row = [&](int sy, uint8_t* dst) {
-    if (sy < sy1) {
-      const uint8_t* srow = im.src + ((size_t)sy * im.W + sx0) * 3;
-      const int ph = (int)(reinterpret_cast<uintptr_t>(srow) & 15);
-      const uint8_t* g0 = srow - ph;
-      const int nvec = (nbytes + ph + 15) >> 4;
+    const int yr = sy - im.pad_y;
+    if (sy < sy1 && yr >= 0 && yr < im.H && rx1 > rx0) {
+      const uint8_t* srow = im.src + ((size_t)yr * im.W + rx0) * 3;
+      const int a16 = (int)(reinterpret_cast<uintptr_t>(srow) & 15);
+      const uint8_t* g0 = srow - a16;
+      uint8_t* d0 = dst + row_phase(sy) + (rx0 + im.pad_x - sx0) * 3 - a16;   // 16-byte aligned, >= dst
+      const int nvec = ((rx1 - rx0) * 3 + a16 + 15) >> 4;
       for (int i = tid; i < nvec; i += PP_THREADS) {
         const uint8_t* g = g0 + 16 * i;
         const long left = img_end - g;     // bytes of the image from g on
-        cp_async_16_partial(dst + 16 * i, g, left >= 16 ? 16 : (left > 0 ? (int)left : 0));
+        cp_async_16_partial(d0 + 16 * i, g, left >= 16 ? 16 : (left > 0 ? (int)left : 0));
       }
     }
     cp_async_commit();
   };
+  // canvas pixels outside the image take the background colour (expand2square, mm_utils.py:16-35)
+  auto fill_row = [&](int sy, uint8_t* dst) {
+    const int ph = row_phase(sy);
+    const int yr = sy - im.pad_y;
+    const bool row_real = yr >= 0 && yr < im.H;
+    const uint8_t b0 = (uint8_t)(im.bg & 0xff), b1 = (uint8_t)((im.bg >> 8) & 0xff), b2 = (uint8_t)((im.bg >> 16) & 0xff);
+    for (int px = tid; px < sx1 - sx0; px += PP_THREADS) {
+      const int xr = sx0 + px - im.pad_x;
+      if (row_real && xr >= 0 && xr < im.W) continue;
+      uint8_t* q = dst + ph + px * 3;
+      q[0] = b0; q[1] = b1; q[2] = b2;
+    }
+  };
   // visual prompts: blend the instances over the row in place (one thread per pixel; the instance list
-  // sits in shared memory and every RGBA overlay pixel is one aligned 32-bit load)
+  // sits in shared memory and every RGBA overlay pixel is one aligned 32-bit load); image coordinates
   auto blend_row = [&](int sy, uint8_t* dst) {
     const int ph = row_phase(sy);
-    const int npx = sx1 - sx0;
-    for (int px = tid; px < npx; px += PP_THREADS) {
-      const int xs = sx0 + px;
+    const int yr = sy - im.pad_y;
+    if (yr < 0 || yr >= im.H) return;
+    for (int px = tid; px < sx1 - sx0; px += PP_THREADS) {
+      const int xr = sx0 + px - im.pad_x;
+      if (xr < 0 || xr >= im.W) continue;
       uint8_t* q = dst + ph + px * 3;
       int r = q[0], g = q[1], b = q[2];
       for (int pi = 0; pi < n_prims; ++pi) {
         const vz_prim& p = s_prims[pi];
         uint32_t ov;
         if (p.type == VZ_PRIM_LAYER) {
-          ov = __ldg(reinterpret_cast<const uint32_t*>(im.layers) + ((size_t)p.layer * im.H + sy) * im.W + xs);
+          ov = __ldg(reinterpret_cast<const uint32_t*>(im.layers) + ((size_t)p.layer * im.H + yr) * im.W + xr);
         } else {
-          if (!rect_covers(p, xs, sy)) continue;
+          if (!rect_covers(p, xr, yr)) continue;
           ov = p.rgba;
         }
         const int al = (int)(ov >> 24);
@@ -227,8 +252,9 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PreArgs
     cp_async_wait<NBUF - 2>();   // row sy has landed (for this thread's copies) ...
     __syncthreads();             // ... and for everyone's; row sy - 1 is no longer read by anybody
     issue_row(sy + NBUF - 1, s_row + ((sy + NBUF - 1 - sy0) % NBUF) * a.row_buf_bytes);
-    if (im.prim_count != 0) {
-      blend_row(sy, cur);
+    if (needs_fill || im.prim_count != 0) {
+      if (needs_fill) fill_row(sy, cur);
+      if (im.prim_count != 0) blend_row(sy, cur);
       __syncthreads();
     }
     // horizontal pass for this thread's pixel: taps beyond the column's count have zero coefficients

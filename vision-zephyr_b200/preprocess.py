@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .anyres import TILE, TablePool, anyres_views, single_view
+from .anyres import TILE, TablePool, anyres_views, single_view, fixed_view
 
 OPENAI_CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 OPENAI_CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
@@ -94,8 +94,11 @@ def _struct_array_to_dev(arr, device) -> torch.Tensor:
 
 
 def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut: np.ndarray,
-               prompts: Optional[Sequence[Sequence[VisualPrompt]]] = None) -> PreprocessPlan:
-    """images: u8 CUDA tensors [H,W,3]; views[i]: list of view dicts (see anyres.anyres_views)."""
+               prompts: Optional[Sequence[Sequence[VisualPrompt]]] = None,
+               canvases: Optional[Sequence[Optional[dict]]] = None) -> PreprocessPlan:
+    """images: u8 CUDA tensors [H,W,3]; views[i]: list of view dicts (see anyres.anyres_views);
+    canvases[i] (optional): dict(W, H, pad_x, pad_y, bg) = the virtual source the views' tables address
+    (anyres.fixed_view: expand2square padding / centre crop); default = the image itself."""
     device = images[0].device
     pool = TablePool()
     n_img = len(images)
@@ -144,6 +147,13 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
         d.src = im.data_ptr()
         d.layers = lay_dev.data_ptr() if lay_dev is not None else None
         d.W, d.H = W, H
+        cv = canvases[i] if canvases is not None and canvases[i] is not None else None
+        cW, cH = (cv["W"], cv["H"]) if cv else (W, H)
+        if cv:
+            d.pad_x, d.pad_y = int(cv["pad_x"]), int(cv["pad_y"])
+            r_, g_, b_ = cv.get("bg", (0, 0, 0))
+            d.bg = (r_ & 255) | ((g_ & 255) << 8) | ((b_ & 255) << 16)
+        max_w = max(max_w, cW)
         d.prim_begin, d.prim_count = begin, len(prim_list) - begin
         if d.prim_count > 32:
             raise ValueError("at most 32 visual-prompt instances per image")
@@ -154,8 +164,8 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
             t.out_w, t.out_h = v["out_w"], v["out_h"]
             t.off_x, t.off_y = v["off_x"], v["off_y"]
             t.tile_x, t.tile_y = v["tile_x"], v["tile_y"]
-            t.tab_h = pool.offset(W, v["out_w"])
-            t.tab_v = pool.offset(H, v["out_h"])
+            t.tab_h = pool.offset(cW, v["out_w"], v.get("filt", "lanczos"))
+            t.tab_v = pool.offset(cH, v["out_h"], v.get("filt", "lanczos"))
             tile_list.append(t)
     n_tiles = len(tile_list)
     tile_arr = (_lib.TileDesc * n_tiles)(*tile_list)
@@ -236,10 +246,13 @@ def process_any_resolution_images(images: Sequence[torch.Tensor], grid_pinpoints
 
 
 def process_fixed_images(images: Sequence[torch.Tensor], lut: np.ndarray, prompts=None,
-                         out_mode: str = "patches", mode: str = "identity"):
-    """Fixed-336 path (config 2): blend visual prompts onto 336x336 images, normalise, patchify."""
-    views = [single_view((int(im.shape[1]), int(im.shape[0])), mode) for im in images]
-    plan = build_plan(images, views, lut, prompts)
+                         out_mode: str = "patches", mode: str = "identity", image_mean=None):
+    """Fixed-336 path: blend visual prompts onto the images, bring them to 336x336 the way
+    mm_utils.process_images / the training loader do (mode: 'identity' | 'resize' | 'plain' | 'square' |
+    'pad', see anyres.fixed_view), normalise, patchify.  Config 2 = 'identity' with prompts."""
+    vc = [fixed_view((int(im.shape[1]), int(im.shape[0])), mode, image_mean) for im in images]
+    views, canvases = [v for v, _ in vc], [c for _, c in vc]
+    plan = build_plan(images, views, lut, prompts, canvases)
     out = run_plan(plan, out_mode)
     if out_mode == "patches":
         return PatchBatch(out, plan.tiles_per_image, plan.image_sizes)
