@@ -153,3 +153,34 @@ def test_sharded_path_world1_equals_unsharded(vision_path, golden_dir):
         if created:
             dist.destroy_process_group()
     assert torch.equal(ref[4], got[4]) and torch.equal(ref[5], got[5]) and torch.equal(ref[2], got[2])
+
+
+def test_full_size_batch_agrees_with_one_image_at_a_time(vision_path, golden_dir):
+    """BASELINE config 3 at full size (8 anyres images = 40 tiles, the bench workload) through a size-independent
+    property: tiles are independent, so encoding the batch must agree with encoding every image on its own.
+    The two runs take different kernel forms (2-CTA 256x256 tiles + stream-K tails at 40 tiles, 1-CTA 128-wide tiles
+    at 5), so this ties the big configuration to the small ones that are checked against the reference goldens.
+    Same prompt for every sample, so the batch-global text length (quirk Q3) is the same in both runs."""
+    import vision_zephyr_b200 as vz
+    lut = _lut(golden_dir)
+    sizes = [(1000, 900), (900, 1000), (1344, 1344), (700, 650), (1000, 900), (800, 760), (1200, 1100), (672, 672)]
+    imgs = [torch.from_numpy(synth_image(40 + i, w, h)).cuda() for i, (w, h) in enumerate(sizes)]
+    ids1 = torch.randint(3, 32000, (1, 64), generator=torch.Generator().manual_seed(7))
+    ids1[0, 10] = -200
+    ids = ids1.repeat(8, 1).cuda()
+    pb = vz.process_any_resolution_images(imgs, PINPOINTS_C3, lut, out_mode="patches")
+    assert pb.tiles_per_image == [5] * 8
+    full = vision_path.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, pb, sizes)[4]
+    torch.cuda.synchronize()
+    assert full.shape == (8, 63 + 160, 4096) and torch.isfinite(full.float()).all()
+    worst_cos, worst_err = 1.0, 0.0
+    for i in range(8):
+        pbi = vz.process_any_resolution_images(imgs[i:i + 1], PINPOINTS_C3, lut, out_mode="patches")
+        one = vision_path.prepare_inputs_labels_for_multimodal(ids[i:i + 1], None, None, None, None, pbi, sizes[i:i + 1])[4]
+        torch.cuda.synchronize()
+        a, b = full[i, 10:170].float().cpu().numpy(), one[0, 10:170].float().cpu().numpy()
+        worst_cos = min(worst_cos, float(cos_rows(a, b).min()))
+        worst_err = max(worst_err, float(np.abs(a - b).max()))
+        assert torch.equal(full[i, :10], one[0, :10]) and torch.equal(full[i, 170:], one[0, 170:])   # text rows: exact copies
+    print(f"batch of 40 tiles vs one image at a time: min cos {worst_cos:.6f} max_abs {worst_err:.4g}")
+    assert worst_cos >= 0.9995 and worst_err <= 0.1

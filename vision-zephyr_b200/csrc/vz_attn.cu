@@ -417,11 +417,7 @@ int qattn_launch(int mode, const void* q, int q_rs, int q_zrows, const void* k0,
   a.L = L; a.use_pad = (mode == 0) ? 1 : 0;
   a.out = reinterpret_cast<__nv_bfloat16*>(out); a.ldo = ldo;
   a.scale = 0.044194173824159216f;  // 1/sqrt(512)
-  static bool attr_done = false;
-  if (!attr_done) {
-    VZ_CUDA_CHECK(cudaFuncSetAttribute(qattn32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QA_SMEM));
-    attr_done = true;
-  }
+  VZ_ENSURE_DYN_SMEM(qattn32_kernel, QA_SMEM);
   dim3 grid(VZ_QF_HEADS, Z);
   qattn32_kernel<<<grid, QA_THREADS, QA_SMEM, st>>>(a);
   VZ_LAUNCH_CHECK();

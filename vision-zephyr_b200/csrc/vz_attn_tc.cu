@@ -434,11 +434,7 @@ int vit_attn_tc_launch(const void* qkv, void* out, int T, cudaStream_t st) {
   VZ_TRY(encode_tmap_2d_bf16(&tmKV, qkv, (long long)T * TOK, 3 * VZ_VIT_WIDTH, 3 * VZ_VIT_WIDTH, HD, BKV));
   // output as [tile][577 rows][1024]: a 32-row store box that runs past a tile's last row is clipped by the TMA
   VZ_TRY(encode_tmap_3d_bf16(&tmO, out, TOK, VZ_VIT_WIDTH, VZ_VIT_WIDTH, 32, T, (long long)TOK * VZ_VIT_WIDTH));
-  static bool attr_done = false;
-  if (!attr_done) {
-    VZ_CUDA_CHECK(cudaFuncSetAttribute(vit_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    attr_done = true;
-  }
+  VZ_ENSURE_DYN_SMEM(vit_attn_tc_kernel, SMEM_TOTAL);
   int dev = 0, num_sms = 0;
   VZ_CUDA_CHECK(cudaGetDevice(&dev));
   VZ_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));

@@ -4,6 +4,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -36,6 +38,20 @@ void count_launch();
   do {                          \
     int _s = (expr);            \
     if (_s != VZ_OK) return _s; \
+  } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: set it once per
+// device for the kernel `func` (one `mask` per kernel; devices 0..63).  Racing first calls are harmless.
+#define VZ_ENSURE_DYN_SMEM(func, bytes)                                                              \
+  do {                                                                                               \
+    static std::atomic<unsigned long long> vz_mask_{0};                                              \
+    int vz_dev_ = 0;                                                                                 \
+    VZ_CUDA_CHECK(cudaGetDevice(&vz_dev_));                                                          \
+    const unsigned long long vz_bit_ = 1ull << (vz_dev_ & 63);                                       \
+    if (!(vz_mask_.load(std::memory_order_relaxed) & vz_bit_)) {                                     \
+      VZ_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
+      vz_mask_.fetch_or(vz_bit_, std::memory_order_relaxed);                                         \
+    }                                                                                                \
   } while (0)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -628,12 +628,7 @@ int launch_tc(const vz_gemm_args& a, const GemmDev& p_in, int num_sms, cudaStrea
   VZ_TRY(make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM, a.batch, a.a_bstride));
   if (BKN) VZ_TRY(make_tmap(&tmB, a.W, a.K, a.N, a.ldw, 64, a.batch, a.w_bstride));   // [K, N]: 64 x 64 boxes
   else VZ_TRY(make_tmap(&tmB, a.W, a.N, a.K, a.ldw, TWO ? BN / 2 : BN, a.batch, a.w_bstride));
-  static bool attr_done = false;  // idempotent attribute; benign race
-  if (!attr_done) {
-    VZ_CUDA_CHECK(cudaFuncSetAttribute((gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO, BKN>),
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_done = true;
-  }
+  VZ_ENSURE_DYN_SMEM((gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO, BKN>), C::SMEM_BYTES);
   GemmDev p = p_in;
   const long tiles = (long)p.num_m * p.num_n * p.batch;
   const int workers = TWO ? num_sms / 2 : num_sms;

@@ -80,7 +80,7 @@ int gemm_batched(const void* A, int lda, long long sa, const void* W, int ldw, l
 
 struct VitWs {
   void* hs[VZ_VIT_LAYERS + 1];
-  void *xn, *qkv, *attn, *mid, *h;
+  void *qkv, *attn, *mid, *h;
   float *statsA, *statsB;  // [M][<=16][2] partial row statistics (LayerNorm fused into the GEMMs)
   void* sk;                // stream-K scratch of the GEMMs
   size_t sk_bytes;
@@ -94,7 +94,6 @@ VitWs vit_layout(void* base, int T) {
   // hidden states are contiguous so tests can copy them out in one go
   uint8_t* hs0 = reinterpret_cast<uint8_t*>(b.take((VZ_VIT_LAYERS + 1) * M * VZ_VIT_WIDTH * kB16));
   for (int i = 0; i <= VZ_VIT_LAYERS; ++i) w.hs[i] = base ? hs0 + (size_t)i * M * VZ_VIT_WIDTH * kB16 : nullptr;
-  w.xn = b.take(M * VZ_VIT_WIDTH * kB16);
   w.qkv = b.take(M * 3 * VZ_VIT_WIDTH * kB16);
   w.attn = b.take(M * VZ_VIT_WIDTH * kB16);
   w.mid = b.take(M * VZ_VIT_WIDTH * kB16);
@@ -108,7 +107,7 @@ VitWs vit_layout(void* base, int T) {
 }
 
 struct QfWs {
-  void *featsN, *qk, *S, *Pm, *PF, *x, *xn, *qkv, *attn, *q, *hbuf, *q0n, *qkv0, *tn, *kv_text, *attn0, *x1;
+  void *featsN, *qk, *S, *Pm, *PF, *x, *qkv, *attn, *q, *hbuf, *q0n, *qkv0, *tn, *kv_text, *attn0, *x1;
   float* stats;            // [M][<=64][2] partial row statistics of the residual stream (norms folded into GEMMs)
   void* sk;                // stream-K scratch of the GEMMs
   size_t sk_bytes;
@@ -127,7 +126,6 @@ QfWs qf_layout(void* base, int T, int n_samples, int text_rows) {
   w.Pm = b.take((size_t)T * HQ * VZ_VIT_PATCHES * kB16);              // [T][256][576]
   w.PF = b.take((size_t)T * HQ * VZ_FUSED_WIDTH * kB16);              // [T][256][5120]
   w.x = b.take(M * VZ_QF_WIDTH * kB16);
-  w.xn = b.take(M * VZ_QF_WIDTH * kB16);
   w.qkv = b.take(M * 3 * VZ_QF_WIDTH * kB16);
   w.attn = b.take(M * VZ_QF_WIDTH * kB16);
   w.q = b.take(M * VZ_QF_WIDTH * kB16);

@@ -358,11 +358,7 @@ extern "C" int vz_preprocess(const vz_image_desc* images, int n_images, const vz
                       (size_t)((max_ksize + 3) / 4) * TILE * 16;
   if (smem > 220 * 1024) return VZ_ERR_UNSUPPORTED;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static bool attr_done = false;
-  if (!attr_done) {
-    VZ_CUDA_CHECK(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_done = true;
-  }
+  VZ_ENSURE_DYN_SMEM(preprocess_kernel, 220 * 1024);
   dim3 grid(24, n_tiles);
   preprocess_kernel<<<grid, PP_THREADS, smem, st>>>(a);
   VZ_LAUNCH_CHECK();
