@@ -245,8 +245,12 @@ class VisZephyrB200MetaForCausalLM(ABC):
             lo, hi = bounds[rank]
             if list(local_tiles) != list(tiles_per_image[lo:hi]):
                 raise ValueError(f"rank {rank} was given tiles {local_tiles}, expected {tiles_per_image[lo:hi]}")
+            rows_per_rank = [sum(tiles_per_image[a:b]) * model.mm_projector.num_queries for a, b in bounds]
+            from .dist import peer_gather_for
+            peer = peer_gather_for(sum(rows_per_rank), embed.shape[1], torch.bfloat16, dev, group)
         else:
             tiles_per_image, lo, hi = list(local_tiles), 0, len(local_tiles)
+            peer = None
         n_images = len(tiles_per_image)
         B, S = input_ids.shape
         if n_images > B:
@@ -284,12 +288,23 @@ class VisZephyrB200MetaForCausalLM(ABC):
             tile_sample = torch.repeat_interleave(torch.arange(hi - lo, dtype=torch.int32),
                                                   torch.tensor(tiles_per_image[lo:hi])).to(dev)
             text = TextPack(text_emb, text_off, text_rows, hi - lo, L_text, tile_sample)
-            vis_local = proj.forward_packed(feats, text, feats_normed=True)      # [T,32,4096] bf16
+            out_view = None
+            if peer is not None:
+                # the exchange step IS the projector's last kernel: its final LayerNorm stores go straight
+                # into the destination rank's receive buffer (peer-mapped over NVLink)
+                out_view = peer.slot(dst, sum(rows_per_rank[:rank]), rows_per_rank[rank])
+                out_view = out_view.view(sum(tiles_per_image[lo:hi]), proj.num_queries, -1)
+            vis_local = proj.forward_packed(feats, text, feats_normed=True, out=out_view)      # [T,32,4096] bf16
             vis_local = vis_local.reshape(-1, vis_local.shape[-1])
 
         # ---- the one exchange step ------------------------------------------------------------
-        if sharded:
-            rows_per_rank = [sum(tiles_per_image[a:b]) * proj.num_queries for a, b in bounds]
+        if sharded and peer is not None:
+            peer.finish()                                   # one device-side barrier; no data collective
+            if rank != dst:
+                peer.skip_local()
+                return None, None, None, past_key_values, None, None
+            vis = peer.local(sum(rows_per_rank))
+        elif sharded:
             vis = gather_visual_tokens(vis_local, rows_per_rank, group)
             if rank != dst:
                 return None, None, None, past_key_values, None, None
