@@ -20,9 +20,12 @@
 // warps without a valid query row (rows >= 577 of the last query block) only keep the barriers going.
 #include "vz_common.cuh"
 
+#include <stdlib.h>
+
 namespace vz {
 namespace {
 
+constexpr int VZ_ATTN_POLY_DEFAULT = 0;
 constexpr int TOK = VZ_VIT_TOKENS;          // 577
 constexpr int HD = 64;                      // head dim
 constexpr int BQ = 128, BKV = 64;           // query rows per CTA, keys per block
@@ -52,6 +55,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for x <= ~8 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, cubic
+// for 2^f (relative error < 1.5e-4, far below the bf16 rounding P gets anyway), exponent added as integer.
+// Every PE-th exponential of a key block takes this route so the 16-lane MUFU pipe and the FMA
+// pipe share the softmax (FA-4's trick); x is clamped at -125 so the result never leaves the normal range.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;          // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.0555041f, 0.2402265f);
+  p = fmaf(p, f, 0.6931472f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// (template parameter PE of the kernel: every PE-th exponential; 0 = all exponentials on the MUFU pipe)
+
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // exp2 may run up to 2^8 above the value it would have with the exact running maximum before the
@@ -77,7 +95,7 @@ struct SoftmaxState {
 // first NVALID are real keys (the rest of the tile's last block belongs to the next tile).
 // g = this CTA's running key-block counter (across work items): buffer b = g & 1, use = g >> 1;
 // j = block index inside the item (the accumulator is only touched when j > 0).
-template <int NCOL, int NVALID>
+template <int NCOL, int NVALID, int PE>
 __device__ __forceinline__ void softmax_block(SoftmaxState& s, uint32_t g, int j, int r, uint32_t t_lane,
                                               uint32_t tmem_base, uint32_t tmem_o, uint64_t* bar_s_full,
                                               uint64_t* bar_s_free, uint64_t* bar_p_full, uint64_t* bar_pv_done) {
@@ -124,8 +142,12 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& s, uint32_t g, int j
 #pragma unroll
   for (int i = 0; i < NCOL; i += 2) {
     // keys beyond NVALID are masked: probability 0 without spending an exponential on them
-    const float p0 = i < NVALID ? ex2_approx(fmaf(__uint_as_float(v[i]), s.sl2, -m_sl2)) : 0.f;
-    const float p1 = i + 1 < NVALID ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), s.sl2, -m_sl2)) : 0.f;
+    const float x0 = fmaf(__uint_as_float(v[i]), s.sl2, -m_sl2), x1 = fmaf(__uint_as_float(v[i + 1]), s.sl2, -m_sl2);
+    constexpr int PE1 = PE > 0 ? PE : 1;
+    const bool poly0 = PE > 0 && NCOL == 64 && (i % PE1) == PE1 - 1;      // compile-time after unrolling
+    const bool poly1 = PE > 0 && NCOL == 64 && ((i + 1) % PE1) == PE1 - 1;
+    const float p0 = i < NVALID ? (poly0 ? ex2_poly(x0) : ex2_approx(x0)) : 0.f;
+    const float p1 = i + 1 < NVALID ? (poly1 ? ex2_poly(x1) : ex2_approx(x1)) : 0.f;
     ls4[(i >> 1) % NCH] += p0 + p1;
     pk[i >> 1] = pack_bf16x2(p0, p1);
   }
@@ -167,6 +189,7 @@ __device__ __forceinline__ void item_coords(int item, int& qb, int& h, int& t) {
   t = th / VZ_VIT_HEADS;
 }
 
+template <int PE>
 __global__ void __launch_bounds__(THREADS, 2)
 vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    const __grid_constant__ CUtensorMap tmO, float scale, int n_items) {
@@ -398,16 +421,16 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (lane == 0) { mbar_arrive(&bar_s_free[b]); mbar_arrive(&bar_p_full[b]); }
         __syncwarp();
       };
-      if (active) softmax_block<BKV, BKV>(stt, g, 0, r, t_lane, tmem_base, tmem_o, bar_s_full, bar_s_free, bar_p_full,
+      if (active) softmax_block<BKV, BKV, PE>(stt, g, 0, r, t_lane, tmem_base, tmem_o, bar_s_full, bar_s_free, bar_p_full,
                                           bar_pv_done);
       else idle_block();
       ++g;
       if (pend) epilogue(pq, ph, pt, n - 1, pl, pact);
       if (active) {
         for (int j = 1; j < NKB - 1; ++j, ++g)
-          softmax_block<BKV, BKV>(stt, g, j, r, t_lane, tmem_base, tmem_o, bar_s_full, bar_s_free, bar_p_full,
+          softmax_block<BKV, BKV, PE>(stt, g, j, r, t_lane, tmem_base, tmem_o, bar_s_full, bar_s_free, bar_p_full,
                                   bar_pv_done);
-        softmax_block<LAST_N, LAST_VALID>(stt, g, NKB - 1, r, t_lane, tmem_base, tmem_o, bar_s_full, bar_s_free,
+        softmax_block<LAST_N, LAST_VALID, PE>(stt, g, NKB - 1, r, t_lane, tmem_base, tmem_o, bar_s_full, bar_s_free,
                                           bar_p_full, bar_pv_done);
         ++g;
       } else {
@@ -434,14 +457,24 @@ int vit_attn_tc_launch(const void* qkv, void* out, int T, cudaStream_t st) {
   VZ_TRY(encode_tmap_2d_bf16(&tmKV, qkv, (long long)T * TOK, 3 * VZ_VIT_WIDTH, 3 * VZ_VIT_WIDTH, HD, BKV));
   // output as [tile][577 rows][1024]: a 32-row store box that runs past a tile's last row is clipped by the TMA
   VZ_TRY(encode_tmap_3d_bf16(&tmO, out, TOK, VZ_VIT_WIDTH, VZ_VIT_WIDTH, 32, T, (long long)TOK * VZ_VIT_WIDTH));
-  VZ_ENSURE_DYN_SMEM(vit_attn_tc_kernel, SMEM_TOTAL);
+  // share of the exponentials computed on the FMA pipe (VZ_ATTN_POLY = 0 | 4 | 8: none, every 4th, every 8th)
+  static const int poly = []() { const char* e = getenv("VZ_ATTN_POLY"); return e ? atoi(e) : VZ_ATTN_POLY_DEFAULT; }();
   int dev = 0, num_sms = 0;
   VZ_CUDA_CHECK(cudaGetDevice(&dev));
   VZ_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   // persistent: two CTAs per SM walk the (tile, head, query block) items round-robin
   const int n_items = NQB * VZ_VIT_HEADS * T;
   const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
-  vit_attn_tc_kernel<<<grid, THREADS, SMEM_TOTAL, st>>>(tmQ, tmKV, tmO, 0.125f, n_items);
+  if (poly == 4) {
+    VZ_ENSURE_DYN_SMEM(vit_attn_tc_kernel<4>, SMEM_TOTAL);
+    vit_attn_tc_kernel<4><<<grid, THREADS, SMEM_TOTAL, st>>>(tmQ, tmKV, tmO, 0.125f, n_items);
+  } else if (poly == 8) {
+    VZ_ENSURE_DYN_SMEM(vit_attn_tc_kernel<8>, SMEM_TOTAL);
+    vit_attn_tc_kernel<8><<<grid, THREADS, SMEM_TOTAL, st>>>(tmQ, tmKV, tmO, 0.125f, n_items);
+  } else {
+    VZ_ENSURE_DYN_SMEM(vit_attn_tc_kernel<0>, SMEM_TOTAL);
+    vit_attn_tc_kernel<0><<<grid, THREADS, SMEM_TOTAL, st>>>(tmQ, tmKV, tmO, 0.125f, n_items);
+  }
   VZ_LAUNCH_CHECK();
   return VZ_OK;
 }

@@ -143,9 +143,13 @@ fuse_kernel(const FuseArgs a, const float* __restrict__ g, const float* __restri
 #pragma unroll
   for (int grp = 0; grp < 5; ++grp) {
     const int c = grp * VZ_VIT_WIDTH + threadIdx.x * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + c)), g1 = __ldg(reinterpret_cast<const float4*>(g + c + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c)), b1 = __ldg(reinterpret_cast<const float4*>(b + c + 4));
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     float r[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] = (v[grp][i] - mean) * rstd * g[c + i] + b[c + i];
+    for (int i = 0; i < 8; ++i) r[i] = (v[grp][i] - mean) * rstd * gg[i] + bb[i];
     *reinterpret_cast<uint4*>(o + grp * VZ_VIT_WIDTH) = pack8(r);
   }
 }
