@@ -55,18 +55,18 @@ def splice_c5():
     print(f"splice_plan   config5: {tp*1e6:.1f} us (latency-bound single CTA; {17*B*S/1e3:.0f} KB)")
 
 
-def preprocess(cfg):
+def preprocess(cfg, batch=16):
     lut = vz.clip_lut()
     if cfg == 2:
-        imgs = [torch.from_numpy(np.random.default_rng(i).integers(0, 256, (336, 336, 3), dtype=np.uint8)).cuda() for i in range(16)]
+        imgs = [torch.from_numpy(np.random.default_rng(i).integers(0, 256, (336, 336, 3), dtype=np.uint8)).cuda() for i in range(batch)]
         prompts = []
-        for i in range(16):
+        for i in range(batch):
             lay = np.zeros((336, 336, 4), np.uint8); lay[50:200, 60:220] = (0, 255, 0, 128)
             prompts.append([vz.VisualPrompt("rectangle", rgba=(255, 0, 0, 128), bbox=(30, 40, 200, 220), width=3),
                             vz.VisualPrompt("layer", layer=lay), vz.VisualPrompt("layer", layer=lay[::-1].copy())])
         views = [anyres.single_view((336, 336)) for _ in imgs]
         plan = build_plan(imgs, views, lut, prompts)
-        bytes_ = 16 * (338688 + 2 * 451584 + 677376)
+        bytes_ = batch * (338688 + 2 * 451584 + 677376)
     else:
         sizes = [(1000, 900), (900, 1000), (1344, 1344), (700, 650), (1000, 900), (800, 760), (1200, 1100), (672, 672)]
         pins = [[336, 672], [672, 336], [672, 672], [336, 1008], [1008, 336]]
@@ -76,10 +76,11 @@ def preprocess(cfg):
         bytes_ = sum(3 * w * h for w, h in sizes) + plan.n_tiles * 677376
     out = run_plan(plan, "patches")
     t = timeit(lambda: run_plan(plan, "patches", out))
-    print(f"preprocess config{cfg}: {plan.n_tiles} tiles, {bytes_/1e6:.1f} MB algorithmic in {t*1e6:.1f} us = {bytes_/t/1e9:.0f} GB/s "
+    print(f"preprocess config{cfg}{'' if batch == 16 else f' (batch {batch})'}: {plan.n_tiles} tiles, {bytes_/1e6:.1f} MB algorithmic in {t*1e6:.1f} us = {bytes_/t/1e9:.0f} GB/s "
           f"({bytes_/t/1e9/PEAK:.3f} of measured HBM peak)")
 
 
 splice_c5()
 preprocess(2)
+preprocess(2, batch=256)
 preprocess(3)

@@ -153,6 +153,72 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PreArgs
     if (ya <= yb) { sy0 = s_vmin[ya]; sy1 = s_vmin[yb] + s_vcnt[yb]; }
   }
   if (sx1 <= sx0) sy1 = sy0;  // tile lies completely in the padding
+
+  int acc[BAND][3];
+#pragma unroll
+  for (int y = 0; y < BAND; ++y)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[y][c] = 1 << (PREC - 1);
+
+  // ---- fast path: no resampling (identity tables, one tap per axis: the fixed-336 inputs of config 2) ----
+  // Nothing is staged or walked row by row: the thread of output pixel x gathers its 14 source pixels
+  // straight from global memory (all loads of a visual-prompt layer in flight together), blends the
+  // instances in order and leaves the values in the accumulators in the fixed-point form the common
+  // epilogue expects.  HBM-bound apart from the launch.
+  if (ksh == 1 && ksv == 1) {
+    const int rx = td.tile_x + x - td.off_x;
+    const bool col_ok = tid < TILE && rx >= 0 && rx < td.out_w;
+    const int xr = (col_ok ? h_min[rx] : 0) - im.pad_x;
+    const int kh = col_ok ? h_kk[rx] : 0;
+    uint32_t rgb[BAND];
+    bool real[BAND];
+    int yrs[BAND];
+#pragma unroll
+    for (int y = 0; y < BAND; ++y) {
+      const int ry = ry0 + y;
+      const bool row_ok = ry >= 0 && ry < td.out_h;
+      const int yr = (row_ok ? v_min[ry] : 0) - im.pad_y;
+      yrs[y] = yr;
+      real[y] = col_ok && row_ok && xr >= 0 && xr < im.W && yr >= 0 && yr < im.H;
+      uint32_t v = im.bg & 0xffffffu;
+      if (real[y]) {
+        const uint8_t* q = im.src + ((size_t)yr * im.W + xr) * 3;
+        v = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
+      }
+      rgb[y] = v;
+    }
+    for (int pi = 0; pi < n_prims; ++pi) {
+      const vz_prim p = s_prims[pi];
+      uint32_t ov[BAND];
+      if (p.type == VZ_PRIM_LAYER) {
+        const uint32_t* lay = reinterpret_cast<const uint32_t*>(im.layers) + (size_t)p.layer * im.H * im.W;
+#pragma unroll
+        for (int y = 0; y < BAND; ++y) ov[y] = real[y] ? __ldg(lay + (size_t)yrs[y] * im.W + xr) : 0u;
+      } else {
+#pragma unroll
+        for (int y = 0; y < BAND; ++y) ov[y] = (real[y] && rect_covers(p, xr, yrs[y])) ? p.rgba : 0u;
+      }
+#pragma unroll
+      for (int y = 0; y < BAND; ++y) {
+        const int al = (int)(ov[y] >> 24);   // alpha 0 leaves the pixel untouched (blend_over)
+        const int r = blend_over((int)(rgb[y] & 0xff), (int)(ov[y] & 0xff), al);
+        const int g = blend_over((int)((rgb[y] >> 8) & 0xff), (int)((ov[y] >> 8) & 0xff), al);
+        const int bl = blend_over((int)((rgb[y] >> 16) & 0xff), (int)((ov[y] >> 16) & 0xff), al);
+        rgb[y] = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)bl << 16);
+      }
+    }
+#pragma unroll
+    for (int y = 0; y < BAND; ++y) {
+      const int ry = ry0 + y;
+      const int kv = (ry >= 0 && ry < td.out_h) ? v_kk[ry] : 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int hv = clip8((1 << (PREC - 1)) + (int)((rgb[y] >> (8 * c)) & 0xff) * kh);   // the two one-tap passes
+        acc[y][c] = (1 << (PREC - 1)) + hv * kv;
+      }
+    }
+    sy1 = sy0;   // no row loop
+  }
   if (sy1 - sy0 > vt_rows) __trap();   // cannot happen: a band spans < 3.4 * ksize source rows (see vz_preprocess)
   // ---- vertical coefficient table: entry [i][y] = tap of source row sy0 + i in band row y, else 0 ----
   for (int i = tid; i < (sy1 - sy0) * VT_STRIDE; i += PP_THREADS) {
@@ -164,12 +230,6 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PreArgs
     }
     s_vtab[i] = coef;
   }
-
-  int acc[BAND][3];
-#pragma unroll
-  for (int y = 0; y < BAND; ++y)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) acc[y][c] = 1 << (PREC - 1);
 
   const uint8_t* img_end = im.src + (size_t)im.W * im.H * 3;
   // The tables address a virtual CANVAS; the image sits at (pad_x, pad_y) inside it (expand2square
