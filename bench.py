@@ -237,22 +237,62 @@ def main():
         return path.prepare_inputs_labels_for_multimodal(ids_dev, None, None, None, None, pb, sizes_global)
 
     out_host = {}
+    # e2e pipeline (user-level code around the public API): the H2D copy of step k + 1 and the D2H read of
+    # step k - 1 run on their own streams while step k computes; every step still copies ITS inputs from
+    # pinned host memory and reads ITS result back.  Two sets of device input buffers alternate.
+    h2d_stream, d2h_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    staged = [None, None]          # per buffer set: (device images, device ids, ready event)
+    set_free = [None, None]        # event: the compute that read this buffer set has finished
+    e2e_state = {"k": 0, "d2h_done": None}
+
+    def stage_inputs(k):
+        """enqueue the host->device copies of step k on the copy stream"""
+        s = k & 1
+        with torch.cuda.stream(h2d_stream):
+            if set_free[s] is not None:
+                h2d_stream.wait_event(set_free[s])
+            if staged[s] is None:
+                imgs = [torch.empty_like(x, device=dev) for x in host_imgs]
+                ids = torch.empty_like(ids_host, device=dev)
+            else:
+                imgs, ids, _ = staged[s]
+            for d, h in zip(imgs, host_imgs):
+                d.copy_(h, non_blocking=True)
+            ids.copy_(ids_host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(h2d_stream)
+        staged[s] = (imgs, ids, ev)
 
     def step_e2e():
         """public API from HOST buffers: H2D of images + ids, descriptor build, kernels, D2H of the result"""
-        imgs = [x.to(dev, non_blocking=True) for x in host_imgs]
-        ids = ids_host.to(dev, non_blocking=True)
+        k = e2e_state["k"]
+        cur = torch.cuda.current_stream()
+        if staged[k & 1] is None or k == 0:
+            stage_inputs(k)
+        imgs, ids, ready = staged[k & 1]
+        stage_inputs(k + 1)                       # next step's inputs travel while this step computes
+        cur.wait_event(ready)
         pb = vz.process_any_resolution_images(imgs, PINPOINTS, lut, out_mode="patches")
         if world > 1:
             r = path.prepare_inputs_labels_for_multimodal_sharded(ids, None, None, None, None, pb, tiles_global, sizes_global)
         else:
             r = path.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, pb, sizes_global)
+        done = torch.cuda.Event()
+        done.record(cur)
+        set_free[k & 1] = done
         if r[4] is not None:
             if "emb" not in out_host:
-                out_host["emb"] = torch.empty(r[4].shape, dtype=r[4].dtype).pin_memory()
-            out_host["emb"].copy_(r[4], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+                out_host["emb"] = [torch.empty(r[4].shape, dtype=r[4].dtype).pin_memory() for _ in range(2)]
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(done)
+                out_host["emb"][k & 1].copy_(r[4], non_blocking=True)
+                r[4].record_stream(d2h_stream)
+        e2e_state["k"] = k + 1
         return r
+
+    def e2e_drain():
+        h2d_stream.synchronize()
+        d2h_stream.synchronize()
 
     def barrier():
         if world > 1:
@@ -301,7 +341,24 @@ def main():
     # ---- e2e: host buffers --------------------------------------------------------------------
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    e2e_drain()
+
+    def e2e_steps():
+        step_e2e()
+
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        e2e_steps()
+    torch.cuda.current_stream().wait_stream(d2h_stream)      # the last result must have reached the host
+    t1.record()
+    e2e_drain()
+    barrier()
+    ms_e2e_t = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_e2e_t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms_e2e_t.item())
 
     if rank != 0:
         if world > 1:
@@ -313,7 +370,7 @@ def main():
     value = n_global / (ms_step / 1000.0)
     e2e_value = n_global / (ms_e2e / args.steps / 1000.0)
     h2d = sum(x.numel() for x in host_imgs) + ids_host.numel() * 8 + pre_plan.h2d_bytes
-    d2h = out_host["emb"].numel() * 2 + (2 * n_global + 4) * 4
+    d2h = out_host["emb"][0].numel() * 2 + (2 * n_global + 4) * 4
     gemm_tflops = (g_fl.value / 1e12) / (g_ms.value / 1e3) if g_ms.value > 0 else 0.0
     peak_tf = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
     line = {
@@ -326,7 +383,8 @@ def main():
                    "tiles_per_s": value * TILES_PER_IMAGE,
                    "path_tflops_algorithmic": value * TILES_PER_IMAGE * GFLOP_PER_TILE / 1000.0 / world},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "how": "public API from pinned host buffers; the copies of step k+1 / k-1 overlap the kernels of step k (2 copy streams)"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": "gemm_bf16_tcgen05_kernel", "bound": "tensor", "achieved": gemm_tflops, "peak": peak_tf,
