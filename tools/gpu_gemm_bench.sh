@@ -1,4 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for two in 0 1; do echo "== VZ_GEMM_2CTA=$two"; VZ_GEMM_2CTA=$two timeout 300 python tools/gemm_bench.py; done > gpurun_out/gemm_bench.log 2>&1
-cat gpurun_out/gemm_bench.log
+( timeout 900 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu ) > gpurun_out/test_gpu_kernels.log 2>&1
+echo "kernels exit $?"; tail -2 gpurun_out/test_gpu_kernels.log
+( timeout 300 python tools/gemm_bench.py ) > gpurun_out/gemm_bench.log 2>&1
+echo "gemm_bench exit $?"; grep -v "+sk" gpurun_out/gemm_bench.log | tail -9
