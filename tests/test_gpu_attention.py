@@ -103,3 +103,30 @@ def test_vit_attention_kernels_match_torch(impl):
     print(f"vit attention impl={impl}: max_abs_err {err:.4g} (ref max {ref.abs().max().item():.3g}) min row cos {cos:.6f}")
     assert torch.isfinite(out.float()).all()
     assert err < 0.03 and cos > 0.9995
+
+
+@pytest.mark.parametrize("T", [1, 2, 7, 40])
+def test_vit_attention_persistent_schedule(T):
+    """the persistent tcgen05 kernel at tile counts where the 80 T work items are fewer than, not a multiple of, and
+    far more than the 296 resident CTAs (item hand-over, deferred epilogues, Q double buffering), with score outliers
+    that force accumulator rescales late in a row, and rows of the next tile behind every tile's 577th key"""
+    import vision_zephyr_b200  # noqa: F401
+    from vision_zephyr_b200 import _lib as L
+    lib = L.load()
+    qkv = _rand((T * 577, 3072), 1.0, 300 + T)
+    qkv[:, :2048] *= 1.7
+    qkv[5::97, 1024:2048] *= 6.0          # a few keys with very large scores, scattered over the blocks
+    out = torch.full((T * 577, 1024), float("nan"), dtype=torch.bfloat16, device="cuda")
+    L.check(lib.vz_vit_attention(L.ptr(qkv), L.ptr(out), T, 1, L.stream_ptr()), "vit attention")
+    torch.cuda.synchronize()
+    worst = 0.0
+    for t0 in range(0, T, 8):                                  # reference in chunks of 8 tiles
+        t1 = min(T, t0 + 8)
+        x = qkv[t0 * 577:t1 * 577].float().view(t1 - t0, 577, 3, 16, 64)
+        q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+        ref = (torch.softmax((q @ k.transpose(-1, -2)) * 0.125, dim=-1) @ v).transpose(1, 2).reshape(-1, 1024)
+        got = out[t0 * 577:t1 * 577].float()
+        assert torch.isfinite(got).all()
+        worst = max(worst, (got - ref).abs().max().item())
+    print(f"T={T}: max_abs_err {worst:.4g}")
+    assert worst < 0.06
