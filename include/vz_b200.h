@@ -156,7 +156,18 @@ typedef struct {
   int off_x, off_y;    /* where the resized image is pasted on the (black) canvas                 */
   int tile_x, tile_y;  /* origin of this 336x336 tile on the canvas                               */
   int tab_h, tab_v;    /* offsets (in int32 words) of the axis tables inside `tables`             */
+  int hview;           /* vz_preprocess2: index of the horizontal view (image, tab_h) this tile reads */
 } vz_tile_desc;
+
+/* vz_preprocess2: one entry per distinct (image, horizontal table) pair.  Its horizontally resampled
+ * (and blended) rows live in the scratch buffer as RGBX u8x4 pixels [rows][out_w], first pixel at `offset`. */
+typedef struct {
+  int image;           /* index into the image array                                              */
+  int tab_h;           /* word offset of the horizontal axis table                                */
+  int out_w;           /* width after the horizontal pass                                         */
+  int rows;            /* rows of the canvas = rows of the intermediate                           */
+  long long offset;    /* in pixels                                                               */
+} vz_hview_desc;
 
 /* Axis table layout (int32 words), built on the host exactly like Pillow's precompute_coeffs
  * (Resample.c) for (in_size -> out_size):  [0]=ksize, [1]=out_size, then out_size words xmin,
@@ -172,6 +183,19 @@ int vz_preprocess(const vz_image_desc* images, int n_images, const vz_prim* prim
                   const vz_tile_desc* tiles, int n_tiles, const int32_t* tables,
                   const float* lut768, int out_mode, void* out, int max_src_w, int max_ksize,
                   void* stream);
+
+/* Same result as vz_preprocess, as TWO kernels (the form used whenever something is resampled): the
+ * horizontal pass (+ blend, + canvas padding) runs once per source row of every horizontal view into an
+ * RGBX intermediate in `scratch` (it stays in L2), the vertical pass + normalise + patchify reads only
+ * the taps it needs.  No source row is filtered twice (the fused kernel recomputes the horizontal
+ * pass 1.43x because neighbouring 14-row bands overlap).  scratch: device memory, scratch_pixels x 4
+ * bytes, >= the largest offset + rows * out_w of the views; max_span_px = the widest source window
+ * any 256 consecutive output columns of any view need (host-computed from the tables).            */
+int vz_preprocess2(const vz_image_desc* images, int n_images, const vz_prim* prims, int n_prims,
+                   const vz_hview_desc* hviews, int n_hviews, const vz_tile_desc* tiles, int n_tiles,
+                   const int32_t* tables, const float* lut768, int out_mode, void* out, void* scratch,
+                   long long scratch_pixels, int max_span_px, int max_rows, int max_out_w, int max_ksize,
+                   void* stream);
 
 /* f32/bf16 pixel_values [T,3,336,336] -> bf16 patches [T*576,592]; the API-compatible entry of
  * CLIPVisionTower.forward (vision_encoder/vision_encoder.py:80-117) when the caller already holds

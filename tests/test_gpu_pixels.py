@@ -141,3 +141,33 @@ def test_process_images_modes_bit_exact(mode, golden_dir):
             src = P.alpha_composite_rgb(src, ov)
         ref = P.normalize_lut(P.process_images_u8(src, mode)[None], lut)[0]
         assert np.array_equal(got[i][0].cpu().numpy(), ref), (mode, i)
+
+
+def test_two_kernel_and_fused_forms_agree(golden_dir, monkeypatch):
+    """vz_preprocess2 (horizontal pass into an RGBX intermediate, then vertical pass) == vz_preprocess (fused, one CTA
+    per band) bit for bit, on anyres + fixed-mode views with visual prompts, in both output layouts"""
+    import vision_zephyr_b200 as vz
+    from vision_zephyr_b200 import anyres
+    from vision_zephyr_b200.preprocess import build_plan, run_plan
+    lut = _lut(golden_dir)
+    sizes = [(1000, 900), (637, 336), (336, 900), (1344, 1344), (301, 640)]
+    imgs = [torch.from_numpy(synth_image(60 + i, w, h)).cuda() for i, (w, h) in enumerate(sizes)]
+    layer = np.zeros((900, 1000, 4), np.uint8)
+    layer[100:700, 50:900] = (20, 250, 30, 140)
+    prompts = [[vz.VisualPrompt("layer", layer=layer), vz.VisualPrompt("rectangle", rgba=(255, 0, 0, 255), bbox=(10, 20, 950, 800), width=5)]]
+    prompts += [[] for _ in sizes[1:]]
+    views, canvases = [], []
+    for i, (w, h) in enumerate(sizes):
+        if i < 4:
+            views.append(anyres.anyres_views((w, h), PINPOINTS_C3)[0]); canvases.append(None)
+        else:
+            v, c = anyres.fixed_view((w, h), "pad"); views.append(v); canvases.append(c)
+    plan = build_plan(imgs, views, lut, prompts, canvases)
+    assert plan.max_ksize > 1 and plan.n_hviews >= len(sizes)
+    for mode in ("patches", "chw"):
+        monkeypatch.delenv("VZ_PRE_FUSED", raising=False)
+        two = run_plan(plan, mode).clone()
+        monkeypatch.setenv("VZ_PRE_FUSED", "1")
+        fused = run_plan(plan, mode)
+        torch.cuda.synchronize()
+        assert torch.equal(two, fused), mode

@@ -394,6 +394,242 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PreArgs
   }
 }
 
+
+// ================================================================================================
+// Two-kernel form (vz_preprocess2): horizontal pass once per source row, vertical pass by gather.
+// ================================================================================================
+constexpr int HP_THREADS = 256;   // output columns of one horizontal-pass CTA
+constexpr int HP_ROWS = 8;        // source rows of one horizontal-pass CTA (they share the coefficient slice)
+
+struct HArgs {
+  const vz_image_desc* images;
+  const vz_prim* prims;
+  const vz_hview_desc* hviews;
+  const int32_t* tables;
+  uint32_t* scratch;
+  int row_buf_bytes;   // per source row (>= 3 * max span + tap overrun + phase, multiple of 16)
+  int max_ksize;
+};
+
+// Horizontal pass (+ visual-prompt blend, + canvas padding) of HP_ROWS canvas rows x 256 output columns
+// of one view: the rows' source windows are copied into shared memory with cp.async, blended in place,
+// then every thread filters its output pixel (3 channels) with the 4-taps-per-step loop of the fused
+// kernel and writes one RGBX word per row.
+__global__ void __launch_bounds__(HP_THREADS) preprocess_h_kernel(const HArgs a) {
+  extern __shared__ __align__(16) uint8_t pp_smem[];
+  const vz_hview_desc hv = a.hviews[blockIdx.z];
+  const int x0 = blockIdx.x * HP_THREADS, y0 = blockIdx.y * HP_ROWS, tid = threadIdx.x;
+  if (x0 >= hv.out_w || y0 >= hv.rows) return;
+  const vz_image_desc im = a.images[hv.image];
+  const int nrows = min(HP_ROWS, hv.rows - y0);
+  const int32_t* th = a.tables + hv.tab_h;
+  const int ksh = th[0];
+  const int32_t* h_min = th + 2;
+  const int32_t* h_cnt = h_min + hv.out_w;
+  const int32_t* h_kk = h_cnt + hv.out_w;
+  const int ksh4 = (ksh + 3) >> 2;
+  int4* s_hkk4 = reinterpret_cast<int4*>(pp_smem);                                   // [ksh4][256]
+  uint8_t* s_rows = pp_smem + (size_t)((a.max_ksize + 3) >> 2) * HP_THREADS * 16;     // [HP_ROWS][row_buf_bytes]
+  __shared__ vz_prim s_prims[MAX_PRIMS];
+  const int n_prims = im.prim_count < MAX_PRIMS ? im.prim_count : MAX_PRIMS;
+  for (int i = tid; i < n_prims; i += HP_THREADS) s_prims[i] = a.prims[im.prim_begin + i];
+
+  const int x = x0 + tid;
+  const bool valid = x < hv.out_w;
+  const int xl = min(x0 + HP_THREADS - 1, hv.out_w - 1);
+  const int sx0 = h_min[x0], sx1 = h_min[xl] + h_cnt[xl];      // canvas columns this CTA's outputs read
+  const int hx_min = valid ? h_min[x] : sx0;
+  for (int g = 0; g < ksh4; ++g) {
+    int c[4] = {0, 0, 0, 0};
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (4 * g + k < ksh) c[k] = h_kk[x * ksh + 4 * g + k];
+    }
+    s_hkk4[g * HP_THREADS + tid] = make_int4(c[0], c[1], c[2], c[3]);   // read back by this thread only
+  }
+  const uint8_t* img_end = im.src + (size_t)im.W * im.H * 3;
+  const int rx0 = max(sx0 - im.pad_x, 0), rx1 = min(sx1 - im.pad_x, im.W);
+  const bool needs_fill = (sx0 - im.pad_x < 0) || (sx1 - im.pad_x > im.W) || (y0 - im.pad_y < 0) ||
+                          (y0 + nrows - im.pad_y > im.H);
+  auto row_phase = [&](int sy) -> int {
+    const int yr = sy - im.pad_y;
+    if (yr < 0 || yr >= im.H || rx1 <= rx0) return 0;
+    const uintptr_t g = reinterpret_cast<uintptr_t>(im.src + ((size_t)yr * im.W + rx0) * 3);
+    return (int)((g - (uintptr_t)((rx0 + im.pad_x - sx0) * 3)) & 15);
+  };
+  // ---- all rows of the block in flight at once ----
+  for (int r = 0; r < nrows; ++r) {
+    const int sy = y0 + r, yr = sy - im.pad_y;
+    if (yr < 0 || yr >= im.H || rx1 <= rx0) continue;
+    const uint8_t* srow = im.src + ((size_t)yr * im.W + rx0) * 3;
+    const int a16 = (int)(reinterpret_cast<uintptr_t>(srow) & 15);
+    const uint8_t* g0 = srow - a16;
+    uint8_t* d0 = s_rows + r * a.row_buf_bytes + row_phase(sy) + (rx0 + im.pad_x - sx0) * 3 - a16;
+    const int nvec = ((rx1 - rx0) * 3 + a16 + 15) >> 4;
+    for (int i = tid; i < nvec; i += HP_THREADS) {
+      const uint8_t* g = g0 + 16 * i;
+      const long left = img_end - g;
+      cp_async_16_partial(d0 + 16 * i, g, left >= 16 ? 16 : (left > 0 ? (int)left : 0));
+    }
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  if (needs_fill || n_prims != 0) {
+    for (int r = 0; r < nrows; ++r) {
+      const int sy = y0 + r, yr = sy - im.pad_y;
+      const bool row_real = yr >= 0 && yr < im.H;
+      uint8_t* dst = s_rows + r * a.row_buf_bytes + row_phase(sy);
+      for (int px = tid; px < sx1 - sx0; px += HP_THREADS) {
+        const int xr = sx0 + px - im.pad_x;
+        uint8_t* q = dst + px * 3;
+        if (!(row_real && xr >= 0 && xr < im.W)) {      // canvas padding (expand2square)
+          q[0] = (uint8_t)(im.bg & 0xff); q[1] = (uint8_t)((im.bg >> 8) & 0xff); q[2] = (uint8_t)((im.bg >> 16) & 0xff);
+          continue;
+        }
+        if (n_prims == 0) continue;
+        int rr = q[0], gg = q[1], bb = q[2];
+        for (int pi = 0; pi < n_prims; ++pi) {
+          const vz_prim& p = s_prims[pi];
+          uint32_t ov;
+          if (p.type == VZ_PRIM_LAYER) {
+            ov = __ldg(reinterpret_cast<const uint32_t*>(im.layers) + ((size_t)p.layer * im.H + yr) * im.W + xr);
+          } else {
+            if (!rect_covers(p, xr, yr)) continue;
+            ov = p.rgba;
+          }
+          const int al = (int)(ov >> 24);
+          rr = blend_over(rr, (int)(ov & 0xff), al);
+          gg = blend_over(gg, (int)((ov >> 8) & 0xff), al);
+          bb = blend_over(bb, (int)((ov >> 16) & 0xff), al);
+        }
+        q[0] = (uint8_t)rr; q[1] = (uint8_t)gg; q[2] = (uint8_t)bb;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- horizontal filter ----
+  const int4* hk = s_hkk4 + tid;
+  uint32_t* orow = a.scratch + hv.offset + (size_t)y0 * hv.out_w + x;
+  for (int r = 0; r < nrows; ++r) {
+    const uint8_t* cur = s_rows + r * a.row_buf_bytes;
+    const int b0 = row_phase(y0 + r) + (hx_min - sx0) * 3;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(cur) + (b0 >> 2);
+    const uint32_t sh = (uint32_t)(b0 & 3) * 8u;
+    int s0 = 1 << (PREC - 1), s1 = s0, s2 = s0;
+    uint32_t w0 = wp[0];
+    for (int g = 0; g < ksh4; ++g) {
+      const uint32_t w1 = wp[3 * g + 1], w2 = wp[3 * g + 2], w3 = wp[3 * g + 3];
+      const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh);
+      const int4 c = hk[g * HP_THREADS];
+      s0 += byte_of<0>(a0) * c.x + byte_of<3>(a0) * c.y + byte_of<2>(a1) * c.z + byte_of<1>(a2) * c.w;
+      s1 += byte_of<1>(a0) * c.x + byte_of<0>(a1) * c.y + byte_of<3>(a1) * c.z + byte_of<2>(a2) * c.w;
+      s2 += byte_of<2>(a0) * c.x + byte_of<1>(a1) * c.y + byte_of<0>(a2) * c.z + byte_of<3>(a2) * c.w;
+      w0 = w3;
+    }
+    if (valid) orow[(size_t)r * hv.out_w] = (uint32_t)clip8(s0) | ((uint32_t)clip8(s1) << 8) | ((uint32_t)clip8(s2) << 16);
+  }
+}
+
+struct VArgs {
+  const vz_hview_desc* hviews;
+  const vz_tile_desc* tiles;
+  const int32_t* tables;
+  const float* lut;
+  const uint32_t* scratch;
+  void* out;
+  int out_mode;
+  int max_ksize;
+};
+
+// Vertical pass + LUT + im2col of one 14-row band of one tile: the thread of output pixel x gathers, for
+// each of the band's rows, exactly the taps of that row from the RGBX intermediate (coalesced 32-bit
+// loads, L1 / L2 resident), no staging, no barriers inside the loop.
+__global__ void __launch_bounds__(PP_THREADS) preprocess_v_kernel(const VArgs a) {
+  extern __shared__ __align__(16) uint8_t pp_smem[];
+  const int band = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
+  const vz_tile_desc td = a.tiles[t];
+  const vz_hview_desc hv = a.hviews[td.hview];
+  const int32_t* tv = a.tables + td.tab_v;
+  const int ksv = tv[0];
+  const int32_t* v_min = tv + 2;
+  const int32_t* v_cnt = v_min + td.out_h;
+  const int32_t* v_kk = v_cnt + td.out_h;
+  const int stage_bytes = (a.out_mode == VZ_OUT_CHW_F32) ? 3 * BAND * TILE * 4 : 24 * VZ_PATCH_K * 2;
+  uint8_t* s_stage = pp_smem;
+  int32_t* s_vkk = reinterpret_cast<int32_t*>(pp_smem + stage_bytes);   // [BAND][max_ksize]
+  int32_t* s_vmin = s_vkk + BAND * a.max_ksize;
+  int32_t* s_vcnt = s_vmin + BAND;
+  const int ry0 = td.tile_y + band * BAND - td.off_y;
+  if (tid < BAND) {
+    const int ry = ry0 + tid;
+    const bool ok = ry >= 0 && ry < td.out_h;
+    s_vmin[tid] = ok ? v_min[ry] : 0;
+    s_vcnt[tid] = ok ? v_cnt[ry] : 0;
+  }
+  for (int i = tid; i < BAND * ksv; i += PP_THREADS) {
+    const int y = i / ksv, k = i - y * ksv;
+    const int ry = ry0 + y;
+    s_vkk[y * a.max_ksize + k] = (ry >= 0 && ry < td.out_h) ? v_kk[ry * ksv + k] : 0;
+  }
+  if (a.out_mode == VZ_OUT_PATCHES_BF16) {
+    __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(s_stage);
+    for (int i = tid; i < 24 * 4; i += PP_THREADS) sp[(i >> 2) * VZ_PATCH_K + 588 + (i & 3)] = __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  const int x = tid;
+  const int rx = td.tile_x + x - td.off_x;
+  const bool col_ok = tid < TILE && rx >= 0 && rx < td.out_w;
+  const uint32_t* col = a.scratch + hv.offset + (col_ok ? rx : 0);
+  const int px = x / 14, kx = x - px * 14;
+#pragma unroll 2
+  for (int y = 0; y < BAND; ++y) {
+    const int cnt = col_ok ? s_vcnt[y] : 0;
+    const uint32_t* src = col + (size_t)s_vmin[y] * hv.out_w;
+    const int32_t* kk = s_vkk + y * a.max_ksize;
+    int a0 = 1 << (PREC - 1), a1 = a0, a2 = a0;
+    for (int k = 0; k < cnt; ++k) {
+      const uint32_t p = __ldg(src + (size_t)k * hv.out_w);
+      const int c = kk[k];
+      a0 += byte_of<0>(p) * c;
+      a1 += byte_of<1>(p) * c;
+      a2 += byte_of<2>(p) * c;
+    }
+    if (tid < TILE) {
+      const int v0 = cnt > 0 ? clip8(a0) : 0, v1 = cnt > 0 ? clip8(a1) : 0, v2 = cnt > 0 ? clip8(a2) : 0;
+      if (a.out_mode == VZ_OUT_PATCHES_BF16) {
+        __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(s_stage) + px * VZ_PATCH_K + y * 14 + kx;
+        sp[0] = __float2bfloat16_rn(a.lut[v0]);
+        sp[196] = __float2bfloat16_rn(a.lut[256 + v1]);
+        sp[392] = __float2bfloat16_rn(a.lut[512 + v2]);
+      } else {
+        float* sf = reinterpret_cast<float*>(s_stage) + y * TILE + x;   // [3][BAND][336]
+        sf[0] = a.lut[v0];
+        sf[BAND * TILE] = a.lut[256 + v1];
+        sf[2 * BAND * TILE] = a.lut[512 + v2];
+      }
+    }
+  }
+  __syncthreads();
+  if (a.out_mode == VZ_OUT_PATCHES_BF16) {
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) +
+                                          ((size_t)t * VZ_VIT_PATCHES + band * 24) * VZ_PATCH_K);
+    const uint4* s4 = reinterpret_cast<const uint4*>(s_stage);
+    for (int i = tid; i < 24 * VZ_PATCH_K * 2 / 16; i += PP_THREADS) dst[i] = s4[i];
+  } else {
+    const float* sf = reinterpret_cast<const float*>(s_stage);
+    float* o = reinterpret_cast<float*>(a.out);
+    for (int i = tid; i < 3 * BAND * TILE / 4; i += PP_THREADS) {
+      const int e = i * 4;
+      const int c = e / (BAND * TILE), rem = e - c * BAND * TILE;
+      const int y = rem / TILE, xx = rem - y * TILE;
+      *reinterpret_cast<float4*>(o + (((size_t)t * 3 + c) * TILE + band * BAND + y) * TILE + xx) =
+          *reinterpret_cast<const float4*>(sf + e);
+    }
+  }
+}
+
 }  // namespace
 }  // namespace vz
 
@@ -421,6 +657,45 @@ extern "C" int vz_preprocess(const vz_image_desc* images, int n_images, const vz
   VZ_ENSURE_DYN_SMEM(preprocess_kernel, 220 * 1024);
   dim3 grid(24, n_tiles);
   preprocess_kernel<<<grid, PP_THREADS, smem, st>>>(a);
+  VZ_LAUNCH_CHECK();
+  return VZ_OK;
+}
+
+extern "C" int vz_preprocess2(const vz_image_desc* images, int n_images, const vz_prim* prims, int n_prims,
+                              const vz_hview_desc* hviews, int n_hviews, const vz_tile_desc* tiles, int n_tiles,
+                              const int32_t* tables, const float* lut768, int out_mode, void* out, void* scratch,
+                              long long scratch_pixels, int max_span_px, int max_rows, int max_out_w, int max_ksize,
+                              void* stream) {
+  using namespace vz;
+  if (!images || !hviews || !tiles || !tables || !lut768 || !out || !scratch) return VZ_ERR_BAD_ARG;
+  if (n_images <= 0 || n_hviews <= 0 || n_tiles <= 0 || scratch_pixels <= 0) return VZ_ERR_BAD_ARG;
+  if (n_prims > 0 && !prims) return VZ_ERR_BAD_ARG;
+  if (out_mode != VZ_OUT_PATCHES_BF16 && out_mode != VZ_OUT_CHW_F32) return VZ_ERR_BAD_ARG;
+  if (max_span_px <= 0 || max_rows <= 0 || max_out_w <= 0 || max_ksize <= 0 || !aligned16(out) || !aligned16(scratch))
+    return VZ_ERR_BAD_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // ---- horizontal pass ----
+  HArgs h;
+  h.images = images; h.prims = prims; h.hviews = hviews; h.tables = tables;
+  h.scratch = reinterpret_cast<uint32_t*>(scratch);
+  h.row_buf_bytes = ((max_span_px * 3 + 3 * max_ksize + 48 + 15) / 16) * 16;   // + phase + tap overrun slack
+  h.max_ksize = max_ksize;
+  const size_t smem_h = (size_t)((max_ksize + 3) / 4) * HP_THREADS * 16 + (size_t)HP_ROWS * h.row_buf_bytes;
+  if (smem_h > 200 * 1024) return VZ_ERR_UNSUPPORTED;
+  VZ_ENSURE_DYN_SMEM(preprocess_h_kernel, 200 * 1024);
+  dim3 grid_h((max_out_w + HP_THREADS - 1) / HP_THREADS, (max_rows + HP_ROWS - 1) / HP_ROWS, n_hviews);
+  preprocess_h_kernel<<<grid_h, HP_THREADS, smem_h, st>>>(h);
+  VZ_LAUNCH_CHECK();
+  // ---- vertical pass + normalise + patchify ----
+  VArgs v;
+  v.hviews = hviews; v.tiles = tiles; v.tables = tables; v.lut = lut768;
+  v.scratch = reinterpret_cast<const uint32_t*>(scratch); v.out = out; v.out_mode = out_mode; v.max_ksize = max_ksize;
+  const int stage_bytes = (out_mode == VZ_OUT_CHW_F32) ? 3 * BAND * TILE * 4 : 24 * VZ_PATCH_K * 2;
+  const size_t smem_v = (size_t)stage_bytes + (size_t)BAND * max_ksize * 4 + 2 * BAND * 4 + 16;
+  if (smem_v > 200 * 1024) return VZ_ERR_UNSUPPORTED;
+  VZ_ENSURE_DYN_SMEM(preprocess_v_kernel, 200 * 1024);
+  dim3 grid_v(24, n_tiles);
+  preprocess_v_kernel<<<grid_v, PP_THREADS, smem_v, st>>>(v);
   VZ_LAUNCH_CHECK();
   return VZ_OK;
 }

@@ -10,14 +10,16 @@ descriptor tables (tile geometry, LANCZOS coefficients) and moves them to the de
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
+from functools import lru_cache
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
 
 from . import _lib
-from .anyres import TILE, TablePool, anyres_views, single_view, fixed_view
+from .anyres import TILE, TablePool, anyres_views, fixed_view, resample_table, single_view
 
 OPENAI_CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 OPENAI_CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
@@ -86,6 +88,14 @@ class PreprocessPlan:
     keep: list = field(default_factory=list)  # tensors that must outlive the launch
     h2d_bytes: int = 0
     algorithmic_bytes: int = 0
+    # two-kernel form (vz_preprocess2): one horizontal view per distinct (image, horizontal table)
+    hviews_dev: Optional[torch.Tensor] = None
+    n_hviews: int = 0
+    scratch_pixels: int = 0
+    max_span_px: int = 1
+    max_rows: int = 1
+    max_out_w: int = 1
+    scratch: Optional[torch.Tensor] = None
 
 
 def _struct_array_to_dev(arr, device) -> torch.Tensor:
@@ -106,6 +116,7 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
     prim_list, tile_list, keep = [], [], []
     tiles_per_image, sizes = [], []
     max_w, algo = 1, 0
+    hview_index, hview_list, scratch_px, max_span, max_rows, max_out_w = {}, [], 0, 1, 1, 1
     for i, im in enumerate(images):
         if im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3 or not im.is_cuda:
             raise ValueError("images must be uint8 CUDA tensors of shape [H, W, 3]")
@@ -164,8 +175,19 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
             t.out_w, t.out_h = v["out_w"], v["out_h"]
             t.off_x, t.off_y = v["off_x"], v["off_y"]
             t.tile_x, t.tile_y = v["tile_x"], v["tile_y"]
-            t.tab_h = pool.offset(cW, v["out_w"], v.get("filt", "lanczos"))
-            t.tab_v = pool.offset(cH, v["out_h"], v.get("filt", "lanczos"))
+            filt = v.get("filt", "lanczos")
+            t.tab_h = pool.offset(cW, v["out_w"], filt)
+            t.tab_v = pool.offset(cH, v["out_h"], filt)
+            hk = (i, t.tab_h)
+            if hk not in hview_index:
+                hview_index[hk] = len(hview_list)
+                hvd = _lib.HViewDesc()
+                hvd.image, hvd.tab_h, hvd.out_w, hvd.rows, hvd.offset = i, t.tab_h, v["out_w"], cH, scratch_px
+                hview_list.append(hvd)
+                scratch_px += cH * v["out_w"]
+                max_span = max(max_span, _max_span(cW, v["out_w"], filt))
+                max_rows, max_out_w = max(max_rows, cH), max(max_out_w, v["out_w"])
+            t.hview = hview_index[hk]
             tile_list.append(t)
     n_tiles = len(tile_list)
     tile_arr = (_lib.TileDesc * n_tiles)(*tile_list)
@@ -179,14 +201,34 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
         tables_dev=torch.from_numpy(tables).to(device, non_blocking=True),
         lut_dev=torch.from_numpy(np.ascontiguousarray(lut, np.float32)).to(device, non_blocking=True),
         n_images=n_img, n_prims=len(prim_list), max_src_w=max_w, max_ksize=pool.max_ksize, keep=keep)
-    plan.h2d_bytes = (plan.images_dev.numel() + plan.tiles_dev.numel() + plan.tables_dev.numel() * 4 +
+    hview_arr = (_lib.HViewDesc * len(hview_list))(*hview_list)
+    plan.hviews_dev = _struct_array_to_dev(hview_arr, device)
+    plan.n_hviews, plan.scratch_pixels = len(hview_list), scratch_px
+    plan.max_span_px, plan.max_rows, plan.max_out_w = max_span, max_rows, max_out_w
+    plan.h2d_bytes = (plan.images_dev.numel() + plan.tiles_dev.numel() + plan.tables_dev.numel() * 4 + plan.hviews_dev.numel() +
                       (plan.prims_dev.numel() if plan.prims_dev is not None else 0) + 768 * 4)
     plan.algorithmic_bytes = algo
     return plan
 
 
+@lru_cache(maxsize=512)
+def _max_span(in_size: int, out_size: int, filt: str) -> int:
+    """widest source window (in pixels) that 256 consecutive output columns of an axis table read"""
+    t = resample_table(in_size, out_size, filt)
+    n = int(t[1])
+    xmin, cnt = t[2:2 + n], t[2 + n:2 + 2 * n]
+    span = 1
+    for x0 in range(0, n, 256):
+        xl = min(x0 + 255, n - 1)
+        span = max(span, int(xmin[xl] + cnt[xl] - xmin[x0]))
+    return span
+
+
 def run_plan(plan: PreprocessPlan, out_mode: str = "patches", out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Launch vz_preprocess.  out_mode 'patches' -> bf16 [T*576, 592]; 'chw' -> f32 [T,3,336,336]."""
+    """Launch the preprocess kernels.  out_mode 'patches' -> bf16 [T*576, 592]; 'chw' -> f32 [T,3,336,336].
+    Plans that resample anything take the two-kernel form (vz_preprocess2: horizontal pass once per source row
+    into an RGBX intermediate, then vertical pass + normalise + patchify); plans made of identity views only
+    (fixed-336 inputs) and VZ_PRE_FUSED=1 take the fused kernel (vz_preprocess)."""
     lib = _lib.load()
     dev = plan.tiles_dev.device
     T = plan.n_tiles
@@ -200,6 +242,16 @@ def run_plan(plan: PreprocessPlan, out_mode: str = "patches", out: Optional[torc
         mode = _lib.OUT_CHW_F32
     else:
         raise ValueError(out_mode)
+    if plan.max_ksize > 1 and os.environ.get("VZ_PRE_FUSED") != "1":
+        if plan.scratch is None or plan.scratch.numel() < plan.scratch_pixels:
+            plan.scratch = torch.empty(plan.scratch_pixels, dtype=torch.int32, device=dev)
+        st = lib.vz_preprocess2(_lib.ptr(plan.images_dev), plan.n_images, _lib.ptr(plan.prims_dev), plan.n_prims,
+                                _lib.ptr(plan.hviews_dev), plan.n_hviews, _lib.ptr(plan.tiles_dev), T,
+                                _lib.ptr(plan.tables_dev), _lib.ptr(plan.lut_dev), mode, _lib.ptr(out),
+                                _lib.ptr(plan.scratch), plan.scratch_pixels, plan.max_span_px, plan.max_rows,
+                                plan.max_out_w, plan.max_ksize, _lib.stream_ptr())
+        _lib.check(st, "vz_preprocess2")
+        return out
     st = lib.vz_preprocess(_lib.ptr(plan.images_dev), plan.n_images, _lib.ptr(plan.prims_dev), plan.n_prims,
                            _lib.ptr(plan.tiles_dev), T, _lib.ptr(plan.tables_dev), _lib.ptr(plan.lut_dev),
                            mode, _lib.ptr(out), plan.max_src_w, plan.max_ksize, _lib.stream_ptr())
