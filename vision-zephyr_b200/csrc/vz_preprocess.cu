@@ -458,6 +458,10 @@ __global__ void __launch_bounds__(HP_THREADS) preprocess_h_kernel(const HArgs a)
     const uintptr_t g = reinterpret_cast<uintptr_t>(im.src + ((size_t)yr * im.W + rx0) * 3);
     return (int)((g - (uintptr_t)((rx0 + im.pad_x - sx0) * 3)) & 15);
   };
+  // where canvas column sx0 of each row sits in its buffer (computed once, read by everybody)
+  __shared__ int s_phase[HP_ROWS];
+  if (tid < HP_ROWS) s_phase[tid] = tid < nrows ? row_phase(y0 + tid) : 0;
+  __syncthreads();
   // ---- all rows of the block in flight at once ----
   for (int r = 0; r < nrows; ++r) {
     const int sy = y0 + r, yr = sy - im.pad_y;
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(HP_THREADS) preprocess_h_kernel(const HArgs a)
     const uint8_t* srow = im.src + ((size_t)yr * im.W + rx0) * 3;
     const int a16 = (int)(reinterpret_cast<uintptr_t>(srow) & 15);
     const uint8_t* g0 = srow - a16;
-    uint8_t* d0 = s_rows + r * a.row_buf_bytes + row_phase(sy) + (rx0 + im.pad_x - sx0) * 3 - a16;
+    uint8_t* d0 = s_rows + r * a.row_buf_bytes + s_phase[r] + (rx0 + im.pad_x - sx0) * 3 - a16;
     const int nvec = ((rx1 - rx0) * 3 + a16 + 15) >> 4;
     for (int i = tid; i < nvec; i += HP_THREADS) {
       const uint8_t* g = g0 + 16 * i;
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(HP_THREADS) preprocess_h_kernel(const HArgs a)
     for (int r = 0; r < nrows; ++r) {
       const int sy = y0 + r, yr = sy - im.pad_y;
       const bool row_real = yr >= 0 && yr < im.H;
-      uint8_t* dst = s_rows + r * a.row_buf_bytes + row_phase(sy);
+      uint8_t* dst = s_rows + r * a.row_buf_bytes + s_phase[r];
       for (int px = tid; px < sx1 - sx0; px += HP_THREADS) {
         const int xr = sx0 + px - im.pad_x;
         uint8_t* q = dst + px * 3;
@@ -512,9 +516,10 @@ __global__ void __launch_bounds__(HP_THREADS) preprocess_h_kernel(const HArgs a)
   // ---- horizontal filter ----
   const int4* hk = s_hkk4 + tid;
   uint32_t* orow = a.scratch + hv.offset + (size_t)y0 * hv.out_w + x;
-  for (int r = 0; r < nrows; ++r) {
+  const int tap0 = (hx_min - sx0) * 3;
+  for (int r = 0; r < nrows; ++r, orow += hv.out_w) {
     const uint8_t* cur = s_rows + r * a.row_buf_bytes;
-    const int b0 = row_phase(y0 + r) + (hx_min - sx0) * 3;
+    const int b0 = s_phase[r] + tap0;
     const uint32_t* wp = reinterpret_cast<const uint32_t*>(cur) + (b0 >> 2);
     const uint32_t sh = (uint32_t)(b0 & 3) * 8u;
     int s0 = 1 << (PREC - 1), s1 = s0, s2 = s0;
@@ -528,7 +533,7 @@ __global__ void __launch_bounds__(HP_THREADS) preprocess_h_kernel(const HArgs a)
       s2 += byte_of<2>(a0) * c.x + byte_of<1>(a1) * c.y + byte_of<0>(a2) * c.z + byte_of<3>(a2) * c.w;
       w0 = w3;
     }
-    if (valid) orow[(size_t)r * hv.out_w] = (uint32_t)clip8(s0) | ((uint32_t)clip8(s1) << 8) | ((uint32_t)clip8(s2) << 16);
+    if (valid) *orow = (uint32_t)clip8(s0) | ((uint32_t)clip8(s1) << 8) | ((uint32_t)clip8(s2) << 16);
   }
 }
 
