@@ -13,7 +13,7 @@ echo "reference arm exit $?"; tail -1 gpurun_out/bench_ref.log | cut -c1-400
 echo "hbm bench exit $?"; cat gpurun_out/hbm_kernels.log | tail -4
 ( timeout 300 python tools/attn_bench.py ) > gpurun_out/attn_bench.log 2>&1; grep impl gpurun_out/attn_bench.log
 ( timeout 300 python tools/gemm_bench.py ) > gpurun_out/gemm_bench.log 2>&1; cat gpurun_out/gemm_bench.log
-KREGEX='regex:^(gemm_bf16|layernorm_kernel|fuse_kernel|cls_rows|gather_rows|patchify|vit_attn|qattn32|preprocess_kernel|splice_|text_|merge_rows|softmax_rows|row_stats|collate)'
+KREGEX='regex:^(gemm_bf16|layernorm_kernel|fuse_kernel|cls_rows|gather_rows|patchify|vit_attn|qattn32|preprocess_|splice_|text_|merge_rows|softmax_rows|row_stats|collate)'
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 4000 --csv \
     --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
@@ -24,6 +24,6 @@ echo "gemm capture exit $?"
 ncu --set full --clock-control none --import-source on -k regex:vit_attn_tc -s 5 -c 1 \
     -f -o gpurun_out/prof_attn_v9 $CMD > gpurun_out/ncu_full_attn.log 2>&1
 echo "attn capture exit $?"
-ncu --set full --clock-control none -k "regex:^(preprocess_kernel|fuse_kernel|splice_scatter)" -s 3 -c 3 \
+ncu --set full --clock-control none -k "regex:^(preprocess_|fuse_kernel|splice_scatter)" -s 4 -c 4 \
     -f -o gpurun_out/prof_hbm_v9 $CMD > gpurun_out/ncu_full_hbm.log 2>&1
 echo "hbm capture exit $?"
