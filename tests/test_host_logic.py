@@ -68,6 +68,22 @@ def test_fixed_view_geometry():
         anyres.fixed_view((10, 10), "identity")
 
 
+def test_max_span_covers_every_256_column_block():
+    """the horizontal-pass kernel sizes its row buffers from preprocess._max_span: it must bound the source window
+    of any 256 consecutive output columns, including the taps of every column inside the block"""
+    from vision_zephyr_b200.preprocess import _max_span
+    for n_in, n_out, filt in [(1000, 672, "lanczos"), (1344, 336, "lanczos"), (700, 470, "bicubic"), (200, 448, "bicubic"),
+                              (336, 336, "lanczos"), (301, 1008, "lanczos")]:
+        t = anyres.resample_table(n_in, n_out, filt)
+        n = int(t[1])
+        xmin, cnt = t[2:2 + n], t[2 + n:2 + 2 * n]
+        span = _max_span(n_in, n_out, filt)
+        for x0 in range(0, n, 256):
+            xs = np.arange(x0, min(x0 + 256, n))
+            assert int((xmin[xs] + cnt[xs]).max() - xmin[x0]) <= span
+            assert (xmin[xs] >= xmin[x0]).all()
+
+
 def test_merged_row_counts_match_reference(golden_dir):
     g = np.load(f"{golden_dir}/golden_merge.npz")
     for c in range(10):
