@@ -4,23 +4,29 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
 
-Workload (config.workload = "c3_anyres_b8"): per GPU, 8 synthetic RGB images (sizes that all select
-the 672x672 pinpoint -> 1 global + 2x2 tiles = 5 tiles each, 40 tiles), 64-token prompts with one
-<image> placeholder, random-init CLIP ViT-L/14-336 + Q-Former + 32000x4096 embedding table, 'flat'
-merge.  N GPUs = N such shards (weak scaling, BASELINE config 4 at N=8): every rank encodes its 8
-images, ONE all-gather moves the projected visual tokens, rank 0 splices the global batch.
+Main workload (config.workload = "c3_anyres_b8", BASELINE configs 3 / 4): per GPU, 8 synthetic RGB images
+(sizes that all select the 672x672 pinpoint -> 1 global + 2x2 tiles = 5 tiles each, 40 tiles), 64-token
+prompts with one <image> placeholder, random-init CLIP ViT-L/14-336 + Q-Former + 32000x4096 embedding table,
+'flat' merge.  N GPUs = N such shards (weak scaling): every rank encodes its 8 images, ONE exchange step moves
+the projected visual tokens to rank 0, which splices the global batch.
 
-A step = preprocess kernel -> ViT -> fusion -> Q-Former -> (all-gather) -> plan/gather/scatter.
+A step = preprocess kernels -> ViT -> fusion -> Q-Former -> (exchange) -> plan / gather / scatter.
 `value`   : device-resident inputs (u8 images + ids already in HBM), CUDA-event timed, max over ranks.
 `e2e`     : same metric through the public API with HOST buffers: pinned u8 images + ids copied H2D,
             descriptor tables rebuilt, outputs copied D2H, all inside the timed region.
-`roofline`: the tcgen05 GEMM kernel (dominant), FLOPs = 2MNK per launch, CUDA events on its stream.
+`roofline`: the tcgen05 GEMM kernel (dominant), FLOPs = 2MNK per launch, CUDA events on its stream;
+`roofline_extra`: the other kernel families of the step, measured the same way in the same pass.
 `cpu_baseline`: the fp32 oracle port of the reference algorithm on the host cores, bounded sample.
+`parity_ok` / `config.transport` (N > 1): every rank's projected rows, checksummed locally, are found
+            bit-for-bit in rank 0's spliced output, on both transports (outside the timed region).
+At N = 1 the same JSON line also carries `workloads` (BASELINE config 1 = single-image latency, config 5 =
+S <= 2048 prompts spliced and prefilled through a random-init 32-layer Mistral-7B) and `eager_bf16` (the
+reference's own formulation under PyTorch eager bf16 on this GPU: the real bar).  `--workload c5_prefill_b8`
+or `--workload c1_latency` make one of those the main line instead.
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -34,8 +40,8 @@ sys.path.insert(0, ROOT)
 PINPOINTS = [[336, 672], [672, 336], [672, 672], [336, 1008], [1008, 336]]
 IMAGE_SIZES = [(1000, 900), (900, 1000), (1344, 1344), (700, 650), (1000, 900), (800, 760), (1200, 1100), (672, 672)]
 IMAGES_PER_GPU, TILES_PER_IMAGE, SEQ = 8, 5, 64
-GFLOP_PER_TILE = 856.9  # ViT 381.918 + projector 474.997 (L-independent part)
-
+METRIC = "anyres images/sec (ViT-L/14-336 + Q-Former)"
+WEIGHT_BYTES = 2 * (303_507_456 - 1024 * 768 - 2 * 1024 + 1_678_428_160)   # bf16 CLIP (no projection head) + Q-Former
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full
 # capture of this same command (mean over the four ViT GEMM shapes: 249.9, 293.4, 207.5, 117.0 MB)
@@ -47,6 +53,18 @@ def peaks():
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
     except Exception:
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def workload_config(workload):
+    """the static description of a workload: identical in the b200 arm and the reference arm"""
+    if workload == "c3_anyres_b8":
+        return {"workload": "c3_anyres_b8", "images_per_gpu": IMAGES_PER_GPU, "tiles_per_image": TILES_PER_IMAGE,
+                "seq_len": SEQ, "merge": "flat"}
+    if workload == "c5_prefill_b8":
+        return {"workload": "c5_prefill_b8", "images_per_gpu": IMAGES_PER_GPU, "tiles_per_image": TILES_PER_IMAGE,
+                "seq_len": "U[256,2047] per sample, right-padded", "merge": "flat",
+                "llm": "Mistral-7B geometry, 32 layers, random init (HF sdpa)"}
+    return {"workload": "c1_latency", "images_per_gpu": 1, "tiles_per_image": 1, "seq_len": SEQ, "merge": "flat"}
 
 
 class ClockSampler:
@@ -132,6 +150,24 @@ def make_ids(n_samples):
     return ids
 
 
+def make_c5_text(n_samples):
+    """S_i ~ U[256,2047], tokens U[3,31999], one -200 at U[1,32], right-padded with pad id 2,
+    attention_mask = ids != 2 (as the collator, train/train.py:692), labels = ids with the first third -100."""
+    g = torch.Generator().manual_seed(5)
+    lens = torch.randint(256, 2048, (n_samples,), generator=g)
+    S = int(lens.max())
+    ids = torch.full((n_samples, S), 2, dtype=torch.long)
+    labels = torch.full((n_samples, S), -100, dtype=torch.long)
+    for b in range(n_samples):
+        n = int(lens[b])
+        ids[b, :n] = torch.randint(3, 32000, (n,), generator=g)
+        ids[b, int(torch.randint(1, 33, (1,), generator=g))] = -200
+        labels[b, :n] = ids[b, :n]
+        labels[b, :n // 3] = -100
+    mask = (ids != 2).long()
+    return ids, mask, labels, [int(x) for x in lens]
+
+
 # ------------------------------------------------------------------------------------------------
 def run_reference_arm(args):
     """The reference's algorithm on the box's host cores: the pinned fp32 oracle port (the reference
@@ -171,15 +207,194 @@ def run_reference_arm(args):
         one_image(imgs[i % len(imgs)])
     dt = time.perf_counter() - t0
     value = steps / dt
-    line = {"impl": "reference", "metric": "anyres images/sec (ViT-L/14-336 + Q-Former)", "value": value,
+    line = {"impl": "reference", "metric": METRIC, "value": value,
             "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
             "ms_per_step": 1000 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "c3_anyres_b8", "sample": "1 image (5 tiles) per step", "seq_len": SEQ},
+            "config": workload_config("c3_anyres_b8"),
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"{steps} timed steps x 1 anyres image (5 tiles, 63 text tokens), fp32 torch oracle"},
+                             "sample": f"{steps} timed steps x 1 anyres image of the workload's 8 (5 tiles, 63 text tokens), "
+                                       "fp32 torch oracle; a rate, so comparable with the 8-image step"},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def event_time(fn, steps, warmup=3, flush=None):
+    """mean ms per call over `steps` calls (CUDA events on the current stream, sync on both sides)"""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+    ts = []
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def bench_c1_latency(path, lut, dev, steps):
+    """BASELINE config 1: ONE 336x336 image, 64-token prompt, through the public API, inputs in HBM.
+    Weight-streaming bound: one tile touches all 3.97 GB of bf16 weights once."""
+    import vision_zephyr_b200 as vz
+    pk, _ = peaks()
+    img = torch.from_numpy(np.random.default_rng(0).integers(0, 256, (336, 336, 3), dtype=np.uint8)).to(dev)
+    ids = make_ids(1).to(dev)
+
+    def call():
+        pb = vz.process_fixed_images([img], lut, out_mode="patches")
+        return path.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, pb, [(336, 336)])[4]
+
+    ms = event_time(call, max(steps, 20), warmup=5)
+    out = call()
+    assert out.shape == (1, SEQ - 1 + 32, 4096)
+    gbs = WEIGHT_BYTES / (ms * 1e-3) / 1e9
+    return {"ms_per_image": ms, "images_per_s": 1000.0 / ms,
+            "roofline": {"bound": "hbm", "what": "bf16 weights streamed once per call (ViT 0.61 GB + Q-Former 3.36 GB)",
+                         "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                         "floor_ms": WEIGHT_BYTES / pk["hbm_gbs"] / 1e6},
+            "config": workload_config("c1_latency")}
+
+
+def bench_c5(dev, lut, steps, llm_layers=32):
+    """BASELINE config 5: C3's 8 anyres images + prompts of S_i ~ U[256,2047] tokens, spliced and handed to a
+    random-init Mistral-7B-geometry LLM THROUGH the reference-shaped caller (VisZephyrB200ForCausalLM.forward ->
+    prepare_inputs_labels_for_multimodal -> MistralForCausalLM.forward(inputs_embeds=...))."""
+    import vision_zephyr_b200 as vz
+    from vision_zephyr_b200.language_model import VisZephyrB200ForCausalLM, random_mistral_config
+    from vision_zephyr_b200.runtime import random_init_
+    from vision_zephyr_b200 import _lib
+    pk, _ = peaks()
+    cfg = random_mistral_config(num_hidden_layers=llm_layers)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    t0 = time.time()
+    try:
+        with torch.device(dev):
+            model = VisZephyrB200ForCausalLM(cfg)
+    finally:
+        torch.set_default_dtype(old)
+    model.eval().requires_grad_(False)
+    random_init_(model, seed=0)
+    build_s = time.time() - t0
+    imgs = [torch.from_numpy(x).to(dev) for x in make_inputs(0)]
+    sizes = [IMAGE_SIZES[i % len(IMAGE_SIZES)] for i in range(IMAGES_PER_GPU)]
+    ids, mask, labels, lens = make_c5_text(IMAGES_PER_GPU)
+    ids, mask, labels = ids.to(dev), mask.to(dev), labels.to(dev)
+    pb = vz.process_any_resolution_images(imgs, PINPOINTS, lut, out_mode="patches")
+
+    def path_only():
+        pbi = vz.process_any_resolution_images(imgs, PINPOINTS, lut, out_mode="patches")
+        return model.prepare_inputs_labels_for_multimodal(ids, None, mask, None, labels, pbi, sizes)
+
+    lib = _lib.load()
+    with torch.no_grad():
+        r = path_only()
+        B, Lmax = r[4].shape[:2]
+        real = int(r[2].sum())
+        assert B == IMAGES_PER_GPU and Lmax == max(lens) - 1 + TILES_PER_IMAGE * 32 and torch.isfinite(r[4].float()).all()
+        l0 = lib.vz_kernel_launches()
+        ms_path = event_time(path_only, steps, warmup=3)
+        launches = int(lib.vz_kernel_launches() - l0) // (steps + 3)
+
+        def prefill():
+            return model(input_ids=ids, attention_mask=mask, images=pb, images_size=sizes, use_cache=False, logits_to_keep=1)
+
+        def llm_only():
+            return model(inputs_embeds=r[4], attention_mask=r[2], use_cache=False, logits_to_keep=1)
+
+        out = prefill()
+        assert out.logits.shape[0] == B and torch.isfinite(out.logits.float()).all()
+        ms_total = event_time(prefill, max(3, steps // 4), warmup=1)
+        ms_llm = event_time(llm_only, max(3, steps // 4), warmup=1)
+    # the scatter alone at this geometry (HBM-bound): bytes = SURVEY 8(d)(4)
+    from vision_zephyr_b200 import arch
+    ctx = model._plan_splice(ids, mask, labels, [TILES_PER_IMAGE] * B, sizes)
+    info = model._plan_info(ctx)
+    vis = torch.randn((B * TILES_PER_IMAGE * 32, 4096), device=dev).to(torch.bfloat16)
+    embed = model.get_model().embed_tokens.weight
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def scatter():
+        return arch.splice_scatter(ctx["ids"], ctx["labels"], embed, vis, None, ctx["slots"], ctx["prefix"], B,
+                                   ctx["total_vis_rows"], ctx["plan"], info["Lmax"], False)
+
+    lib.vz_profile(1)
+    for _ in range(10):
+        flush.zero_()
+        scatter()
+    prof = _lib.profile_read()
+    lib.vz_profile(0)
+    n_sc, ms_sc, _ = prof["splice_scatter"]
+    S = ids.shape[1]
+    sc_bytes = sum(info["lengths"]) * 8192 + B * info["Lmax"] * 8192 + 17 * B * S + 24 * B * info["Lmax"]
+    sc_gbs = sc_bytes / (ms_sc / n_sc * 1e-3) / 1e9
+    del model, flush
+    torch.cuda.empty_cache()
+    return {"path_ms_per_step": ms_path, "path_images_per_s": B / ms_path * 1e3,
+            "prefill_ms_total": ms_total, "llm_only_ms": ms_llm, "path_share_of_prefill": ms_path / ms_total,
+            "spliced_tokens": real, "padded_tokens": B * Lmax, "prefill_tokens_per_s": real / ms_total * 1e3,
+            "Lmax": Lmax, "L_text": max(lens) - 1, "text_lens": lens, "gpu_launches_per_step": launches,
+            "llm_build_s": build_s,
+            "splice_scatter": {"bound": "hbm", "achieved": sc_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                               "frac": sc_gbs / pk["hbm_gbs"], "bytes": sc_bytes, "us": ms_sc / n_sc * 1e3,
+                               "l2": "512 MB flush between launches"},
+            "config": workload_config("c5_prefill_b8"),
+            "how": "VisZephyrB200ForCausalLM.forward(input_ids, attention_mask, images, images_size, logits_to_keep=1): "
+                   "B200 path + HF Mistral (sdpa, bf16); inputs resident in HBM"}
+
+
+def bench_eager_bf16(path, dev, steps):
+    """The reference's own formulation (oracle/model.py = its modules restated) under PyTorch eager bf16 on this
+    GPU: cuBLAS + ATen, K/V projections and all 32 + L rows included, on the main workload's shapes (40 tiles,
+    L = 63).  ViT + fusion + Q-Former only (no preprocess / splice), i.e. a lower bound on the reference's step."""
+    from oracle import model as M
+    T, L = IMAGES_PER_GPU * TILES_PER_IMAGE, SEQ - 1
+    P = path.model.vision_tower._packed
+    one = lambda n: torch.ones(n, device=dev, dtype=torch.bfloat16)
+    zero = lambda n: torch.zeros(n, device=dev, dtype=torch.bfloat16)
+    p = "vision_model."
+    clip = {p + "embeddings.class_embedding": P["class_emb"],
+            p + "embeddings.patch_embedding.weight": P["patch_w"][:, :588].reshape(1024, 3, 14, 14).contiguous(),
+            p + "embeddings.position_embedding.weight": P["pos_emb"],
+            p + "pre_layrnorm.weight": P["pre_ln_g"].bfloat16(), p + "pre_layrnorm.bias": P["pre_ln_b"].bfloat16()}
+    for l in range(24):
+        q = f"{p}encoder.layers.{l}."
+        wq, wk, wv = P[f"{l}.w_qkv"].split(1024, 0)
+        bq, bk, bv = P[f"{l}.b_qkv"].bfloat16().split(1024, 0)
+        # (the packed weights have the LayerNorm affine folded in; timing only needs the shapes)
+        clip.update({q + "self_attn.q_proj.weight": wq, q + "self_attn.k_proj.weight": wk, q + "self_attn.v_proj.weight": wv,
+                     q + "self_attn.q_proj.bias": bq, q + "self_attn.k_proj.bias": bk, q + "self_attn.v_proj.bias": bv,
+                     q + "self_attn.out_proj.weight": P[f"{l}.w_o"], q + "self_attn.out_proj.bias": P[f"{l}.b_o"].bfloat16(),
+                     q + "layer_norm1.weight": one(1024), q + "layer_norm1.bias": zero(1024),
+                     q + "layer_norm2.weight": one(1024), q + "layer_norm2.bias": zero(1024),
+                     q + "mlp.fc1.weight": P[f"{l}.w_fc1"], q + "mlp.fc1.bias": P[f"{l}.b_fc1"].bfloat16(),
+                     q + "mlp.fc2.weight": P[f"{l}.w_fc2"], q + "mlp.fc2.bias": P[f"{l}.b_fc2"].bfloat16()})
+    qf = {k: v.detach() for k, v in path.model.mm_projector.state_dict().items()}
+    px = torch.randn((T, 3, 336, 336), device=dev, dtype=torch.bfloat16)
+    text = (torch.randn((T, L, 4096), device=dev) * 0.02).to(torch.bfloat16)
+
+    def step():
+        with torch.no_grad():
+            return M.encode_images(clip, qf, px, text)
+
+    ms = event_time(step, max(5, steps // 2), warmup=3)
+    return {"value": IMAGES_PER_GPU / ms * 1e3, "unit": "images/s", "ms_per_step": ms,
+            "what": "reference formulation (oracle/model.py) under PyTorch eager bf16 on this GPU, ViT + fusion + Q-Former "
+                    "of the main workload (40 tiles, L = 63); preprocess and splice not included"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -189,12 +404,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3_anyres_b8", choices=["c3_anyres_b8", "c5_prefill_b8", "c1_latency"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c1 / c5 / eager-bf16 side measurements at N = 1")
+    ap.add_argument("--llm-layers", type=int, default=32)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    import ctypes as C
     import torch.distributed as dist
     import vision_zephyr_b200 as vz
     from vision_zephyr_b200 import _lib
@@ -209,9 +428,33 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    lut = vz.clip_lut()
+    pk, pk_kind = peaks()
+
+    # ---- side workloads as the main line ------------------------------------------------------------
+    if args.workload != "c3_anyres_b8":
+        if world > 1:
+            raise SystemExit("--workload c5_prefill_b8 / c1_latency are single-GPU measurements")
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        sampler.mark_begin()
+        if args.workload == "c1_latency":
+            path = random_init_(VisionEmbeddingPath(device=dev), seed=0)
+            r = bench_c1_latency(path, lut, dev, args.steps)
+            value, ms_step, roof = r["images_per_s"], r["ms_per_image"], r["roofline"]
+        else:
+            r = bench_c5(dev, lut, args.steps, args.llm_layers)
+            value, ms_step = r["path_images_per_s"], r["path_ms_per_step"]
+            roof = r["splice_scatter"]
+        sampler.mark_end()
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": 1, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": r["config"], "detail": r,
+                "roofline": roof, "clocks": sampler.stop()}
+        print(json.dumps(line), flush=True)
+        return
 
     path = random_init_(VisionEmbeddingPath(device=dev), seed=0)
-    lut = vz.clip_lut()
     n_global = IMAGES_PER_GPU * world
     tiles_global = [TILES_PER_IMAGE] * n_global
     sizes_global = [IMAGE_SIZES[i % len(IMAGE_SIZES)] for r in range(world) for i in range(IMAGES_PER_GPU)]
@@ -227,13 +470,13 @@ def main():
     pre_plan = build_plan(dev_imgs, views, lut)
     assert pre_plan.tiles_per_image == [TILES_PER_IMAGE] * IMAGES_PER_GPU, pre_plan.tiles_per_image
 
-    def step_device():
+    def step_device(keep_local=False):
         """inputs resident in HBM; preprocess descriptors (pure geometry) prebuilt"""
         patches = run_plan(pre_plan, "patches")
         pb = PatchBatch(patches, pre_plan.tiles_per_image, pre_plan.image_sizes)
         if world > 1:
             return path.prepare_inputs_labels_for_multimodal_sharded(ids_dev, None, None, None, None, pb, tiles_global,
-                                                                     sizes_global)
+                                                                     sizes_global, keep_local=keep_local)
         return path.prepare_inputs_labels_for_multimodal(ids_dev, None, None, None, None, pb, sizes_global)
 
     out_host = {}
@@ -320,37 +563,78 @@ def main():
         assert out[4].shape == (n_global, SEQ - 1 + TILES_PER_IMAGE * 32, 4096), out[4].shape
         assert torch.isfinite(out[4].float()).all()
 
+    # ---- multi-GPU correctness, outside the timed region ---------------------------------------------
+    # Every rank checksums the rows ITS projector produced (fp32 sum + first and last row); rank 0 must find
+    # exactly those rows at their place in the spliced global batch -- on the default transport (peer stores
+    # when available) and on the NCCL all-gather, whose outputs must also be bit-identical to each other.
+    transport, parity = "none", None
+    if world > 1:
+        D = 4096
+        outs, parity = {}, {}
+        env_before = os.environ.get("VZ_PEER_GATHER")
+        for env in (env_before, "0"):
+            if env is None:
+                os.environ.pop("VZ_PEER_GATHER", None)
+            else:
+                os.environ["VZ_PEER_GATHER"] = env
+            r = step_device(keep_local=True)
+            name = path.last_transport
+            loc = path.last_local_tokens
+            chk = torch.cat([loc.float().sum().reshape(1), loc[0].float(), loc[-1].float()]).contiguous()
+            allchk = torch.empty((world, chk.numel()), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(allchk, chk)
+            torch.cuda.synchronize()
+            if rank == 0:
+                emb = r[4]
+                ok = True
+                for rr in range(world):
+                    rows = emb[rr * IMAGES_PER_GPU:(rr + 1) * IMAGES_PER_GPU, 10:10 + TILES_PER_IMAGE * 32].reshape(-1, D)
+                    got = torch.cat([rows.float().sum().reshape(1), rows[0].float(), rows[-1].float()])
+                    ok = ok and bool(torch.equal(got[1:], allchk[rr, 1:]))
+                    ok = ok and abs(float(got[0]) - float(allchk[rr, 0])) <= 1e-6 * max(1.0, abs(float(allchk[rr, 0])))
+                parity[name] = ok
+                outs[name] = emb.clone()
+            if env == env_before:
+                transport = name
+        if env_before is None:
+            os.environ.pop("VZ_PEER_GATHER", None)
+        else:
+            os.environ["VZ_PEER_GATHER"] = env_before
+        if rank == 0 and len(outs) == 2:
+            a, b = list(outs.values())
+            parity["transports_bit_identical"] = bool(torch.equal(a, b))
+        outs = None
+        step_device()     # back on the default transport before timing
+        barrier()
+
     # ---- timed region: device-resident inputs -------------------------------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.mark_begin()
     l0 = lib.vz_kernel_launches()
     ms_total = timed(step_device, args.steps)
     launches = int(lib.vz_kernel_launches() - l0)
-    # ---- same steps again with CUDA events around every GEMM launch (roofline of the dominant kernel).
-    # The two event records per launch (356 per step) stretch a step by ~5 %, so `value` comes from the
-    # clean pass above and the per-launch GEMM durations from this instrumented pass of the same K steps.
-    import ctypes as C
-    lib.vz_gemm_profile(1)
+    # ---- same steps again with CUDA events around every kernel launch (rooflines of the kernel families).
+    # The two event records per launch (~470 per step) stretch a step by ~5 %, so `value` comes from the
+    # clean pass above and the per-launch durations from this instrumented pass of the same K steps.
+    lib.vz_profile(1)
     ms_instr = timed(step_device, args.steps)
-    n_g, g_ms, g_fl = C.c_longlong(0), C.c_double(0), C.c_double(0)
-    _lib.check(lib.vz_gemm_profile_read(C.byref(n_g), C.byref(g_ms), C.byref(g_fl)), "gemm profile")
-    lib.vz_gemm_profile(0)
+    prof = _lib.profile_read()
+    lib.vz_profile(0)
+    if rank == 0:
+        sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host buffers --------------------------------------------------------------------
     for _ in range(2):
         step_e2e()
     e2e_drain()
-
-    def e2e_steps():
-        step_e2e()
-
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
-        e2e_steps()
+        step_e2e()
     torch.cuda.current_stream().wait_stream(d2h_stream)      # the last result must have reached the host
     t1.record()
     e2e_drain()
@@ -365,23 +649,56 @@ def main():
             dist.destroy_process_group()
         return
 
-    pk, pk_kind = peaks()
     ms_step = ms_total / args.steps
     value = n_global / (ms_step / 1000.0)
     e2e_value = n_global / (ms_e2e / args.steps / 1000.0)
     h2d = sum(x.numel() for x in host_imgs) + ids_host.numel() * 8 + pre_plan.h2d_bytes
     d2h = out_host["emb"][0].numel() * 2 + (2 * n_global + 4) * 4
-    gemm_tflops = (g_fl.value / 1e12) / (g_ms.value / 1e3) if g_ms.value > 0 else 0.0
+    n_g, g_ms, g_fl = prof.get("gemm_bf16_tcgen05", (0, 0.0, 0.0))
+    gemm_tflops = (g_fl / 1e12) / (g_ms / 1e3) if g_ms > 0 else 0.0
     peak_tf = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    hbm = pk["hbm_gbs"]
+    # algorithmic bytes the launchers cannot know: preprocess = u8 sources + bf16 patch rows;
+    # scatter = rows read + rows written + the integer side arrays
+    pre_bytes = sum(x.numel() for x in host_imgs) + pre_plan.n_tiles * 677376
+    Lout = SEQ - 1 + TILES_PER_IMAGE * 32
+    sc_bytes = n_global * Lout * 8192 * 2 + 17 * n_global * SEQ + 24 * n_global * Lout
+    extra = []
+    for name, (n, ms, work) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        if name == "gemm_bf16_tcgen05":
+            continue
+        ent = {"kernel": name, "launches_per_step": n / args.steps, "ms_per_step": ms / args.steps,
+               "share_of_step": ms / ms_instr}
+        if name == "vit_attn_tc":
+            tf = work / 1e12 / (ms / 1e3)
+            ent.update(bound="tensor", achieved=tf, peak=peak_tf, unit="TFLOP/s", frac=tf / peak_tf,
+                       note="exp2-bound before tensor-bound: 333 k exp2 per (tile, head)")
+        elif name == "fuse":
+            gb = work / 1e9 / (ms / 1e3)
+            ent.update(bound="hbm", achieved=gb, peak=hbm, unit="GB/s", frac=gb / hbm)
+        elif name == "splice_scatter":
+            gb = sc_bytes * args.steps / 1e9 / (ms / 1e3)
+            ent.update(bound="hbm", achieved=gb, peak=hbm, unit="GB/s", frac=gb / hbm,
+                       note="L=63 geometry: 14.6 MB per launch, launch-latency sized; config 5 geometry under workloads")
+        elif name in ("layernorm", "softmax_rows"):
+            gb = work / 1e9 / (ms / 1e3)
+            ent.update(bound="hbm", achieved=gb, peak=hbm, unit="GB/s", frac=gb / hbm)
+        extra.append(ent)
+    pre_ms = sum(prof.get(k, (0, 0.0, 0.0))[1] for k in ("preprocess_h", "preprocess_v", "preprocess_fused"))
+    if pre_ms > 0:
+        gb = pre_bytes * args.steps / 1e9 / (pre_ms / 1e3)
+        extra.append({"kernel": "preprocess (h + v passes)", "ms_per_step": pre_ms / args.steps, "bound": "hbm",
+                      "achieved": gb, "peak": hbm, "unit": "GB/s", "frac": gb / hbm, "bytes_per_step": pre_bytes,
+                      "share_of_step": pre_ms / ms_instr})
+    config = workload_config("c3_anyres_b8")
+    config.update({"global_images": n_global, "parallelism": f"dp{world}", "transport": transport,
+                   "l2_policy": "no flush needed: every step streams 4.0 GB of weights + 1.2 GB of hidden states + 0.9 GB of activations, far beyond the 126 MB L2",
+                   "tiles_per_s": value * TILES_PER_IMAGE})
     line = {
-        "metric": "anyres images/sec (ViT-L/14-336 + Q-Former)", "value": value, "unit": "images/s",
+        "metric": METRIC, "value": value, "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "c3_anyres_b8", "images_per_gpu": IMAGES_PER_GPU, "tiles_per_image": TILES_PER_IMAGE,
-                   "global_images": n_global, "seq_len": SEQ, "merge": "flat", "parallelism": f"dp{world}",
-                   "l2_policy": "no flush needed: every step streams 4.0 GB of weights + 1.2 GB of hidden states + 0.9 GB of activations, far beyond the 126 MB L2",
-                   "tiles_per_s": value * TILES_PER_IMAGE,
-                   "path_tflops_algorithmic": value * TILES_PER_IMAGE * GFLOP_PER_TILE / 1000.0 / world},
+        "config": config,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e / args.steps,
                 "how": "public API from pinned host buffers; the copies of step k+1 / k-1 overlap the kernels of step k (2 copy streams)"},
@@ -392,14 +709,34 @@ def main():
                      # dram__bytes_read+write per launch, ncu --set full, mean over the four ViT GEMM shapes
                      # (profiles/r1_v9_final.md); algorithmic bytes of the same launches: 219 MB
                      "traffic": TRAFFIC_PER_LAUNCH, "traffic_source": "profiles/r1_v9_final.md",
-                     "peak_source": f"{pk_kind} bf16_tflops_sustained", "launches": int(n_g.value),
-                     "gemm_ms_per_step": g_ms.value / args.steps,
-                     "measured_in": "second pass of the same K steps with CUDA events around every GEMM launch",
+                     "peak_source": f"{pk_kind} bf16_tflops_sustained", "launches": int(n_g),
+                     "gemm_ms_per_step": g_ms / args.steps,
+                     "measured_in": "second pass of the same K steps with CUDA events around every kernel launch",
                      "instrumented_ms_per_step": ms_instr / args.steps,
-                     "gemm_share_of_step": (g_ms.value / ms_instr) if ms_instr else None},
+                     "gemm_share_of_step": (g_ms / ms_instr) if ms_instr else None},
+        "roofline_extra": extra,
     }
+    if world > 1:
+        line["parity_ok"] = bool(parity) and all(parity.values())
+        line["parity"] = parity
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample()
+    if world == 1 and not args.no_extras:
+        wl = {}
+        for name, fn in (("c1_latency", lambda: bench_c1_latency(path, lut, dev, args.steps)),
+                         ("eager_bf16", lambda: bench_eager_bf16(path, dev, args.steps))):
+            try:
+                wl[name] = fn()
+            except Exception as e:      # a side measurement must not lose the main line
+                wl[name] = {"error": f"{type(e).__name__}: {e}"}
+        line["eager_bf16"] = wl.pop("eager_bf16")
+        del path
+        torch.cuda.empty_cache()
+        try:
+            wl["c5_prefill_b8"] = bench_c5(dev, lut, args.steps, args.llm_layers)
+        except Exception as e:
+            wl["c5_prefill_b8"] = {"error": f"{type(e).__name__}: {e}"}
+        line["workloads"] = wl
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -111,6 +111,18 @@ int vz_gemm_stats_partials(int M, int N);
 long long vz_kernel_launches(void);
 int vz_gemm_profile(int enable);
 int vz_gemm_profile_read(long long* launches, double* total_ms, double* total_flops);
+/* The same for every kernel family: vz_profile(1) records CUDA events around every launch of the library
+ * (each on its own stream); vz_profile_read(tag) synchronises them and returns the launches of that family,
+ * their summed milliseconds and their summed algorithmic work (FLOPs for the tensor-core kernels, bytes for
+ * the HBM-bound ones, 0 where the launcher cannot know it).  vz_gemm_profile* = tag VZ_PROF_GEMM.          */
+enum {
+  VZ_PROF_GEMM = 0, VZ_PROF_VIT_ATTN = 1, VZ_PROF_FUSE = 2, VZ_PROF_PRE_H = 3, VZ_PROF_PRE_V = 4,
+  VZ_PROF_PRE_FUSED = 5, VZ_PROF_SPLICE_SCATTER = 6, VZ_PROF_QATTN = 7, VZ_PROF_SOFTMAX = 8,
+  VZ_PROF_LAYERNORM = 9, VZ_PROF_TEXT_GATHER = 10, VZ_PROF_OTHER = 11, VZ_PROF_COUNT = 12
+};
+int vz_profile(int enable);
+int vz_profile_read(int tag, long long* launches, double* total_ms, double* total_work);
+const char* vz_profile_tag_name(int tag);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Row kernels                                                                                 */

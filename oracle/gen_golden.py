@@ -13,6 +13,8 @@ What is pinned
   golden_text.npz     tokenizer_image_token (stub word-hash tokenizer) and DataCollatorForSupervisedDataset
   golden_model.npz    CLIPVisionTower + QFormer outputs (fp32, seeded weights from oracle/weights.py)
                       for config 1 (one 336x336 tile, 63 text tokens) and a 5-tile anyres image
+  golden_model_long.npz  the same at BASELINE config 5's text length: S = 2048, B = 2 (1 + 3 tiles), L = 2047
+  golden_modes.npz    mm_utils.process_images in its four aspect modes through the Pillow-backed CLIP processor
 """
 import argparse
 import hashlib
@@ -306,7 +308,8 @@ def gen_text():
 
 
 # --------------------------------------------------------------------------------------------
-def gen_model():
+def _reference_glue():
+    """the unmodified reference tower + QFormer + mixin around an embedding table, seeded weights"""
     import tempfile
     from PIL import Image
     from transformers import CLIPVisionConfig, CLIPVisionModel
@@ -367,7 +370,13 @@ def gen_model():
             self.captured["vis"] = out
             return out
 
-    glue = Glue()
+    return Glue(), proc, projector
+
+
+def gen_model():
+    from PIL import Image
+    from vis_zephyr.model.multi_scale_process import process_any_resolution_image
+    glue, proc, projector = _reference_glue()
     out = {}
     with torch.no_grad():
         # config 1: one 336x336 image, ids of length 64 with one -200 at position 10
@@ -417,16 +426,90 @@ def gen_model():
     print("golden_model.npz written")
 
 
+def gen_model_long():
+    """BASELINE config 5 regime (S = 2048): the reference's prepare_inputs_labels_for_multimodal on B = 2,
+    sample 0 with ~2000 real tokens and ONE 336x336 tile, sample 1 with ~300 real tokens + pads and a
+    3-tile anyres image -> text conditioning rows L = 2047 with a large zero-padded tail (quirk Q3)."""
+    from PIL import Image
+    from vis_zephyr.model.multi_scale_process import process_any_resolution_image
+    glue, proc, projector = _reference_glue()
+    out = {}
+    S = 2048
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(21)
+        ids = torch.randint(3, 32000, (2, S), generator=g)
+        ids[ids == 2] = 3
+        ids[0, 17] = -200
+        ids[0, 2001:] = 2                   # 2000 real tokens + the image slot, then pads
+        ids[1, 9] = -200
+        ids[1, 301:] = 2
+        mask = (ids != 2).long()
+        labels = ids.clone()
+        labels[0, :700] = -100
+        labels[1, :100] = -100
+        labels[ids == 2] = -100
+        img0 = synth_image(7, 336, 336)
+        px0 = proc.preprocess(Image.fromarray(img0), return_tensors="pt")["pixel_values"]      # [1,3,336,336]
+        img1 = synth_image(1, 637, 336)
+        px1 = process_any_resolution_image(Image.fromarray(img1), proc, PINPOINTS_SHIPPED)     # [3,3,336,336]
+        r = glue.prepare_inputs_labels_for_multimodal(ids, None, mask, None, labels, [px0, px1],
+                                                      [(336, 336), (637, 336)])
+        out["ids"], out["mask"], out["labels"] = ids.numpy(), mask.numpy(), labels.numpy()
+        out["tiles"] = np.array([px0.shape[0], px1.shape[0]], np.int64)
+        out["vis"] = glue.captured["vis"].numpy().astype(np.float16)               # [4,32,4096]
+        out["vis_probe32"] = glue.captured["vis"][:, :, ::64].numpy().astype(np.float32)
+        out["out_labels"] = r[5].numpy()
+        out["out_mask"] = r[2].numpy()
+        out["embeds_shape"] = np.array(r[4].shape, np.int64)
+        out["embeds_probe"] = r[4][:, ::7, ::512].numpy().astype(np.float32)
+        print("long done", r[4].shape)
+    np.savez_compressed(os.path.join(GOLD, "golden_model_long.npz"), **out)
+    print("golden_model_long.npz written")
+
+
+MODE_SIZES = [(700, 500), (420, 901), (336, 336), (1000, 1000), (301, 640)]
+
+
+def gen_modes():
+    """mm_utils.process_images (expand2square / centre-square crop / LANCZOS squash / plain) through the
+    Pillow-backed CLIP processor (what the reference's pinned transformers 4.52.4 runs): SHA-256 of the
+    f32 pixel tensors, plus the 768-entry LUT of that processor."""
+    from PIL import Image
+    from transformers.models.clip import CLIPImageProcessorPil
+    from vis_zephyr.model.mm_utils import process_images
+    proc = CLIPImageProcessorPil(size={"shortest_edge": 336}, crop_size={"height": 336, "width": 336},
+                                 image_mean=[0.48145466, 0.4578275, 0.40821073],
+                                 image_std=[0.26862954, 0.26130258, 0.27577711], resample=3)
+    ramp = np.zeros((336, 336, 3), np.uint8)
+    ramp[:] = (np.arange(336) % 256)[None, :, None]
+    px = proc.preprocess(Image.fromarray(ramp), return_tensors="pt")["pixel_values"][0].numpy()
+    out = {"lut": np.stack([px[c, 0, :256] for c in range(3)]).astype(np.float32),
+           "sizes": np.array(MODE_SIZES, np.int64)}
+    rng = np.random.default_rng(12)
+    for si, (W, H) in enumerate(MODE_SIZES):
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        for mode in ("pad", "square", "resize", "plain"):
+            cfg = types.SimpleNamespace(aspect_ratio_mode=mode)
+            t = process_images(Image.fromarray(img), proc, cfg).numpy().astype(np.float32)
+            assert t.shape == (3, 336, 336)
+            out[f"s{si}_{mode}_sha"] = np.array(sha(t))
+            out[f"s{si}_{mode}_probe"] = t[:, ::48, ::48].copy()
+    np.savez_compressed(os.path.join(GOLD, "golden_modes.npz"), **out)
+    print("golden_modes.npz written", len(out))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-model", action="store_true")
     ap.add_argument("--only", default="")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
-    todo = a.only.split(",") if a.only else ["pixels", "vip", "merge", "splice", "text", "model"]
+    todo = a.only.split(",") if a.only else ["pixels", "vip", "merge", "splice", "text", "modes", "model", "model_long"]
     if "pixels" in todo: gen_pixels()
     if "vip" in todo: gen_vip()
     if "merge" in todo: gen_merge()
     if "splice" in todo: gen_splice()
     if "text" in todo: gen_text()
+    if "modes" in todo: gen_modes()
     if "model" in todo and not a.skip_model: gen_model()
+    if "model_long" in todo and not a.skip_model: gen_model_long()

@@ -83,6 +83,46 @@ def test_qformer_matches_oracle(vision_path, seeded_weights):
     assert (ref_t - ref_nt).abs().max() > 1e-3
 
 
+@pytest.mark.parametrize("L", [31, 32, 33, 512, 2047])
+def test_qformer_long_ragged_text_matches_oracle(vision_path, seeded_weights, L):
+    """BASELINE config 5 regime: the packed text form (one row set per SAMPLE, zero padding collapsed to one
+    key with multiplicity L - S') against the oracle run LITERALLY on all 32 + L rows of every tile.
+    L = 31 / 32 / 33 straddle the 32-key chunk of the block-0 self-attention (own 32 rows + text + pad key),
+    512 and 2047 walk 17 / 65 chunks across both segment boundaries; sample 1 keeps a third of the rows, so
+    its pad key carries a multiplicity of up to 1 365; 3 tiles share the 2 samples' text K/V."""
+    from oracle import model as M
+    from vision_zephyr_b200.projector import TextPack
+    proj = vision_path.model.mm_projector
+    tiles = [1, 2]
+    T = sum(tiles)
+    s_len = [L, max(L // 3, 1)]
+    feats = _rand((T, 576, 5120), 1.0, 30 + L)
+    rows = [_rand((n, 4096), 0.02, 40 + L + i) for i, n in enumerate(s_len)]
+    dense = torch.zeros((T, L, 4096), dtype=torch.bfloat16, device="cuda")
+    t0 = 0
+    for smp, nt in enumerate(tiles):
+        dense[t0:t0 + nt, :s_len[smp]] = rows[smp][None]
+        t0 += nt
+    with torch.no_grad():
+        ref = M.qformer_forward(seeded_weights["qf"], feats.float().cpu(), dense.float().cpu())
+    R = sum(s_len)
+    emb = torch.cat(rows + [torch.zeros((1, 4096), dtype=torch.bfloat16, device="cuda")])
+    off = torch.tensor([0, s_len[0], R], dtype=torch.int32, device="cuda")
+    tile_sample = torch.tensor([0, 1, 1], dtype=torch.int32, device="cuda")
+    got = proj.forward_packed(feats, TextPack(emb, off, R, 2, L, tile_sample)).float().cpu()
+    got_dense = proj(feats, dense).float().cpu()          # reference signature: every tile its own sample
+    for name, g in (("packed", got), ("dense", got_dense)):
+        cos = torch.nn.functional.cosine_similarity(g, ref, dim=-1)
+        err = (g - ref).abs().max().item()
+        print(f"qformer L={L} {name}: min cos {cos.min().item():.6f} max_abs {err:.4g}")
+        assert cos.min() > 0.999 and err < 0.15, (L, name)
+    # tiles 1 and 2 share a sample but see different features; the zero-pad tail must matter for sample 1
+    if L >= 32:
+        with torch.no_grad():
+            short = M.qformer_forward(seeded_weights["qf"], feats[1:2].float().cpu(), dense[1:2, :s_len[1]].float().cpu())
+        assert (short - ref[1:2]).abs().max() > 1e-3
+
+
 @pytest.mark.parametrize("impl", [1, 0])
 def test_vit_attention_kernels_match_torch(impl):
     """both attention kernels (tcgen05 = 1, legacy mma.sync = 0) against fp32 torch attention."""

@@ -69,6 +69,38 @@ def test_anyres_two_samples_matches_reference(vision_path, golden_dir):
     assert np.abs(probe - g["c3_embeds_probe"]).max() <= MAX_ABS
 
 
+def test_config5_long_text_matches_reference(vision_path, golden_dir):
+    """S = 2048 (BASELINE config 5's text length), B = 2 with 1 + 3 tiles: the reference's own
+    prepare_inputs_labels_for_multimodal output (golden_model_long.npz).  Text conditioning has L = 2047 rows
+    per sample (pad-token embeddings included, quirk Q3), i.e. 65 key chunks in the block-0 self-attention
+    and a 4 095-row text K/V GEMM."""
+    import vision_zephyr_b200 as vz
+    from helpers import PINPOINTS_SHIPPED
+    g = np.load(f"{golden_dir}/golden_model_long.npz")
+    lut = _lut(golden_dir)
+    img0 = torch.from_numpy(synth_image(7, 336, 336)).cuda()
+    img1 = torch.from_numpy(synth_image(1, 637, 336)).cuda()
+    pb0 = vz.process_fixed_images([img0], lut, out_mode="chw")                      # list of [1,3,336,336]
+    pb1 = vz.process_any_resolution_images([img1], PINPOINTS_SHIPPED, lut, out_mode="chw")
+    images = [pb0[0], pb1[0]]
+    assert [int(x.shape[0]) for x in images] == g["tiles"].tolist() == [1, 3]
+    ids, mask, labels = (torch.from_numpy(g[k]).cuda() for k in ("ids", "mask", "labels"))
+    r = vision_path.prepare_inputs_labels_for_multimodal(ids, None, mask, None, labels, images, [(336, 336), (637, 336)])
+    torch.cuda.synchronize()
+    assert list(r[4].shape) == g["embeds_shape"].tolist()
+    assert np.array_equal(r[5].cpu().numpy(), g["out_labels"])
+    assert r[2].dtype == torch.int64 and np.array_equal(r[2].cpu().numpy(), g["out_mask"])
+    emb = r[4].float().cpu().numpy()
+    ref_vis = g["vis"].astype(np.float32)                                           # [4,32,4096]
+    got = np.concatenate([emb[0, 17:17 + 32].reshape(1, 32, 4096), emb[1, 9:9 + 96].reshape(3, 32, 4096)])
+    cos = cos_rows(got, ref_vis)
+    err = np.abs(got - ref_vis).max()
+    print(f"config5 (S=2048) visual tokens: min cos {cos.min():.6f} max_abs {err:.4g}")
+    assert cos.min() >= COS_MIN and err <= MAX_ABS
+    probe = r[4][:, ::7, ::512].float().cpu().numpy()
+    assert np.abs(probe - g["embeds_probe"]).max() <= MAX_ABS
+
+
 def test_tensor_and_patchbatch_inputs_agree(vision_path, golden_dir):
     """reference-style pixel tensors (list / 5-D) and the fused PatchBatch give identical bits."""
     import vision_zephyr_b200 as vz

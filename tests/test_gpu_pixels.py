@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import PINPOINTS_C3, PINPOINTS_SHIPPED, synth_image, vip_overlays
+from helpers import PINPOINTS_C3, PINPOINTS_SHIPPED, sha, synth_image, vip_overlays
 
 pytestmark = pytest.mark.gpu
 
@@ -141,6 +141,21 @@ def test_process_images_modes_bit_exact(mode, golden_dir):
             src = P.alpha_composite_rgb(src, ov)
         ref = P.normalize_lut(P.process_images_u8(src, mode)[None], lut)[0]
         assert np.array_equal(got[i][0].cpu().numpy(), ref), (mode, i)
+
+
+def test_process_images_modes_match_reference_golden(golden_dir):
+    """the four aspect modes through the kernel == SHA-256 of mm_utils.process_images' own output
+    (golden_modes.npz, generated by the reference with the Pillow-backed CLIP processor)"""
+    import vision_zephyr_b200 as vz
+    g = np.load(f"{golden_dir}/golden_modes.npz")
+    lut = g["lut"]
+    rng = np.random.default_rng(12)
+    imgs = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for (W, H) in g["sizes"].tolist()]
+    # the generator drew image s, then ran its 4 modes: same draw order here
+    for mode in ("pad", "square", "resize", "plain"):
+        got = vz.process_fixed_images([torch.from_numpy(x).cuda() for x in imgs], lut, out_mode="chw", mode=mode)
+        for si in range(len(imgs)):
+            assert sha(got[si][0].cpu().numpy().astype(np.float32)) == str(g[f"s{si}_{mode}_sha"]), (si, mode)
 
 
 def test_two_kernel_and_fused_forms_agree(golden_dir, monkeypatch):

@@ -161,3 +161,90 @@ def test_gather_visual_tokens_world2_gloo():
     res = sorted(q.get(timeout=120) for _ in range(2))
     [p.join(60) for p in procs]
     assert res == [(0, True, (17 * 32, 8)), (1, True, (17 * 32, 8))]
+
+
+def test_shard_images_leaves_no_rank_empty_and_minimises_the_largest_shard():
+    """the greedy cut handed out empty shards ([7,1,1,1] on 4 ranks); the partition must be the
+    min-max contiguous one and every rank must get an image while n >= world."""
+    import itertools
+    import random
+    assert shard_images([7, 1, 1, 1], 4) == [(0, 1), (1, 2), (2, 3), (3, 4)]
+    rng = random.Random(0)
+    for _ in range(1500):
+        n, w = rng.randint(0, 9), rng.randint(1, 5)
+        t = [rng.randint(1, 9) for _ in range(n)]
+        b = shard_images(t, w)
+        assert len(b) == w and b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        if n >= w:
+            assert all(e > s for s, e in b), (t, w, b)
+            best = min(max(sum(t[a:c]) for a, c in zip((0,) + cuts, cuts + (n,)))
+                       for cuts in itertools.combinations(range(1, n), w - 1))
+            assert max(sum(t[s:e]) for s, e in b) == best, (t, w, b, best)
+
+
+def test_initialize_vision_modules_mirrors_the_reference(tmp_path):
+    """vis_zephyr_arch.py:49-102 on a bare host (fresh-build branch, FSDP list form, 'unpad' newline, adapter
+    load with the 'model.mm_projector.' prefix the trainer writes).  The 1.7 B-parameter projector is built on
+    the meta device here; the value round trip runs on the GPU (tests/test_gpu_llm.py)."""
+    from types import SimpleNamespace
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    from vision_zephyr_b200 import arch
+    d = str(tmp_path / "clip")
+    cfg = CLIPVisionConfig(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+                           image_size=336, patch_size=14, projection_dim=768, hidden_act="quick_gelu")
+    with torch.device("meta"):
+        hf = CLIPVisionModel(cfg)
+    hf = hf.to_empty(device="cpu").to(torch.bfloat16)
+    for p in hf.parameters():
+        p.data.normal_(0, 0.02)
+    hf.save_pretrained(d)
+    del hf
+
+    class Base(torch.nn.Module):
+        def __init__(self, config):
+            super().__init__()
+            self.config = config
+            self.dtype = torch.bfloat16
+
+    class Host(arch.VisZephyrB200MetaModel, Base):
+        pass
+
+    built = {}
+
+    def meta_projector(config, **kw):
+        with torch.device("meta"):
+            built["p"] = vz.build_multimodal_projector(config)
+        return built["p"]
+
+    host = Host(SimpleNamespace(hidden_size=4096))           # no mm_vision_tower in the config: nothing built yet
+    assert host.get_vision_tower() is None and not hasattr(host, "mm_projector")
+    args = SimpleNamespace(mm_vision_tower=d, mm_vision_select_layer="-2,-5,-8,-11,6", mm_vision_select_feature="patch",
+                           pretrain_mm_mlp_adapter=None, mm_patch_merge_type="spatial_unpad",
+                           mm_grid_pinpoints="[[336, 672]]", image_aspect_ratio="anyres")
+    orig = arch.build_multimodal_projector
+    arch.build_multimodal_projector = meta_projector
+    try:
+        host.initialize_vision_modules(args, fsdp=["full_shard"])
+    finally:
+        arch.build_multimodal_projector = orig
+    assert type(host.vision_tower) is list and host.get_vision_tower().is_loaded
+    c = host.config
+    assert (c.mm_vision_tower, c.use_mm_proj, c.mm_projector_type, c.mm_hidden_size) == (d, True, "linear", 5120)
+    assert (c.mm_vision_select_layer, c.mm_vision_select_feature, c.mm_patch_merge_type) == \
+        ("-2,-5,-8,-11,6", "patch", "spatial_unpad")
+    assert (c.mm_grid_pinpoints, c.image_aspect_ratio, c.mm_use_im_start_end) == ("[[336, 672]]", "anyres", False)
+    assert host.mm_projector is built["p"]
+    assert host.image_newline.shape == (4096,) and host.image_newline.dtype == torch.bfloat16
+    assert 0.5 / 64 < host.image_newline.float().std().item() < 2.0 / 64          # N(0, 1/sqrt(4096))
+    # second call: existing modules are kept, the tower reloads, a frozen projector is un-frozen
+    host.mm_projector.requires_grad_(False)
+    host.initialize_vision_modules(args, fsdp=["full_shard"])
+    assert host.mm_projector is built["p"] and all(p.requires_grad for p in host.mm_projector.parameters())
+    # key format of mm_projector.bin (train/vis_zephyr_trainer.py:326-343) -> get_w -> projector keys
+    from vision_zephyr_b200.language_model import mm_adapter_state
+    wrapper = torch.nn.Module()
+    wrapper.model = host
+    names = [k for k, _ in wrapper.named_parameters() if "mm_projector" in k]
+    assert names[0].startswith("model.mm_projector.")
+    stripped = {k.split("mm_projector.")[1] for k in names}
+    assert stripped == set(host.mm_projector.state_dict().keys())

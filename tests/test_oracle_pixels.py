@@ -117,3 +117,17 @@ def test_process_images_modes_match_pillow_flow():
             left, top = (nw - 336) // 2, (nh - 336) // 2
             ref = np.asarray(r.crop((left, top, left + 336, top + 336)))
             assert np.array_equal(P.process_images_u8(img, mode, mean), ref), (W, H, mode)
+
+
+def test_process_images_modes_match_reference_golden(golden_dir):
+    """oracle process_images_u8 + LUT == mm_utils.process_images itself (golden_modes.npz: the reference
+    function run through the Pillow-backed CLIP processor, the backend its pinned transformers uses)"""
+    g = np.load(f"{golden_dir}/golden_modes.npz")
+    lut = g["lut"]
+    rng = np.random.default_rng(12)
+    for si, (W, H) in enumerate(g["sizes"].tolist()):
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        for mode in ("pad", "square", "resize", "plain"):
+            got = P.normalize_lut(P.process_images_u8(img, mode)[None], lut)[0]
+            assert np.array_equal(got[:, ::48, ::48], g[f"s{si}_{mode}_probe"]), (W, H, mode)
+            assert sha(got.astype(np.float32)) == str(g[f"s{si}_{mode}_sha"]), (W, H, mode)

@@ -91,6 +91,7 @@ ROWS_PLAIN, ROWS_PATCH_EMBED, ROWS_RES_MOD = 0, 1, 2
 PRIM_LAYER, PRIM_RECT = 0, 1
 OUT_PATCHES_BF16, OUT_CHW_F32 = 0, 1
 MERGE_FLAT, MERGE_SPATIAL, MERGE_SPATIAL_UNPAD, MERGE_SINGLE_NEWLINE = 0, 1, 2, 3
+PROF_COUNT = 12
 
 # every symbol include/vz_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
@@ -104,6 +105,9 @@ SYMBOLS = {
     "vz_kernel_launches": (C.c_longlong, []),
     "vz_gemm_profile": (_i, [_i]),
     "vz_gemm_profile_read": (_i, [C.POINTER(C.c_longlong), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "vz_profile": (_i, [_i]),
+    "vz_profile_read": (_i, [_i, C.POINTER(C.c_longlong), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "vz_profile_tag_name": (C.c_char_p, [_i]),
     "vz_layernorm_bf16": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, C.c_float, _vp]),
     "vz_preprocess": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp]),
     "vz_preprocess2": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, C.c_longlong, _i, _i, _i, _i, _vp]),
@@ -165,3 +169,15 @@ def ptr(t):
 def stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def profile_read():
+    """{kernel family: (launches, total ms, total algorithmic work)} of everything recorded since vz_profile(1)."""
+    lib = load()
+    out = {}
+    for tag in range(PROF_COUNT):
+        n, ms, wk = C.c_longlong(0), C.c_double(0), C.c_double(0)
+        check(lib.vz_profile_read(tag, C.byref(n), C.byref(ms), C.byref(wk)), "vz_profile_read")
+        if n.value:
+            out[lib.vz_profile_tag_name(tag).decode()] = (int(n.value), float(ms.value), float(wk.value))
+    return out

@@ -45,6 +45,54 @@ class VisZephyrB200MetaModel:
             vt = vt[0]
         return vt
 
+    def initialize_vision_modules(self, model_args, fsdp=None):
+        """vis_zephyr_arch.py:49-102, statement for statement (called from train/train.py:803 after the LLM is
+        built): build or load the tower (kept in a one-element list under FSDP so it is not wrapped), write the
+        nine config.mm_* attributes, build the projector (+ image_newline ~ N(0, 1/hidden) for 'unpad' merge
+        types) or un-freeze an existing one, and load `pretrain_mm_mlp_adapter` (an mm_projector.bin written by
+        train/vis_zephyr_trainer.py:304-348) by stripping the 'mm_projector.' prefix."""
+        vision_tower = model_args.mm_vision_tower
+        mm_vision_select_layer = model_args.mm_vision_select_layer
+        mm_vision_select_feature = model_args.mm_vision_select_feature
+        mm_projector_train = model_args.pretrain_mm_mlp_adapter
+        mm_patch_merge_type = model_args.mm_patch_merge_type
+
+        self.config.mm_vision_tower = vision_tower
+        if self.get_vision_tower() is None:
+            vision_tower = build_vision_tower(model_args)
+            self.vision_tower = [vision_tower] if fsdp and len(fsdp) > 0 else vision_tower
+        else:
+            vision_tower = self.vision_tower[0] if fsdp and len(fsdp) > 0 else self.vision_tower
+            vision_tower.load_model()
+
+        self.config.use_mm_proj = True
+        self.config.mm_projector_type = getattr(model_args, "mm_projector_type", "linear")
+        # the reference reads self.vision_tower.hidden_size (:73), which breaks on the FSDP list form; same value
+        self.config.mm_hidden_size = vision_tower.hidden_size
+        self.config.mm_vision_select_layer = mm_vision_select_layer
+        self.config.mm_vision_select_feature = mm_vision_select_feature
+        self.config.mm_patch_merge_type = mm_patch_merge_type
+        self.config.mm_grid_pinpoints = getattr(model_args, "mm_grid_pinpoints", None)
+        self.config.image_aspect_ratio = getattr(model_args, "image_aspect_ratio", "square")
+        self.config.mm_use_im_start_end = getattr(model_args, "mm_use_im_start_end", False)
+
+        if getattr(self, "mm_projector", None) is None:
+            self.mm_projector = build_multimodal_projector(self.config)
+            if "unpad" in mm_patch_merge_type:
+                embed_std = 1 / torch.sqrt(torch.tensor(self.config.hidden_size, dtype=self.dtype))
+                self.image_newline = nn.Parameter(torch.randn(self.config.hidden_size, dtype=self.dtype) * embed_std)
+        else:
+            for p in self.mm_projector.parameters():   # un-freeze a projector LoRA froze
+                p.requires_grad = True
+
+        if mm_projector_train is not None:
+            projector_weights = torch.load(mm_projector_train, map_location="cpu")
+
+            def get_w(weights, keyword):
+                return {k.split(keyword + ".")[1]: v for k, v in weights.items() if keyword in k}
+
+            self.mm_projector.load_state_dict(get_w(projector_weights, "mm_projector"))
+
 
 def _slots_to_device(descs: List[dict], device):
     n = len(descs)
@@ -204,16 +252,18 @@ class VisZephyrB200MetaForCausalLM(ABC):
 
     def prepare_inputs_labels_for_multimodal_sharded(self, input_ids, position_ids, attention_mask,
                                                      past_key_values, labels, local_images, tiles_per_image,
-                                                     images_size=None, group=None, dst=0):
+                                                     images_size=None, group=None, dst=0, keep_local=False):
         """Data-parallel form (north_star): every rank holds the (small) global text batch and encodes
         only ITS contiguous block of images (`local_images`, a PatchBatch or list of tile tensors for the
-        images dist.shard_images assigns to this rank); the projected visual tokens are all-gathered and
-        rank `dst` splices the global batch.  Other ranks return None for the tensors."""
+        images dist.shard_images assigns to this rank); the projected visual tokens travel to rank `dst`
+        (peer stores or one all-gather, `self.last_transport` says which), which splices the global batch.
+        Other ranks return None for the tensors.  keep_local=True (checks only) also leaves this rank's
+        projected rows in `self.last_local_tokens`."""
         return self._prepare(input_ids, position_ids, attention_mask, past_key_values, labels, local_images,
-                             images_size, list(tiles_per_image), group, dst)
+                             images_size, list(tiles_per_image), group, dst, keep_local)
 
     def _prepare(self, input_ids, position_ids, attention_mask, past_key_values, labels, images, images_size,
-                 global_tiles, group, dst):
+                 global_tiles, group, dst, keep_local=False):
         vision_tower = self.get_vision_tower()
         if vision_tower is None or images is None or input_ids.shape[1] == 1:
             return input_ids, position_ids, attention_mask, past_key_values, None, labels
@@ -235,70 +285,45 @@ class VisZephyrB200MetaForCausalLM(ABC):
             # the reference's 4-D / 3-D branch fails inside QFormer.forward (quirk Q1)
             raise RuntimeError("Tensors must have same number of dimensions: got 3 and 2 "
                                "(pass images as a list of [T_i,3,336,336] tensors or a 5-D tensor)")
+        proj = model.mm_projector
         sharded = global_tiles is not None
         if sharded:
             import torch.distributed as tdist
-            from .dist import gather_visual_tokens, shard_images
+            from .dist import (TRANSPORT_NCCL, TRANSPORT_PEER, gather_visual_tokens, peer_gather_for, shard_images)
             world, rank = tdist.get_world_size(group), tdist.get_rank(group)
             tiles_per_image = global_tiles
             bounds = shard_images(tiles_per_image, world)
             lo, hi = bounds[rank]
             if list(local_tiles) != list(tiles_per_image[lo:hi]):
                 raise ValueError(f"rank {rank} was given tiles {local_tiles}, expected {tiles_per_image[lo:hi]}")
-            rows_per_rank = [sum(tiles_per_image[a:b]) * model.mm_projector.num_queries for a, b in bounds]
-            from .dist import peer_gather_for
+            rows_per_rank = [sum(tiles_per_image[a:b]) * proj.num_queries for a, b in bounds]
             peer = peer_gather_for(sum(rows_per_rank), embed.shape[1], torch.bfloat16, dev, group)
+            self.last_transport = TRANSPORT_PEER if peer is not None else TRANSPORT_NCCL
         else:
             tiles_per_image, lo, hi = list(local_tiles), 0, len(local_tiles)
             peer = None
-        n_images = len(tiles_per_image)
-        B, S = input_ids.shape
-        if n_images > B:
-            raise IndexError("index out of range: more images than samples")  # input_ids[i], :167
-        input_ids = input_ids.to(dev).contiguous()
-        mask_u8 = None
-        if attention_mask is not None:
-            mask_u8 = attention_mask.to(dev).bool().to(torch.uint8).contiguous()
-        labels_dev = labels.to(dev).contiguous() if labels is not None else None
 
         # ---- plan on the device while the host queues the tower ----------------------------------
-        proj = model.mm_projector
-        descs = self._slot_descs(tiles_per_image, images_size, proj.num_queries)
-        slots_dev, slot_prefix, total_vis_rows = _slots_to_device(descs, dev)
-        max_len = getattr(self.config, "tokenizer_model_max_length", None) or 0
-        plan = splice_plan(input_ids, mask_u8, slots_dev, n_images, max_len)
+        ctx = self._plan_splice(input_ids, attention_mask, labels, tiles_per_image, images_size)
 
         # ---- tower (independent of the text) ---------------------------------------------------
         feats = None
         if hi > lo:
             feats = vision_tower.encode_patches(patches, pre_norm=proj.pre_norm_params())
 
-        # ---- text conditioning: one row set per SAMPLE, shared by its tiles; the reference
-        # conditions image i on ids[i] (:163-176) and pads to the batch-global max (quirk Q3) -----
-        info = plan.wait()
-        if info["slots_used"] > n_images:
-            raise IndexError("list index out of range: more image slots consumed than image features")
-        L_text = max(info["text_len"][:n_images])
-        vis_local = torch.empty((0, embed.shape[1]), dtype=torch.bfloat16, device=dev)
-        if hi > lo:
-            text_rows = sum(info["text_len"][lo:hi])
-            text_emb, text_off = text_gather(input_ids, embed, plan, text_rows, lo, hi)
-            if text_emb.dtype != torch.bfloat16:
-                text_emb = text_emb.to(torch.bfloat16)
-            tile_sample = torch.repeat_interleave(torch.arange(hi - lo, dtype=torch.int32),
-                                                  torch.tensor(tiles_per_image[lo:hi])).to(dev)
-            text = TextPack(text_emb, text_off, text_rows, hi - lo, L_text, tile_sample)
-            out_view = None
-            if peer is not None:
-                # the exchange step IS the projector's last kernel: its final LayerNorm stores go straight
-                # into the destination rank's receive buffer (peer-mapped over NVLink)
-                out_view = peer.slot(dst, sum(rows_per_rank[:rank]), rows_per_rank[rank])
-                out_view = out_view.view(sum(tiles_per_image[lo:hi]), proj.num_queries, -1)
-            vis_local = proj.forward_packed(feats, text, feats_normed=True, out=out_view)      # [T,32,4096] bf16
-            vis_local = vis_local.reshape(-1, vis_local.shape[-1])
+        out_view = None
+        if peer is not None and hi > lo and not keep_local:
+            # the exchange step IS the projector's last kernel: its final LayerNorm stores go straight
+            # into the destination rank's receive buffer (peer-mapped over NVLink)
+            out_view = peer.slot(dst, sum(rows_per_rank[:rank]), rows_per_rank[rank])
+        vis_local = self._project_shard(ctx, feats, tiles_per_image, lo, hi, out_view)
+        if keep_local:
+            self.last_local_tokens = vis_local
 
         # ---- the one exchange step ------------------------------------------------------------
         if sharded and peer is not None:
+            if keep_local and hi > lo:
+                peer.slot(dst, sum(rows_per_rank[:rank]), rows_per_rank[rank]).copy_(vis_local)
             peer.finish()                                   # one device-side barrier; no data collective
             if rank != dst:
                 peer.skip_local()
@@ -310,18 +335,78 @@ class VisZephyrB200MetaForCausalLM(ABC):
                 return None, None, None, past_key_values, None, None
         else:
             vis = vis_local
+        return self._splice(ctx, vis, position_ids, attention_mask, past_key_values, labels)
+
+    # -- the three stages of the path (also the units bench.py times and the multi-GPU checks re-run) ------
+    def _plan_splice(self, input_ids, attention_mask, labels, tiles_per_image, images_size):
+        """Upload ids / mask / labels + the slot table and launch the plan kernel (no host wait)."""
+        model = self.get_model()
+        embed = model.embed_tokens.weight
+        dev = embed.device
+        n_images = len(tiles_per_image)
+        B, S = input_ids.shape
+        if n_images > B:
+            raise IndexError("index out of range: more images than samples")  # input_ids[i], :167
+        ids_dev = input_ids.to(dev).contiguous()
+        mask_u8 = None
+        if attention_mask is not None:
+            mask_u8 = attention_mask.to(dev).bool().to(torch.uint8).contiguous()
+        labels_dev = labels.to(dev).contiguous() if labels is not None else None
+        descs = self._slot_descs(tiles_per_image, images_size, model.mm_projector.num_queries)
+        slots_dev, slot_prefix, total_vis_rows = _slots_to_device(descs, dev)
+        max_len = getattr(self.config, "tokenizer_model_max_length", None) or 0
+        plan = splice_plan(ids_dev, mask_u8, slots_dev, n_images, max_len)
+        return dict(ids=ids_dev, mask=mask_u8, labels=labels_dev, slots=slots_dev, prefix=slot_prefix,
+                    total_vis_rows=total_vis_rows, plan=plan, n_images=n_images, info=None)
+
+    @staticmethod
+    def _plan_info(ctx):
+        """The one host round-trip of the path: the planned lengths (output shapes depend on them)."""
+        if ctx["info"] is None:
+            info = ctx["plan"].wait()
+            if info["slots_used"] > ctx["n_images"]:
+                raise IndexError("list index out of range: more image slots consumed than image features")
+            ctx["info"] = info
+        return ctx["info"]
+
+    def _project_shard(self, ctx, feats, tiles_per_image, lo, hi, out_view=None):
+        """Text conditioning + Q-Former for images [lo, hi): one text row set per SAMPLE, shared by its tiles;
+        the reference conditions image i on ids[i] (:163-176) and pads to the BATCH-GLOBAL max (quirk Q3), so L
+        comes from the global plan.  Returns bf16 [sum T_i * 32, 4096] (written into out_view when given)."""
+        model = self.get_model()
+        embed, proj = model.embed_tokens.weight, model.mm_projector
+        dev = embed.device
+        info = self._plan_info(ctx)
+        if hi <= lo:
+            return torch.empty((0, embed.shape[1]), dtype=torch.bfloat16, device=dev)
+        L_text = max(info["text_len"][:ctx["n_images"]])
+        text_rows = sum(info["text_len"][lo:hi])
+        text_emb, text_off = text_gather(ctx["ids"], embed, ctx["plan"], text_rows, lo, hi)
+        if text_emb.dtype != torch.bfloat16:
+            text_emb = text_emb.to(torch.bfloat16)
+        tile_sample = torch.repeat_interleave(torch.arange(hi - lo, dtype=torch.int32),
+                                              torch.tensor(tiles_per_image[lo:hi])).to(dev)
+        text = TextPack(text_emb, text_off, text_rows, hi - lo, L_text, tile_sample)
+        if out_view is not None:
+            out_view = out_view.view(sum(tiles_per_image[lo:hi]), proj.num_queries, -1)
+        vis_local = proj.forward_packed(feats, text, feats_normed=True, out=out_view)      # [T,32,4096] bf16
+        return vis_local.reshape(-1, vis_local.shape[-1])
+
+    def _splice(self, ctx, vis, position_ids, attention_mask, past_key_values, labels):
+        """merge + splice + pad/collate of the global batch (vis_zephyr_arch.py:214-333, :396-530)."""
+        model = self.get_model()
+        embed = model.embed_tokens.weight
+        dev = embed.device
+        info = self._plan_info(ctx)
         if vis.dtype != embed.dtype:
             vis = vis.to(embed.dtype)
-
-        # ---- merge + splice -----------------------------------------------------------------------
         newline = getattr(model, "image_newline", None)
         if newline is not None:
             newline = newline.detach().to(device=dev, dtype=embed.dtype).contiguous()
         pad_left = getattr(self.config, "tokenizer_padding_side", "right") == "left"
         out_embeds, out_labels, out_mask, out_pos = splice_scatter(
-            input_ids, labels_dev, embed, vis, newline, slots_dev, slot_prefix, n_images, total_vis_rows,
-            plan, info["Lmax"], pad_left)
-
+            ctx["ids"], ctx["labels"], embed, vis, newline, ctx["slots"], ctx["prefix"], ctx["n_images"],
+            ctx["total_vis_rows"], ctx["plan"], info["Lmax"], pad_left)
         new_mask = None
         if attention_mask is not None:
             new_mask = out_mask.to(dtype=attention_mask.dtype)

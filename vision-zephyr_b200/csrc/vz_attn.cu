@@ -419,6 +419,7 @@ int qattn_launch(int mode, const void* q, int q_rs, int q_zrows, const void* k0,
   a.scale = 0.044194173824159216f;  // 1/sqrt(512)
   VZ_ENSURE_DYN_SMEM(qattn32_kernel, QA_SMEM);
   dim3 grid(VZ_QF_HEADS, Z);
+  ProfScope prof(VZ_PROF_QATTN, 0.0, st);
   qattn32_kernel<<<grid, QA_THREADS, QA_SMEM, st>>>(a);
   VZ_LAUNCH_CHECK();
   return VZ_OK;

@@ -465,6 +465,8 @@ int vit_attn_tc_launch(const void* qkv, void* out, int T, cudaStream_t st) {
   // persistent: two CTAs per SM walk the (tile, head, query block) items round-robin
   const int n_items = NQB * VZ_VIT_HEADS * T;
   const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
+  // algorithmic FLOPs: QK^T and PV, 2 * 577 * 577 * 64 each, per (tile, head)
+  ProfScope prof(VZ_PROF_VIT_ATTN, 4.0 * TOK * TOK * HD * VZ_VIT_HEADS * T, st);
   if (poly == 4) {
     VZ_ENSURE_DYN_SMEM(vit_attn_tc_kernel<4>, SMEM_TOTAL);
     vit_attn_tc_kernel<4><<<grid, THREADS, SMEM_TOTAL, st>>>(tmQ, tmKV, tmO, 0.125f, n_items);

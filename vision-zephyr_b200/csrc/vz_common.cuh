@@ -54,6 +54,16 @@ void count_launch();
     }                                                                                                \
   } while (0)
 
+// measurement hook (vz_profile): CUDA events around a launch, tagged by kernel family (VZ_PROF_* in vz_b200.h)
+struct ProfScope {
+  cudaEvent_t e1;
+  cudaStream_t st;
+  ProfScope(int tag, double work, cudaStream_t stream);
+  ~ProfScope();
+  ProfScope(const ProfScope&) = delete;
+  ProfScope& operator=(const ProfScope&) = delete;
+};
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // internal launchers shared between translation units

@@ -23,16 +23,36 @@ static std::atomic<uint32_t> g_sk_epoch{0};   // stream-K hand-over flags carry 
 constexpr size_t kSkFlagBytes = 8192;         // >= SMs * epilogue warps * 4 bytes
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-// Optional measurement hook (bench.py): CUDA events around every tcgen05 GEMM launch, on the
-// launching stream, plus the algorithmic FLOPs of that launch.  Off by default.
-struct GemmProf {
+// Optional measurement hook (bench.py): CUDA events around every kernel launch of the library, on the
+// launching stream, tagged by kernel family, plus the algorithmic work (FLOPs or bytes) of that launch.
+// Off by default; a ProfScope costs one relaxed load when off.
+struct Prof {
   std::mutex mu;
-  bool on = false;
+  std::atomic<bool> on{false};
   std::vector<cudaEvent_t> pool;
   size_t used = 0;
-  std::vector<double> flops;
+  std::vector<int> tag;
+  std::vector<double> work;
 };
-static GemmProf g_prof;
+static Prof g_prof;
+
+ProfScope::ProfScope(int tag, double work, cudaStream_t stream) : e1(nullptr), st(stream) {
+  if (!g_prof.on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  while (g_prof.used + 2 > g_prof.pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    g_prof.pool.push_back(e);
+  }
+  cudaEvent_t e0 = g_prof.pool[g_prof.used++];
+  e1 = g_prof.pool[g_prof.used++];
+  g_prof.tag.push_back(tag);
+  g_prof.work.push_back(work);
+  cudaEventRecord(e0, st);
+}
+ProfScope::~ProfScope() {
+  if (e1) cudaEventRecord(e1, st);
+}
 
 namespace {
 
@@ -655,21 +675,7 @@ int launch_tc(const vz_gemm_args& a, const GemmDev& p_in, int num_sms, cudaStrea
     }
   }
   const int grid = (p.sk_tiles > 0 ? workers : (tiles < workers ? (int)tiles : workers)) * (TWO ? 2 : 1);
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (g_prof.on) {
-    std::lock_guard<std::mutex> lk(g_prof.mu);
-    if (g_prof.used + 2 > g_prof.pool.size()) {
-      for (int i = 0; i < 2; ++i) {
-        cudaEvent_t e;
-        VZ_CUDA_CHECK(cudaEventCreate(&e));
-        g_prof.pool.push_back(e);
-      }
-    }
-    e0 = g_prof.pool[g_prof.used++];
-    e1 = g_prof.pool[g_prof.used++];
-    g_prof.flops.push_back(2.0 * a.M * (double)a.N * a.K * p.batch);
-    VZ_CUDA_CHECK(cudaEventRecord(e0, st));
-  }
+  ProfScope prof(VZ_PROF_GEMM, 2.0 * a.M * (double)a.N * a.K * p.batch, st);
   if (TWO) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -687,7 +693,6 @@ int launch_tc(const vz_gemm_args& a, const GemmDev& p_in, int num_sms, cudaStrea
     gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO, BKN><<<grid, kThreads, C::SMEM_BYTES, st>>>(tmA, tmB, p);
     VZ_LAUNCH_CHECK();
   }
-  if (e1) VZ_CUDA_CHECK(cudaEventRecord(e1, st));
   return VZ_OK;
 }
 
@@ -866,31 +871,47 @@ int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
 
 extern "C" long long vz_kernel_launches(void) { return vz::g_launches.load(); }
 
-extern "C" int vz_gemm_profile(int enable) {
+extern "C" int vz_profile(int enable) {
   std::lock_guard<std::mutex> lk(vz::g_prof.mu);
-  vz::g_prof.on = enable != 0;
+  vz::g_prof.on.store(enable != 0);
   vz::g_prof.used = 0;
-  vz::g_prof.flops.clear();
+  vz::g_prof.tag.clear();
+  vz::g_prof.work.clear();
   return VZ_OK;
 }
 
-// Synchronises the recorded events and returns launches, summed milliseconds and summed FLOPs.
-extern "C" int vz_gemm_profile_read(long long* launches, double* total_ms, double* total_flops) {
+// Synchronises the recorded events and returns launches, summed milliseconds and summed work of one tag.
+extern "C" int vz_profile_read(int tag, long long* launches, double* total_ms, double* total_work) {
   std::lock_guard<std::mutex> lk(vz::g_prof.mu);
-  double ms = 0, fl = 0;
+  double ms = 0, wk = 0;
+  long long cnt = 0;
   const size_t n = vz::g_prof.used / 2;
   for (size_t i = 0; i < n; ++i) {
+    if (vz::g_prof.tag[i] != tag) continue;
     float t = 0;
     cudaError_t e = cudaEventSynchronize(vz::g_prof.pool[2 * i + 1]);
     if (e == cudaSuccess) e = cudaEventElapsedTime(&t, vz::g_prof.pool[2 * i], vz::g_prof.pool[2 * i + 1]);
     if (e != cudaSuccess) return vz::cuda_fail(e);
     ms += t;
-    fl += vz::g_prof.flops[i];
+    wk += vz::g_prof.work[i];
+    ++cnt;
   }
-  if (launches) *launches = (long long)n;
+  if (launches) *launches = cnt;
   if (total_ms) *total_ms = ms;
-  if (total_flops) *total_flops = fl;
+  if (total_work) *total_work = wk;
   return VZ_OK;
+}
+
+extern "C" const char* vz_profile_tag_name(int tag) {
+  static const char* names[VZ_PROF_COUNT] = {"gemm_bf16_tcgen05", "vit_attn_tc", "fuse", "preprocess_h", "preprocess_v",
+                                             "preprocess_fused", "splice_scatter", "qattn", "softmax_rows", "layernorm",
+                                             "text_gather", "other"};
+  return (tag >= 0 && tag < VZ_PROF_COUNT) ? names[tag] : "?";
+}
+
+extern "C" int vz_gemm_profile(int enable) { return vz_profile(enable); }
+extern "C" int vz_gemm_profile_read(long long* launches, double* total_ms, double* total_flops) {
+  return vz_profile_read(VZ_PROF_GEMM, launches, total_ms, total_flops);
 }
 
 extern "C" int vz_gemm_stats_partials(int M, int N) { return vz::gemm_stats_partials(M, N); }

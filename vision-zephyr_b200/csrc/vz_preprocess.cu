@@ -661,7 +661,10 @@ extern "C" int vz_preprocess(const vz_image_desc* images, int n_images, const vz
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   VZ_ENSURE_DYN_SMEM(preprocess_kernel, 220 * 1024);
   dim3 grid(24, n_tiles);
-  preprocess_kernel<<<grid, PP_THREADS, smem, st>>>(a);
+  {
+    ProfScope prof(VZ_PROF_PRE_FUSED, 0.0, st);
+    preprocess_kernel<<<grid, PP_THREADS, smem, st>>>(a);
+  }
   VZ_LAUNCH_CHECK();
   return VZ_OK;
 }
@@ -689,7 +692,10 @@ extern "C" int vz_preprocess2(const vz_image_desc* images, int n_images, const v
   if (smem_h > 200 * 1024) return VZ_ERR_UNSUPPORTED;
   VZ_ENSURE_DYN_SMEM(preprocess_h_kernel, 200 * 1024);
   dim3 grid_h((max_out_w + HP_THREADS - 1) / HP_THREADS, (max_rows + HP_ROWS - 1) / HP_ROWS, n_hviews);
-  preprocess_h_kernel<<<grid_h, HP_THREADS, smem_h, st>>>(h);
+  {
+    ProfScope prof(VZ_PROF_PRE_H, 0.0, st);
+    preprocess_h_kernel<<<grid_h, HP_THREADS, smem_h, st>>>(h);
+  }
   VZ_LAUNCH_CHECK();
   // ---- vertical pass + normalise + patchify ----
   VArgs v;
@@ -700,7 +706,10 @@ extern "C" int vz_preprocess2(const vz_image_desc* images, int n_images, const v
   if (smem_v > 200 * 1024) return VZ_ERR_UNSUPPORTED;
   VZ_ENSURE_DYN_SMEM(preprocess_v_kernel, 200 * 1024);
   dim3 grid_v(24, n_tiles);
-  preprocess_v_kernel<<<grid_v, PP_THREADS, smem_v, st>>>(v);
+  {
+    ProfScope prof(VZ_PROF_PRE_V, 0.0, st);
+    preprocess_v_kernel<<<grid_v, PP_THREADS, smem_v, st>>>(v);
+  }
   VZ_LAUNCH_CHECK();
   return VZ_OK;
 }

@@ -266,6 +266,7 @@ int row_stats_launch(const void* x, int ldx, int M, int D, float* stats, cudaStr
 
 int softmax_rows_launch(const float* s, void* p, int rows, int n, float scale, cudaStream_t st) {
   if (n > 24 * 32) return VZ_ERR_UNSUPPORTED;
+  ProfScope prof(VZ_PROF_SOFTMAX, (double)rows * n * 6.0, st);   // f32 scores in, bf16 probabilities out
   softmax_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(s, reinterpret_cast<__nv_bfloat16*>(p), rows, n,
                                                       scale * 1.4426950408889634f);
   VZ_LAUNCH_CHECK();
@@ -279,6 +280,7 @@ int layernorm_launch(const void* x, int ldx, const float* g, const float* b, voi
   if (D % 8 != 0 || D > 8192 || (ldx & 7) || (ldo & 7)) return VZ_ERR_UNSUPPORTED;
   if (!aligned16(x) || !aligned16(out) || !aligned16(g) || !aligned16(b)) return VZ_ERR_BAD_ARG;
   int threads = ((D / 8 + 31) / 32) * 32;
+  ProfScope prof(VZ_PROF_LAYERNORM, (double)M * D * 4.0, st);
   layernorm_kernel<<<M, threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, g, b,
                                           reinterpret_cast<__nv_bfloat16*>(out), ldo, D, eps,
                                           row_map, rows_per_map > 0 ? rows_per_map : 1);
@@ -290,6 +292,8 @@ int fuse_launch(const void* const* hs21, int T, const float* g, const float* b, 
                 cudaStream_t st) {
   FuseArgs a;
   for (int i = 0; i < 21; ++i) a.hs[i] = reinterpret_cast<const __nv_bfloat16*>(hs21[i]);
+  // algorithmic bytes: 21 hidden-state rows of 1024 bf16 read + one fused row of 5120 bf16 written, per patch
+  ProfScope prof(VZ_PROF_FUSE, (double)T * VZ_VIT_PATCHES * (21.0 * VZ_VIT_WIDTH + VZ_FUSED_WIDTH) * 2.0, st);
   fuse_kernel<<<T * VZ_VIT_PATCHES, 128, 0, st>>>(a, g, b, reinterpret_cast<__nv_bfloat16*>(out), 1e-5f);
   VZ_LAUNCH_CHECK();
   return VZ_OK;

@@ -339,6 +339,7 @@ extern "C" int vz_text_gather(const int64_t* input_ids, int B, int S, const void
   text_off_kernel<<<1, 32, 0, st>>>(text_len, B, text_off);
   VZ_LAUNCH_CHECK();
   dim3 grid((S + 31) / 32, B);
+  ProfScope prof(VZ_PROF_TEXT_GATHER, 0.0, st);
   text_gather_kernel<<<grid, 256, 0, st>>>(input_ids, B, S, reinterpret_cast<const uint4*>(embed_table),
                                            (int)(row_bytes / 16), text_off, reinterpret_cast<uint4*>(text_emb));
   VZ_LAUNCH_CHECK();
@@ -382,6 +383,7 @@ extern "C" int vz_splice_scatter(const int64_t* input_ids, const int64_t* labels
   long blocks = (items + 7) / 8;
   const long cap = (long)sms * 8;  // 8 CTAs of 256 threads per SM
   if (blocks > cap) blocks = cap;
+  ProfScope prof(VZ_PROF_SPLICE_SCATTER, 0.0, reinterpret_cast<cudaStream_t>(stream));
   splice_scatter_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   VZ_LAUNCH_CHECK();
   return VZ_OK;

@@ -25,27 +25,43 @@ import torch.distributed as dist
 
 
 def shard_images(tiles_per_image: Sequence[int], world_size: int) -> List[Tuple[int, int]]:
-    """Contiguous [begin, end) image ranges per rank, balanced by tile count (greedy on the prefix)."""
+    """Contiguous [begin, end) image ranges per rank that MINIMISE the largest tile count of any rank (the
+    step time is set by the slowest rank).  No rank is left empty while there are at least as many images as
+    ranks.  Binary search on the cap + a greedy left-to-right fill, O(n log sum)."""
     n = len(tiles_per_image)
-    total = sum(tiles_per_image)
-    bounds, acc, start = [], 0, 0
-    prefix = [0]
-    for t in tiles_per_image:
-        prefix.append(prefix[-1] + t)
-    for r in range(world_size):
-        if r == world_size - 1:
-            end = n
+    if world_size <= 0:
+        raise ValueError("world_size must be positive")
+    tiles = [int(t) for t in tiles_per_image]
+
+    def cut(cap):
+        """greedy bounds under `cap` tiles per rank, keeping one image for every later rank; None if infeasible"""
+        bounds, start = [], 0
+        for r in range(world_size):
+            later = world_size - 1 - r
+            if r == world_size - 1:
+                end = n
+            else:
+                limit = max(n - later, start) if n - start > later else start   # images this rank may take at most
+                end, acc = start, 0
+                while end < limit and acc + tiles[end] <= cap:
+                    acc += tiles[end]
+                    end += 1
+                if end == start and n - start > later:        # must take one image but it does not fit the cap
+                    return None
+            if sum(tiles[start:end]) > cap:
+                return None
+            bounds.append((start, end))
+            start = end
+        return bounds
+
+    lo, hi = max(tiles, default=0), max(sum(tiles), 0)
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if cut(mid) is None:
+            lo = mid + 1
         else:
-            target = total * (r + 1) / world_size
-            end = start
-            while end < n and abs(prefix[end + 1] - target) <= abs(prefix[end] - target):
-                end += 1
-            # leave at least one image for each remaining rank when possible
-            end = min(end, n - min(world_size - 1 - r, n - end) if n - end >= world_size - 1 - r else end)
-        end = max(end, start)
-        bounds.append((start, end))
-        start = end
-    return bounds
+            hi = mid
+    return cut(lo)
 
 
 def gather_visual_tokens(local_rows: torch.Tensor, rows_per_rank: Sequence[int], group=None) -> torch.Tensor:
@@ -101,25 +117,48 @@ class PeerGather:
 
 
 _peer_cache = {}
+TRANSPORT_PEER, TRANSPORT_NCCL = "peer_store", "nccl_all_gather"
+
+
+def peer_transport_requested() -> str:
+    """VZ_PEER_GATHER: '1' = peer stores REQUIRED (fail loudly when unavailable), '0' = all-gather,
+    unset / 'auto' = peer stores when every rank can set them up, else all-gather."""
+    v = os.environ.get("VZ_PEER_GATHER", "auto").lower()
+    return {"1": "require", "0": "off"}.get(v, "auto")
 
 
 def peer_gather_for(rows_total: int, width: int, dtype, device, group=None):
-    """A PeerGather big enough for `rows_total` rows, or None when the peer transport is not usable
-    (CPU / gloo group, symmetric memory missing, VZ_PEER_GATHER=0).  Collective: every rank of the
-    group must call it with the same arguments (they derive them from the global shard plan)."""
-    if os.environ.get("VZ_PEER_GATHER", "1") == "0" or torch.device(device).type != "cuda":
+    """A PeerGather big enough for `rows_total` rows, or None when the all-gather transport is to be used
+    (CPU / gloo group, VZ_PEER_GATHER=0, or symmetric memory unavailable on ANY rank).  Collective: every
+    rank of the group calls it with the same arguments (derived from the global shard plan).  The ranks
+    AGREE on the outcome (all_reduce MIN of a success flag) before the decision is cached, so a failure on
+    a subset of ranks can never leave the others waiting in a barrier.  With VZ_PEER_GATHER=1 an unavailable
+    peer transport raises instead of falling back."""
+    mode = peer_transport_requested()
+    if mode == "off" or torch.device(device).type != "cuda":
+        if mode == "require" and torch.device(device).type != "cuda":
+            raise RuntimeError("VZ_PEER_GATHER=1 but the model is not on a CUDA device")
         return None
     key = (id(group), str(device), width, dtype)
     pg = _peer_cache.get(key)
     if pg is False:
         return None
     if pg is None or pg.rows < rows_total:
+        new, err = None, None
         try:
-            pg = PeerGather(max(rows_total, pg.rows * 2 if pg else 0), width, dtype, device, group)
-        except Exception as e:  # no P2P mapping on this box / group: fall back to the collective, once
+            new = PeerGather(max(rows_total, pg.rows * 2 if pg else 0), width, dtype, device, group)
+        except Exception as e:   # no P2P mapping on this box / group
+            err = e
+        ok = torch.tensor([1 if new is not None else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            why = f"{type(err).__name__}: {err}" if err is not None else "another rank could not map the peer buffer"
+            if mode == "require":
+                raise RuntimeError(f"vision_zephyr_b200: VZ_PEER_GATHER=1 but the peer-store transport is unavailable ({why})")
             import warnings
-            warnings.warn(f"vision_zephyr_b200: peer gather unavailable ({type(e).__name__}: {e}); using all_gather")
+            warnings.warn(f"vision_zephyr_b200: peer gather unavailable ({why}); every rank uses all_gather")
             _peer_cache[key] = False
             return None
+        pg = new
         _peer_cache[key] = pg
     return pg

@@ -1,0 +1,108 @@
+"""The two B200 mixins applied to HF Mistral: the LLM-side callers of the path.
+
+This is what INTEGRATION.md section 1 produces when applied to the reference's
+  VisZephyrConfig / VisZephyrModel / VisZephyrForCausalLM   vis_zephyr/model/language_model/vis_zephyr.py:19-170
+i.e. the SAME class statements with the B200 mixins as bases.  The LLM body itself stays HF Mistral
+(out of scope); only the hand-over is here: forward / generate call
+prepare_inputs_labels_for_multimodal and pass the 6-tuple on (vis_zephyr.py:76-98, :124-142), and
+generation re-attaches `images` / `images_size` to the step inputs (:144-168).
+Used by tests/test_gpu_llm.py, bench.py's c5_prefill_b8 workload and tools/; save_mm_projector is the
+pre-training checkpoint writer of train/vis_zephyr_trainer.py:326-343.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+from transformers import MistralConfig, MistralForCausalLM, MistralModel
+
+from .arch import VisZephyrB200MetaForCausalLM, VisZephyrB200MetaModel
+
+_TUPLE_KEYS = ("input_ids", "position_ids", "attention_mask", "past_key_values", "inputs_embeds", "labels")
+
+
+class VisZephyrB200Config(MistralConfig):
+    model_type = "vis_zephyr_b200"
+
+
+class VisZephyrB200Model(VisZephyrB200MetaModel, MistralModel):
+    config_class = VisZephyrB200Config
+
+    def __init__(self, config: MistralConfig):
+        super().__init__(config)
+
+
+class VisZephyrB200ForCausalLM(MistralForCausalLM, VisZephyrB200MetaForCausalLM):
+    config_class = VisZephyrB200Config
+
+    def __init__(self, config):
+        super(MistralForCausalLM, self).__init__(config)       # skip MistralForCausalLM's own body
+        self.model = VisZephyrB200Model(config)
+        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+        self.post_init()
+
+    def get_model(self):
+        return self.model
+
+    def _multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels, images, images_size):
+        out = self.prepare_inputs_labels_for_multimodal(input_ids, position_ids, attention_mask, past_key_values,
+                                                        labels, images, images_size)
+        return dict(zip(_TUPLE_KEYS, out))
+
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None,
+                inputs_embeds=None, labels=None, use_cache=None, output_attentions=None,
+                output_hidden_states=None, images=None, images_size=None, return_dict=None, **kwargs):
+        args = dict(input_ids=input_ids, position_ids=position_ids, attention_mask=attention_mask,
+                    past_key_values=past_key_values, inputs_embeds=inputs_embeds, labels=labels)
+        if inputs_embeds is None:
+            args = self._multimodal(input_ids, position_ids, attention_mask, past_key_values, labels, images, images_size)
+        # extra keyword arguments (e.g. logits_to_keep) go through to HF Mistral; the reference drops them
+        return super().forward(use_cache=use_cache, output_attentions=output_attentions,
+                               output_hidden_states=output_hidden_states, return_dict=return_dict, **args, **kwargs)
+
+    @torch.no_grad()
+    def generate(self, input_ids=None, images=None, images_size=None, **kwargs):
+        position_ids = kwargs.pop("position_ids", None)
+        attention_mask = kwargs.pop("attention_mask", None)
+        if "inputs_embeds" in kwargs:
+            raise NotImplementedError("`inputs_embeds` is not supported in this generate function.")
+        if images is not None:
+            mm = self._multimodal(input_ids, position_ids, attention_mask, None, None, images, images_size)
+            position_ids, attention_mask, inputs_embeds = mm["position_ids"], mm["attention_mask"], mm["inputs_embeds"]
+        else:
+            inputs_embeds = self.get_model().embed_tokens(input_ids)
+        return super().generate(position_ids=position_ids, attention_mask=attention_mask,
+                                inputs_embeds=inputs_embeds, **kwargs)
+
+    def prepare_inputs_for_generation(self, input_ids, past_key_values=None, inputs_embeds=None, **kwargs):
+        extra = {k: kwargs.pop(k, None) for k in ("images", "images_size")}
+        inputs = super().prepare_inputs_for_generation(input_ids=input_ids, past_key_values=past_key_values,
+                                                       inputs_embeds=inputs_embeds, **kwargs)
+        inputs.update({k: v for k, v in extra.items() if v is not None})
+        return inputs
+
+
+def mm_adapter_state(model: nn.Module, keys_to_match=("mm_projector", "vision_resampler")) -> Dict[str, torch.Tensor]:
+    """The tensors train/vis_zephyr_trainer.py:326-337 selects for mm_projector.bin: every named parameter
+    whose name contains one of the keys, under its full name (e.g. 'model.mm_projector.blocks.0.norm1.weight')."""
+    return {k: p.detach().cpu().clone() for k, p in model.named_parameters() if any(m in k for m in keys_to_match)}
+
+
+def save_mm_projector(model: nn.Module, path: str) -> None:
+    """Write an mm_projector.bin that both the reference (vis_zephyr_arch.py:95-102, model/builder.py:118-120)
+    and initialize_vision_modules here load by name."""
+    torch.save(mm_adapter_state(model), path)
+
+
+def random_mistral_config(num_hidden_layers: int = 32, **over) -> VisZephyrB200Config:
+    """Zephyr-7B-beta / Mistral-7B geometry (the shipped config.json:10-35) with the mm_* keys of the path."""
+    from .runtime import DEFAULT_PINPOINTS
+    kw = dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=num_hidden_layers, num_attention_heads=32,
+              num_key_value_heads=8, vocab_size=32000, max_position_embeddings=32768, rms_norm_eps=1e-5,
+              rope_theta=10000.0, sliding_window=None, pad_token_id=2, bos_token_id=1, eos_token_id=2,
+              mm_vision_tower="openai/clip-vit-large-patch14-336", mm_vision_select_layer="-2,-5,-8,-11,6",
+              mm_vision_select_feature="patch", mm_patch_merge_type="flat", image_aspect_ratio="anyres",
+              mm_grid_pinpoints=DEFAULT_PINPOINTS, tokenizer_padding_side="right")
+    kw.update(over)
+    return VisZephyrB200Config(**kw)

@@ -174,6 +174,13 @@ class QFormerB200(nn.Module):
                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """feats bf16 [T,576,5120] -> bf16 [T,32,4096]."""
         lib = _lib.load()
+        if torch.is_grad_enabled() and (feats.requires_grad or (text is not None and text.text_emb.requires_grad)
+                                        or any(p.requires_grad for p in self.parameters())):
+            # the kernels run on detached, packed weights: the result has no grad_fn, so training would
+            # silently stop updating mm_projector (train/train.py:817-836).  Refuse instead.
+            raise _lib.VzError(
+                "QFormerB200.forward is inference-only: call it under torch.no_grad() or freeze the projector "
+                "(requires_grad_(False)); the backward of the B200 path is not built (SURVEY.md 8(f) rank 4)")
         self._ensure_packed()
         if not feats.is_cuda:
             raise _lib.VzError("QFormerB200 runs on CUDA only (no CPU fallback)")

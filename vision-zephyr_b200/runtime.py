@@ -47,6 +47,7 @@ class VisionEmbeddingPath(VisZephyrB200MetaForCausalLM):
             inner = _Inner(self.config)
         self.model = inner.to_empty(device=device)
         self.model.to(dtype)
+        self.model.requires_grad_(False)      # an inference host: the projector's forward refuses to run with grads on
         self.device = torch.device(device)
         self.dtype = dtype
 

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from types import SimpleNamespace
 from typing import Dict, List, Optional
 
@@ -32,16 +33,40 @@ def default_clip_config():
 
 
 class Workspace:
-    """Grow-only device scratch shared by the tower and the projector of one process/stream."""
+    """Grow-only device scratch of one module, ONE BUFFER PER (device, CUDA stream).
+
+    The C ABI is re-entrant (every call works inside the workspace it is handed, on the stream it is
+    handed); what the Python layer has to guarantee is that two concurrent calls never share a workspace.
+    Activations, LayerNorm statistics and the stream-K hand-over slots all live in it, so it is keyed by the
+    caller's current stream: two threads driving one model on two streams (the reference's
+    serve/api.py:161-177 generate-in-a-thread case) get disjoint buffers.  A buffer is allocated while its
+    stream is current, so PyTorch's caching allocator orders its reuse after the kernels of that stream when
+    it is replaced by a larger one."""
 
     def __init__(self):
-        self.buf: Optional[torch.Tensor] = None
+        self._bufs: Dict[tuple, torch.Tensor] = {}
+        self._lock = threading.Lock()
 
     def get(self, nbytes: int, device) -> torch.Tensor:
-        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != torch.device(device):
-            self.buf = None
-            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
-        return self.buf
+        device = torch.device(device)
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device(),
+               torch.cuda.current_stream(device).cuda_stream)
+        with self._lock:
+            buf = self._bufs.get(key)
+            if buf is None or buf.numel() < nbytes:
+                self._bufs.pop(key, None)
+                buf = None
+                buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+                self._bufs[key] = buf
+        return buf
+
+    @property
+    def buf(self):
+        """the current stream's buffer (tests / tools)"""
+        for k, v in self._bufs.items():
+            if k[2] == torch.cuda.current_stream().cuda_stream:
+                return v
+        return None
 
 
 class CLIPVisionTowerB200(nn.Module):
