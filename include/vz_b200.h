@@ -209,6 +209,18 @@ int vz_preprocess2(const vz_image_desc* images, int n_images, const vz_prim* pri
                    long long scratch_pixels, int max_span_px, int max_rows, int max_out_w, int max_ksize,
                    void* stream);
 
+/* The default form whenever something is resampled: same interface and same bits as vz_preprocess2, with the
+ * tap loops on the 4-way byte dot product (coefficients split into three byte limbs, windows aligned down to
+ * four pixels / four rows).  The intermediate in `scratch` is PLANAR: per view, [channel][ceil(rows / 4)][out_w]
+ * 32-bit words, one word = four vertically consecutive u8 pixels of one channel, first word at `offset`;
+ * scratch_words >= the largest offset + 3 * ceil(rows / 4) * out_w.  max_span_px = the widest source window
+ * any 128 consecutive output columns of any view need.  VZ_ERR_UNSUPPORTED for ksize > 58 (use vz_preprocess2). */
+int vz_preprocess3(const vz_image_desc* images, int n_images, const vz_prim* prims, int n_prims,
+                   const vz_hview_desc* hviews, int n_hviews, const vz_tile_desc* tiles, int n_tiles,
+                   const int32_t* tables, const float* lut768, int out_mode, void* out, void* scratch,
+                   long long scratch_words, int max_span_px, int max_rows, int max_out_w, int max_ksize,
+                   void* stream);
+
 /* f32/bf16 pixel_values [T,3,336,336] -> bf16 patches [T*576,592]; the API-compatible entry of
  * CLIPVisionTower.forward (vision_encoder/vision_encoder.py:80-117) when the caller already holds
  * reference-style pixel tensors.  src_is_f32: 1 = float32, 0 = bf16.                            */

@@ -158,14 +158,15 @@ def test_process_images_modes_match_reference_golden(golden_dir):
             assert sha(got[si][0].cpu().numpy().astype(np.float32)) == str(g[f"s{si}_{mode}_sha"]), (si, mode)
 
 
-def test_two_kernel_and_fused_forms_agree(golden_dir, monkeypatch):
-    """vz_preprocess2 (horizontal pass into an RGBX intermediate, then vertical pass) == vz_preprocess (fused, one CTA
-    per band) bit for bit, on anyres + fixed-mode views with visual prompts, in both output layouts"""
+def test_dp4a_two_kernel_and_fused_forms_agree(golden_dir, monkeypatch):
+    """vz_preprocess3 (dp4a: limb-split coefficients, planar intermediate, windows aligned to four) ==
+    vz_preprocess2 (one multiply per tap, RGBX intermediate) == vz_preprocess (fused, one CTA per band) bit for bit,
+    on anyres + fixed-mode views with visual prompts and canvas padding, in both output layouts"""
     import vision_zephyr_b200 as vz
     from vision_zephyr_b200 import anyres
     from vision_zephyr_b200.preprocess import build_plan, run_plan
     lut = _lut(golden_dir)
-    sizes = [(1000, 900), (637, 336), (336, 900), (1344, 1344), (301, 640)]
+    sizes = [(1000, 900), (637, 336), (336, 900), (1344, 1344), (301, 640), (1920, 804), (250, 180), (333, 1000)]
     imgs = [torch.from_numpy(synth_image(60 + i, w, h)).cuda() for i, (w, h) in enumerate(sizes)]
     layer = np.zeros((900, 1000, 4), np.uint8)
     layer[100:700, 50:900] = (20, 250, 30, 140)
@@ -173,16 +174,35 @@ def test_two_kernel_and_fused_forms_agree(golden_dir, monkeypatch):
     prompts += [[] for _ in sizes[1:]]
     views, canvases = [], []
     for i, (w, h) in enumerate(sizes):
-        if i < 4:
+        if i < 4 or i in (5, 6):
             views.append(anyres.anyres_views((w, h), PINPOINTS_C3)[0]); canvases.append(None)
         else:
-            v, c = anyres.fixed_view((w, h), "pad"); views.append(v); canvases.append(c)
+            v, c = anyres.fixed_view((w, h), "pad" if i == 4 else "square"); views.append(v); canvases.append(c)
     plan = build_plan(imgs, views, lut, prompts, canvases)
     assert plan.max_ksize > 1 and plan.n_hviews >= len(sizes)
+    monkeypatch.delenv("VZ_PRE_FUSED", raising=False)
     for mode in ("patches", "chw"):
-        monkeypatch.delenv("VZ_PRE_FUSED", raising=False)
+        monkeypatch.setenv("VZ_PRE_FORM", "dp")
+        dp = run_plan(plan, mode).clone()
+        monkeypatch.setenv("VZ_PRE_FORM", "two")
         two = run_plan(plan, mode).clone()
-        monkeypatch.setenv("VZ_PRE_FUSED", "1")
+        monkeypatch.setenv("VZ_PRE_FORM", "fused")
         fused = run_plan(plan, mode)
         torch.cuda.synchronize()
         assert torch.equal(two, fused), mode
+        bad = (dp != two)
+        assert not bad.any(), (mode, int(bad.sum()), bad.nonzero()[:8].tolist())
+
+
+def test_dp4a_form_large_downscale_and_upscale(golden_dir, monkeypatch):
+    """the dp4a form at the ends of its range: 37-tap windows (1920 -> 336, 10 groups per row) and an upscale
+    (7-tap windows, 3 groups), against the oracle (== Pillow)"""
+    import vision_zephyr_b200 as vz
+    from oracle import pil_ops as P
+    lut = _lut(golden_dir)
+    monkeypatch.setenv("VZ_PRE_FORM", "dp")
+    for i, (w, h) in enumerate([(1920, 1500), (150, 130), (2600, 400)]):
+        img = synth_image(80 + i, w, h)
+        got = vz.process_fixed_images([torch.from_numpy(img).cuda()], lut, out_mode="chw", mode="resize")[0][0]
+        ref = P.normalize_lut(P.process_images_u8(img, "resize")[None], lut)[0]
+        assert np.array_equal(got.cpu().numpy(), ref), (w, h)

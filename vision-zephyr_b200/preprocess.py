@@ -93,6 +93,7 @@ class PreprocessPlan:
     n_hviews: int = 0
     scratch_pixels: int = 0
     max_span_px: int = 1
+    max_span128_px: int = 1
     max_rows: int = 1
     max_out_w: int = 1
     scratch: Optional[torch.Tensor] = None
@@ -116,7 +117,7 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
     prim_list, tile_list, keep = [], [], []
     tiles_per_image, sizes = [], []
     max_w, algo = 1, 0
-    hview_index, hview_list, scratch_px, max_span, max_rows, max_out_w = {}, [], 0, 1, 1, 1
+    hview_index, hview_list, scratch_px, max_span, max_rows, max_out_w, max_span128 = {}, [], 0, 1, 1, 1, 1
     for i, im in enumerate(images):
         if im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3 or not im.is_cuda:
             raise ValueError("images must be uint8 CUDA tensors of shape [H, W, 3]")
@@ -184,8 +185,11 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
                 hvd = _lib.HViewDesc()
                 hvd.image, hvd.tab_h, hvd.out_w, hvd.rows, hvd.offset = i, t.tab_h, v["out_w"], cH, scratch_px
                 hview_list.append(hvd)
-                scratch_px += cH * v["out_w"]
+                # room for both intermediate layouts: RGBX [rows][out_w] (vz_preprocess2) and planar
+                # [3][ceil(rows / 4)][out_w] (vz_preprocess3)
+                scratch_px += max(cH, 3 * ((cH + 3) // 4)) * v["out_w"]
                 max_span = max(max_span, _max_span(cW, v["out_w"], filt))
+                max_span128 = max(max_span128, _max_span(cW, v["out_w"], filt, 128))
                 max_rows, max_out_w = max(max_rows, cH), max(max_out_w, v["out_w"])
             t.hview = hview_index[hk]
             tile_list.append(t)
@@ -205,6 +209,7 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
     plan.hviews_dev = _struct_array_to_dev(hview_arr, device)
     plan.n_hviews, plan.scratch_pixels = len(hview_list), scratch_px
     plan.max_span_px, plan.max_rows, plan.max_out_w = max_span, max_rows, max_out_w
+    plan.max_span128_px = max_span128
     plan.h2d_bytes = (plan.images_dev.numel() + plan.tiles_dev.numel() + plan.tables_dev.numel() * 4 + plan.hviews_dev.numel() +
                       (plan.prims_dev.numel() if plan.prims_dev is not None else 0) + 768 * 4)
     plan.algorithmic_bytes = algo
@@ -212,23 +217,24 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
 
 
 @lru_cache(maxsize=512)
-def _max_span(in_size: int, out_size: int, filt: str) -> int:
-    """widest source window (in pixels) that 256 consecutive output columns of an axis table read"""
+def _max_span(in_size: int, out_size: int, filt: str, block: int = 256) -> int:
+    """widest source window (in pixels) that `block` consecutive output columns of an axis table read"""
     t = resample_table(in_size, out_size, filt)
     n = int(t[1])
     xmin, cnt = t[2:2 + n], t[2 + n:2 + 2 * n]
     span = 1
-    for x0 in range(0, n, 256):
-        xl = min(x0 + 255, n - 1)
+    for x0 in range(0, n, block):
+        xl = min(x0 + block - 1, n - 1)
         span = max(span, int(xmin[xl] + cnt[xl] - xmin[x0]))
     return span
 
 
 def run_plan(plan: PreprocessPlan, out_mode: str = "patches", out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Launch the preprocess kernels.  out_mode 'patches' -> bf16 [T*576, 592]; 'chw' -> f32 [T,3,336,336].
-    Plans that resample anything take the two-kernel form (vz_preprocess2: horizontal pass once per source row
-    into an RGBX intermediate, then vertical pass + normalise + patchify); plans made of identity views only
-    (fixed-336 inputs) and VZ_PRE_FUSED=1 take the fused kernel (vz_preprocess)."""
+    Plans that resample anything take the dp4a form (vz_preprocess3: horizontal pass once per source row into a
+    planar u8 intermediate, then vertical pass + normalise + patchify, four taps per instruction); VZ_PRE_FORM=two
+    selects the older one-multiply-per-tap pair (vz_preprocess2), kept as a cross-check and for ksize > 58; plans
+    made of identity views only (fixed-336 inputs) and VZ_PRE_FORM=fused / VZ_PRE_FUSED=1 take the fused kernel."""
     lib = _lib.load()
     dev = plan.tiles_dev.device
     T = plan.n_tiles
@@ -242,9 +248,18 @@ def run_plan(plan: PreprocessPlan, out_mode: str = "patches", out: Optional[torc
         mode = _lib.OUT_CHW_F32
     else:
         raise ValueError(out_mode)
-    if plan.max_ksize > 1 and os.environ.get("VZ_PRE_FUSED") != "1":
+    form = os.environ.get("VZ_PRE_FORM", "fused" if os.environ.get("VZ_PRE_FUSED") == "1" else "dp")
+    if plan.max_ksize > 1 and form != "fused":
         if plan.scratch is None or plan.scratch.numel() < plan.scratch_pixels:
             plan.scratch = torch.empty(plan.scratch_pixels, dtype=torch.int32, device=dev)
+        if form == "dp" and (plan.max_ksize + 6) // 4 <= 16:
+            st = lib.vz_preprocess3(_lib.ptr(plan.images_dev), plan.n_images, _lib.ptr(plan.prims_dev), plan.n_prims,
+                                    _lib.ptr(plan.hviews_dev), plan.n_hviews, _lib.ptr(plan.tiles_dev), T,
+                                    _lib.ptr(plan.tables_dev), _lib.ptr(plan.lut_dev), mode, _lib.ptr(out),
+                                    _lib.ptr(plan.scratch), plan.scratch_pixels, plan.max_span128_px, plan.max_rows,
+                                    plan.max_out_w, plan.max_ksize, _lib.stream_ptr())
+            _lib.check(st, "vz_preprocess3")
+            return out
         st = lib.vz_preprocess2(_lib.ptr(plan.images_dev), plan.n_images, _lib.ptr(plan.prims_dev), plan.n_prims,
                                 _lib.ptr(plan.hviews_dev), plan.n_hviews, _lib.ptr(plan.tiles_dev), T,
                                 _lib.ptr(plan.tables_dev), _lib.ptr(plan.lut_dev), mode, _lib.ptr(out),
