@@ -221,6 +221,13 @@ int vz_preprocess3(const vz_image_desc* images, int n_images, const vz_prim* pri
                    long long scratch_words, int max_span_px, int max_rows, int max_out_w, int max_ksize,
                    void* stream);
 
+/* The identity form (BASELINE config 2): every tile is the whole of a 336 x 336 image (no resampling, no
+ * canvas): blend the visual prompts, normalise, patchify, four pixels per thread with 32- / 128-bit loads.
+ * Same bits as vz_preprocess on such a plan.  Image base pointers must be 4-byte, layer pointers 16-byte aligned. */
+int vz_preprocess_identity(const vz_image_desc* images, int n_images, const vz_prim* prims, int n_prims,
+                           const vz_tile_desc* tiles, int n_tiles, const float* lut768, int out_mode, void* out,
+                           void* stream);
+
 /* f32/bf16 pixel_values [T,3,336,336] -> bf16 patches [T*576,592]; the API-compatible entry of
  * CLIPVisionTower.forward (vision_encoder/vision_encoder.py:80-117) when the caller already holds
  * reference-style pixel tensors.  src_is_f32: 1 = float32, 0 = bf16.                            */

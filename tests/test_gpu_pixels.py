@@ -206,3 +206,35 @@ def test_dp4a_form_large_downscale_and_upscale(golden_dir, monkeypatch):
         got = vz.process_fixed_images([torch.from_numpy(img).cuda()], lut, out_mode="chw", mode="resize")[0][0]
         ref = P.normalize_lut(P.process_images_u8(img, "resize")[None], lut)[0]
         assert np.array_equal(got.cpu().numpy(), ref), (w, h)
+
+
+def test_identity_form_matches_fused_kernel(golden_dir, monkeypatch):
+    """config 2 shape (336 x 336 images + visual prompts): the vectorised identity kernel (four pixels per thread)
+    == the fused kernel's per-pixel identity path, bit for bit, in both output layouts"""
+    import vision_zephyr_b200 as vz
+    from vision_zephyr_b200.preprocess import build_plan, run_plan
+    from vision_zephyr_b200 import anyres
+    lut = _lut(golden_dir)
+    rng = np.random.default_rng(3)
+    imgs, prompts = [], []
+    for i in range(5):
+        imgs.append(torch.from_numpy(synth_image(120 + i, 336, 336)).cuda())
+        lay = np.zeros((336, 336, 4), np.uint8)
+        y0, x0 = int(rng.integers(0, 200)), int(rng.integers(0, 200))
+        lay[y0:y0 + 120, x0:x0 + 97] = (int(rng.integers(0, 256)), 255, 7, int(rng.integers(1, 256)))
+        lay2 = rng.integers(0, 256, (336, 336, 4), dtype=np.uint8)          # every alpha value, every pixel
+        plist = [vz.VisualPrompt("rectangle", rgba=(255, 0, 0, 128), bbox=(30.7, 40.2, 200.9, 220.1), width=3),
+                 vz.VisualPrompt("layer", layer=lay), vz.VisualPrompt("layer", layer=lay2),
+                 vz.VisualPrompt("rectangle", rgba=(1, 2, 3, 255), bbox=(-5, -7, 340, 335), width=9)]
+        prompts.append(plist[: i])                                           # 0 .. 4 instances
+    views = [anyres.single_view((336, 336)) for _ in imgs]
+    plan = build_plan(imgs, views, lut, prompts)
+    assert plan.all_identity and plan.max_ksize == 1
+    monkeypatch.delenv("VZ_PRE_FUSED", raising=False)
+    for mode in ("patches", "chw"):
+        monkeypatch.setenv("VZ_PRE_FORM", "dp")
+        new = run_plan(plan, mode).clone()
+        monkeypatch.setenv("VZ_PRE_FORM", "fused")
+        old = run_plan(plan, mode)
+        torch.cuda.synchronize()
+        assert torch.equal(new, old), mode

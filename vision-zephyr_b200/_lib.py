@@ -112,6 +112,7 @@ SYMBOLS = {
     "vz_preprocess": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp]),
     "vz_preprocess2": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, C.c_longlong, _i, _i, _i, _i, _vp]),
     "vz_preprocess3": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, C.c_longlong, _i, _i, _i, _i, _vp]),
+    "vz_preprocess_identity": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "vz_patchify": (_i, [_vp, _i, _i, _vp, _vp]),
     "vz_vit_workspace_bytes": (_sz, [_i]),
     "vz_vit_attention": (_i, [_vp, _vp, _i, _i, _vp]),

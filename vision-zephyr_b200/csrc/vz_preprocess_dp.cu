@@ -370,6 +370,113 @@ __global__ void __launch_bounds__(VT) pre_v_dp_kernel(const VArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Identity form (BASELINE config 2: images that already are 336 x 336, one tile each): blend the visual
+// prompts, normalise, patchify -- no resampling, so nothing is staged: a thread owns FOUR consecutive pixels
+// of a row (three aligned 32-bit source loads, one 128-bit load per overlay layer), the 768-entry LUT sits
+// in shared memory already converted to the output type, and the band leaves through 128-bit stores.
+// ------------------------------------------------------------------------------------------------
+constexpr int IT = 256;
+constexpr int QUADS = BAND * (TILE / 4);   // 1176 four-pixel groups per band
+
+struct IArgs {
+  const vz_image_desc* images;
+  const vz_prim* prims;
+  const vz_tile_desc* tiles;
+  const float* lut;
+  void* out;
+  int out_mode;
+};
+
+__global__ void __launch_bounds__(IT) pre_identity_kernel(const IArgs a) {
+  extern __shared__ __align__(16) uint8_t dp_smem[];
+  const int band = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
+  const vz_image_desc im = a.images[a.tiles[t].image];
+  const bool patches = a.out_mode == VZ_OUT_PATCHES_BF16;
+  const int stage_bytes = patches ? 24 * VZ_PATCH_K * 2 : 3 * BAND * TILE * 4;
+  uint8_t* s_stage = dp_smem;
+  float* s_lutf = reinterpret_cast<float*>(dp_smem + stage_bytes);                 // [768] (chw mode)
+  __nv_bfloat16* s_luth = reinterpret_cast<__nv_bfloat16*>(dp_smem + stage_bytes); // [768] (patch mode)
+  __shared__ vz_prim s_prims[MAX_PRIMS];
+  const int n_prims = im.prim_count < MAX_PRIMS ? im.prim_count : MAX_PRIMS;
+  for (int i = tid; i < n_prims; i += IT) s_prims[i] = a.prims[im.prim_begin + i];
+  for (int i = tid; i < 768; i += IT) {
+    if (patches) s_luth[i] = __float2bfloat16_rn(a.lut[i]);
+    else s_lutf[i] = a.lut[i];
+  }
+  if (patches) {
+    __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(s_stage);
+    for (int i = tid; i < 24 * 4; i += IT) sp[(i >> 2) * VZ_PATCH_K + 588 + (i & 3)] = __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int qd = tid; qd < QUADS; qd += IT) {
+    const int ry = qd / (TILE / 4), xq = qd - ry * (TILE / 4);
+    const int y = band * BAND + ry, x = 4 * xq;
+    const uint32_t* sp32 = reinterpret_cast<const uint32_t*>(im.src + ((size_t)y * TILE + x) * 3);
+    const uint32_t w0 = __ldg(sp32), w1 = __ldg(sp32 + 1), w2 = __ldg(sp32 + 2);
+    // w0 = R0 G0 B0 R1 | w1 = G1 B1 R2 G2 | w2 = B2 R3 G3 B3
+    int r[4], g[4], b[4];
+    r[0] = w0 & 0xff; g[0] = (w0 >> 8) & 0xff; b[0] = (w0 >> 16) & 0xff; r[1] = w0 >> 24;
+    g[1] = w1 & 0xff; b[1] = (w1 >> 8) & 0xff; r[2] = (w1 >> 16) & 0xff; g[2] = w1 >> 24;
+    b[2] = w2 & 0xff; r[3] = (w2 >> 8) & 0xff; g[3] = (w2 >> 16) & 0xff; b[3] = w2 >> 24;
+    for (int pi = 0; pi < n_prims; ++pi) {
+      const vz_prim& p = s_prims[pi];
+      uint32_t ov[4];
+      if (p.type == VZ_PRIM_LAYER) {
+        const uint4 o4 = __ldg(reinterpret_cast<const uint4*>(im.layers + (((size_t)p.layer * TILE + y) * TILE + x) * 4));
+        ov[0] = o4.x; ov[1] = o4.y; ov[2] = o4.z; ov[3] = o4.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ov[i] = rect_covers(p, x + i, y) ? p.rgba : 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int al = (int)(ov[i] >> 24);
+        if (al != 0) {
+          r[i] = blend_over(r[i], (int)(ov[i] & 0xff), al);
+          g[i] = blend_over(g[i], (int)((ov[i] >> 8) & 0xff), al);
+          b[i] = blend_over(b[i], (int)((ov[i] >> 16) & 0xff), al);
+        }
+      }
+    }
+    if (patches) {
+      __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(s_stage);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int xx = x + i, px = xx / 14, kx = xx - px * 14;
+        __nv_bfloat16* q = sp + px * VZ_PATCH_K + ry * 14 + kx;
+        q[0] = s_luth[r[i]];
+        q[196] = s_luth[256 + g[i]];
+        q[392] = s_luth[512 + b[i]];
+      }
+    } else {
+      float* sf = reinterpret_cast<float*>(s_stage) + ry * TILE + x;   // [3][BAND][336], 16-byte aligned (x % 4 == 0)
+      *reinterpret_cast<float4*>(sf) = make_float4(s_lutf[r[0]], s_lutf[r[1]], s_lutf[r[2]], s_lutf[r[3]]);
+      *reinterpret_cast<float4*>(sf + BAND * TILE) =
+          make_float4(s_lutf[256 + g[0]], s_lutf[256 + g[1]], s_lutf[256 + g[2]], s_lutf[256 + g[3]]);
+      *reinterpret_cast<float4*>(sf + 2 * BAND * TILE) =
+          make_float4(s_lutf[512 + b[0]], s_lutf[512 + b[1]], s_lutf[512 + b[2]], s_lutf[512 + b[3]]);
+    }
+  }
+  __syncthreads();
+  if (patches) {
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) +
+                                          ((size_t)t * VZ_VIT_PATCHES + band * 24) * VZ_PATCH_K);
+    const uint4* s4 = reinterpret_cast<const uint4*>(s_stage);
+    for (int i = tid; i < 24 * VZ_PATCH_K * 2 / 16; i += IT) dst[i] = s4[i];
+  } else {
+    const float* sf = reinterpret_cast<const float*>(s_stage);
+    float* o = reinterpret_cast<float*>(a.out);
+    for (int i = tid; i < 3 * BAND * TILE / 4; i += IT) {
+      const int e = i * 4;
+      const int c = e / (BAND * TILE), rem = e - c * BAND * TILE;
+      const int yy = rem / TILE, xx = rem - yy * TILE;
+      *reinterpret_cast<float4*>(o + (((size_t)t * 3 + c) * TILE + band * BAND + yy) * TILE + xx) =
+          *reinterpret_cast<const float4*>(sf + e);
+    }
+  }
+}
+
 template <int GMAX>
 int launch_h(const HArgs& h, dim3 grid, size_t smem, cudaStream_t st) {
   VZ_ENSURE_DYN_SMEM(pre_h_dp_kernel<GMAX>, 200 * 1024);
@@ -437,6 +544,30 @@ extern "C" int vz_preprocess3(const vz_image_desc* images, int n_images, const v
   {
     ProfScope prof(VZ_PROF_PRE_V, 0.0, st);
     pre_v_dp_kernel<<<grid_v, VT, smem_v, st>>>(v);
+  }
+  VZ_LAUNCH_CHECK();
+  return VZ_OK;
+}
+
+// Every tile is an identity view of a 336 x 336 image (no canvas, tile origin 0): the caller (preprocess.py)
+// knows that from the geometry it built; image and layer base pointers must be 4- / 16-byte aligned.
+extern "C" int vz_preprocess_identity(const vz_image_desc* images, int n_images, const vz_prim* prims, int n_prims,
+                                      const vz_tile_desc* tiles, int n_tiles, const float* lut768, int out_mode,
+                                      void* out, void* stream) {
+  using namespace vz;
+  if (!images || !tiles || !lut768 || !out || n_images <= 0 || n_tiles <= 0) return VZ_ERR_BAD_ARG;
+  if (n_prims > 0 && !prims) return VZ_ERR_BAD_ARG;
+  if (out_mode != VZ_OUT_PATCHES_BF16 && out_mode != VZ_OUT_CHW_F32) return VZ_ERR_BAD_ARG;
+  if (!aligned16(out)) return VZ_ERR_BAD_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  IArgs a;
+  a.images = images; a.prims = prims; a.tiles = tiles; a.lut = lut768; a.out = out; a.out_mode = out_mode;
+  const size_t smem = (size_t)(out_mode == VZ_OUT_CHW_F32 ? 3 * BAND * TILE * 4 : 24 * VZ_PATCH_K * 2) + 768 * 4;
+  VZ_ENSURE_DYN_SMEM(pre_identity_kernel, 64 * 1024);
+  dim3 grid(24, n_tiles);
+  {
+    ProfScope prof(VZ_PROF_PRE_FUSED, 0.0, st);
+    pre_identity_kernel<<<grid, IT, smem, st>>>(a);
   }
   VZ_LAUNCH_CHECK();
   return VZ_OK;

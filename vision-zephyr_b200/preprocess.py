@@ -94,6 +94,7 @@ class PreprocessPlan:
     scratch_pixels: int = 0
     max_span_px: int = 1
     max_span128_px: int = 1
+    all_identity: bool = False   # every tile = the whole of a 336 x 336 image (vz_preprocess_identity)
     max_rows: int = 1
     max_out_w: int = 1
     scratch: Optional[torch.Tensor] = None
@@ -118,6 +119,7 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
     tiles_per_image, sizes = [], []
     max_w, algo = 1, 0
     hview_index, hview_list, scratch_px, max_span, max_rows, max_out_w, max_span128 = {}, [], 0, 1, 1, 1, 1
+    all_identity = True
     for i, im in enumerate(images):
         if im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3 or not im.is_cuda:
             raise ValueError("images must be uint8 CUDA tensors of shape [H, W, 3]")
@@ -170,7 +172,12 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
         if d.prim_count > 32:
             raise ValueError("at most 32 visual-prompt instances per image")
         tiles_per_image.append(len(views[i]))
+        plain_canvas = cv is None or (cv["W"], cv["H"], int(cv["pad_x"]), int(cv["pad_y"])) == (W, H, 0, 0)
+        if (W, H) != (TILE, TILE) or not plain_canvas or im.data_ptr() % 4 or (lay_dev is not None and lay_dev.data_ptr() % 16):
+            all_identity = False
         for v in views[i]:
+            if (v["out_w"], v["out_h"], v["off_x"], v["off_y"], v["tile_x"], v["tile_y"]) != (TILE, TILE, 0, 0, 0, 0):
+                all_identity = False
             t = _lib.TileDesc()
             t.image = i
             t.out_w, t.out_h = v["out_w"], v["out_h"]
@@ -210,6 +217,7 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
     plan.n_hviews, plan.scratch_pixels = len(hview_list), scratch_px
     plan.max_span_px, plan.max_rows, plan.max_out_w = max_span, max_rows, max_out_w
     plan.max_span128_px = max_span128
+    plan.all_identity = all_identity
     plan.h2d_bytes = (plan.images_dev.numel() + plan.tiles_dev.numel() + plan.tables_dev.numel() * 4 + plan.hviews_dev.numel() +
                       (plan.prims_dev.numel() if plan.prims_dev is not None else 0) + 768 * 4)
     plan.algorithmic_bytes = algo
@@ -266,6 +274,12 @@ def run_plan(plan: PreprocessPlan, out_mode: str = "patches", out: Optional[torc
                                 _lib.ptr(plan.scratch), plan.scratch_pixels, plan.max_span_px, plan.max_rows,
                                 plan.max_out_w, plan.max_ksize, _lib.stream_ptr())
         _lib.check(st, "vz_preprocess2")
+        return out
+    if plan.all_identity and form != "fused":
+        st = lib.vz_preprocess_identity(_lib.ptr(plan.images_dev), plan.n_images, _lib.ptr(plan.prims_dev), plan.n_prims,
+                                        _lib.ptr(plan.tiles_dev), T, _lib.ptr(plan.lut_dev), mode, _lib.ptr(out),
+                                        _lib.stream_ptr())
+        _lib.check(st, "vz_preprocess_identity")
         return out
     st = lib.vz_preprocess(_lib.ptr(plan.images_dev), plan.n_images, _lib.ptr(plan.prims_dev), plan.n_prims,
                            _lib.ptr(plan.tiles_dev), T, _lib.ptr(plan.tables_dev), _lib.ptr(plan.lut_dev),
