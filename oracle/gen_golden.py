@@ -7,6 +7,7 @@ What is pinned
   golden_pixels.npz   process_any_resolution_image + CLIPImageProcessor on synthetic images:
                       tile counts, best-fit resolutions, SHA-256 of the f32 pixel tensors
   golden_vip.npz      image_blending (rectangle / mask / arrow) on 336x336 images: SHA-256 of the RGB result
+  golden_vip_shapes.npz  image_blending for ellipse / triangle / scribble / mask contour and random widths / alphas
   golden_merge.npz    _process_image_patches row maps for flat / spatial / spatial_unpad
   golden_splice.npz   prepare_inputs_labels_for_multimodal index/label/mask/position outputs with a
                       stubbed encode_images (integer-coded features)
@@ -115,6 +116,48 @@ def gen_vip():
         out[f"img{i}_final_probe"] = np.asarray(pil)[::31, ::29].copy()
     np.savez_compressed(os.path.join(GOLD, "golden_vip.npz"), **out)
     print("golden_vip.npz written")
+
+
+VIP_SHAPE_CASES = [  # (image W, H, shape, vip_style, alpha, width, python seed, numpy seed)
+    (336, 336, "rectangle", None, None, None, 11, 0), (336, 336, "ellipse", None, None, None, 12, 0),
+    (336, 336, "triangle", None, 128, None, 13, 101), (336, 336, "scribble", None, None, None, 14, 102),
+    (336, 336, "mask contour", None, None, None, 15, 0), (336, 336, "mask", None, None, None, 16, 0),
+    (336, 336, "arrow", None, None, None, 17, 0), (500, 400, "ellipse", None, 200, 2, 18, 0),
+    (500, 400, "triangle", None, None, None, 19, 103), (640, 480, "scribble", None, 99, 1, 20, 104),
+    (500, 400, "arrow", None, None, 3, 21, 0), (500, 400, "mask contour", None, 255, None, 22, 0),
+    (500, 400, "rectangle", "constant", None, 4, 23, 0),
+]
+
+
+def gen_vip_shapes():
+    """image_blending for the shapes golden_vip.npz does not hold (ellipse, triangle, scribble, mask contour) and
+    for RANDOM widths / alphas, segmentation=None (no shapely query is made then): SHA-256 of the RGB result
+    after every instance; three instances compound on each image."""
+    from PIL import Image
+    stub_shapely()
+    from vis_zephyr.model.vip_processor.conversation_generator import image_blending
+    out = {"n_cases": np.array(len(VIP_SHAPE_CASES))}
+    colors = [(255, 0, 0), (0, 255, 0), (0, 0, 255), (255, 165, 0)]
+    for ci, (W, H, shape, style, alpha, width, pseed, nseed) in enumerate(VIP_SHAPE_CASES):
+        img = synth_image(300 + ci, W, H)
+        rng = np.random.default_rng(4000 + ci)
+        x0, y0 = rng.uniform(20, W * 0.5), rng.uniform(20, H * 0.5)
+        bbox = [float(x0), float(y0), float(x0 + rng.uniform(40, W * 0.4)), float(y0 + rng.uniform(40, H * 0.4))]
+        random.seed(pseed)
+        np.random.seed(nseed)
+        pil = image_blending(Image.fromarray(img), shape=shape, bbox_coor=bbox, segmentation=None, image_size_anchor=336,
+                             rgb_color=colors[ci % 4], vip_style=style, alpha=alpha, width=width)
+        out[f"c{ci}_bbox"] = np.array(bbox, np.float64)
+        out[f"c{ci}_sha"] = np.array(sha(np.asarray(pil)))
+        # a second and third instance on top (the reference's loop, processor.py:58-73)
+        pil = image_blending(pil, shape="rectangle", bbox_coor=[5.5, 7.25, W - 9.0, H - 11.5], segmentation=None,
+                             image_size_anchor=336, rgb_color=colors[(ci + 1) % 4], vip_style=None, alpha=None, width=None)
+        pil = image_blending(pil, shape="mask", bbox_coor=bbox, segmentation=[[x0, y0, x0 + 30, y0 + 5, x0 + 12, y0 + 44]],
+                             image_size_anchor=336, rgb_color=colors[(ci + 2) % 4], vip_style=None, alpha=None, width=None)
+        out[f"c{ci}_sha3"] = np.array(sha(np.asarray(pil)))
+        out[f"c{ci}_probe3"] = np.asarray(pil)[::37, ::41].copy()
+    np.savez_compressed(os.path.join(GOLD, "golden_vip_shapes.npz"), **out)
+    print("golden_vip_shapes.npz written", len(VIP_SHAPE_CASES))
 
 
 # --------------------------------------------------------------------------------------------
@@ -504,9 +547,10 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="")
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
-    todo = a.only.split(",") if a.only else ["pixels", "vip", "merge", "splice", "text", "modes", "model", "model_long"]
+    todo = a.only.split(",") if a.only else ["pixels", "vip", "vip_shapes", "merge", "splice", "text", "modes", "model", "model_long"]
     if "pixels" in todo: gen_pixels()
     if "vip" in todo: gen_vip()
+    if "vip_shapes" in todo: gen_vip_shapes()
     if "merge" in todo: gen_merge()
     if "splice" in todo: gen_splice()
     if "text" in todo: gen_text()

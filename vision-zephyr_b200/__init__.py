@@ -16,6 +16,7 @@ from .projector import QFormerB200, TextPack, build_multimodal_projector, build_
 from .arch import (VisZephyrB200MetaModel, VisZephyrB200MetaForCausalLM, merge_rows, splice_plan,
                    splice_scatter, text_gather)
 from .text_inputs import tokenizer_image_token, collate_supervised
+from .visual_prompts import PromptedImage, image_blending, resolve_visual_prompt
 from . import dist as parallel
 
 __all__ = [
@@ -24,5 +25,5 @@ __all__ = [
     "VisualPrompt", "VisZephyrB200MetaModel", "VisZephyrB200MetaForCausalLM",
     "process_any_resolution_images", "process_fixed_images", "clip_lut", "lut_from_processor",
     "calculate_grid_shape", "select_best_fit_resolution", "unpad_bounds", "merge_rows",
-    "tokenizer_image_token", "collate_supervised",
+    "tokenizer_image_token", "collate_supervised", "image_blending", "resolve_visual_prompt", "PromptedImage",
 ]

@@ -314,7 +314,10 @@ def process_any_resolution_images(images: Sequence[torch.Tensor], grid_pinpoints
                                   prompts=None, out_mode: str = "patches"):
     """Batch version of process_any_resolution_image (multi_scale_process.py:136-183) on u8 CUDA
     images [H,W,3].  Returns PatchBatch (out_mode='patches') or a list of f32 [T_i,3,336,336]
-    tensors in the reference layout (out_mode='chw')."""
+    tensors in the reference layout (out_mode='chw').  Items of `images` may be PromptedImage (the result of
+    visual_prompts.image_blending): their instances are composited first, in order."""
+    from .visual_prompts import split_prompted
+    images, prompts = split_prompted(images, prompts)
     views = []
     for im in images:
         v, _ = anyres_views((int(im.shape[1]), int(im.shape[0])), grid_pinpoints)
@@ -330,7 +333,10 @@ def process_fixed_images(images: Sequence[torch.Tensor], lut: np.ndarray, prompt
                          out_mode: str = "patches", mode: str = "identity", image_mean=None):
     """Fixed-336 path: blend visual prompts onto the images, bring them to 336x336 the way
     mm_utils.process_images / the training loader do (mode: 'identity' | 'resize' | 'plain' | 'square' |
-    'pad', see anyres.fixed_view), normalise, patchify.  Config 2 = 'identity' with prompts."""
+    'pad', see anyres.fixed_view), normalise, patchify.  Config 2 = 'identity' with prompts.  Items of `images`
+    may be PromptedImage (visual_prompts.image_blending)."""
+    from .visual_prompts import split_prompted
+    images, prompts = split_prompted(images, prompts)
     vc = [fixed_view((int(im.shape[1]), int(im.shape[0])), mode, image_mean) for im in images]
     views, canvases = [v for v, _ in vc], [c for _, c in vc]
     plan = build_plan(images, views, lut, prompts, canvases)
