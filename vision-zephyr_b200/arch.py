@@ -195,6 +195,52 @@ def merge_rows(vis: torch.Tensor, image_newline, descs: List[dict]) -> List[torc
     return list(torch.split(out, [d["n_rows"] for d in descs], dim=0))
 
 
+class _SpliceFn(torch.autograd.Function):
+    """vz_splice_scatter under autograd (training: the LLM loss must reach the projector through the spliced
+    rows).  Forward = the scatter kernel.  Backward needs, for every output row, where it came from; instead of
+    a second kernel the SAME scatter is run once more on index-coded 16-byte rows (token id + 1 for embedding
+    rows, -(row + 1) for visual rows, -(R + 1) for image_newline, 0 for padding), which yields the exact
+    provenance map of this very batch; the gradients are then index_add's of the incoming rows."""
+
+    @staticmethod
+    def forward(ctx, vis, embed, newline, sctx, Lmax, pad_left):
+        nl = newline.detach().to(device=embed.device, dtype=embed.dtype).contiguous() if newline is not None else None
+        out = splice_scatter(sctx["ids"], sctx["labels"], embed.detach(), vis.detach().to(embed.dtype).contiguous(), nl,
+                             sctx["slots"], sctx["prefix"], sctx["n_images"], sctx["total_vis_rows"], sctx["plan"], Lmax, pad_left)
+        ctx.sctx, ctx.Lmax, ctx.pad_left = sctx, Lmax, pad_left
+        ctx.shapes = (vis.shape, vis.dtype, embed.shape, embed.dtype, newline is not None)
+        ctx.mark_non_differentiable(out[1], out[2], out[3])
+        return out
+
+    @staticmethod
+    def backward(ctx, d_emb, *unused):
+        sctx = ctx.sctx
+        vshape, vdt, eshape, edt, has_nl = ctx.shapes
+        dev = d_emb.device
+        R, V = vshape[0], eshape[0]
+        code_table = (torch.arange(V, device=dev, dtype=torch.float32) + 1)[:, None].expand(V, 4).contiguous()
+        code_vis = (-(torch.arange(max(R, 1), device=dev, dtype=torch.float32) + 1))[:, None].expand(max(R, 1), 4).contiguous()
+        code_nl = torch.full((4,), -float(R + 1), device=dev, dtype=torch.float32) if has_nl else None
+        codes = splice_scatter(sctx["ids"], sctx["labels"], code_table, code_vis, code_nl, sctx["slots"], sctx["prefix"],
+                               sctx["n_images"], sctx["total_vis_rows"], sctx["plan"], ctx.Lmax, ctx.pad_left)[0]
+        src = codes[..., 0].long().reshape(-1)
+        g = d_emb.reshape(-1, d_emb.shape[-1])
+        d_vis = d_embed = d_nl = None
+        if ctx.needs_input_grad[0]:
+            m = (src < 0) & (src >= -R)
+            d_vis = torch.zeros(vshape, dtype=torch.float32, device=dev)
+            d_vis.index_add_(0, -src[m] - 1, g[m].float())
+            d_vis = d_vis.to(vdt)
+        if ctx.needs_input_grad[1]:
+            m = src > 0
+            d_embed = torch.zeros(eshape, dtype=torch.float32, device=dev)
+            d_embed.index_add_(0, src[m] - 1, g[m].float())
+            d_embed = d_embed.to(edt)
+        if has_nl and ctx.needs_input_grad[2]:
+            d_nl = g[src == -(R + 1)].float().sum(0).to(edt)
+        return d_vis, d_embed, d_nl, None, None, None
+
+
 class VisZephyrB200MetaForCausalLM(ABC):
     """Same surface as VisZephyrMetaForCausalLM (vis_zephyr_arch.py:107)."""
 
@@ -307,9 +353,11 @@ class VisZephyrB200MetaForCausalLM(ABC):
         ctx = self._plan_splice(input_ids, attention_mask, labels, tiles_per_image, images_size)
 
         # ---- tower (independent of the text) ---------------------------------------------------
+        # (training: pre_norm is a trained parameter, so it stays out of the tower's fusion kernel)
+        train = proj.needs_autograd(embed)
         feats = None
         if hi > lo:
-            feats = vision_tower.encode_patches(patches, pre_norm=proj.pre_norm_params())
+            feats = vision_tower.encode_patches(patches, pre_norm=None if train else proj.pre_norm_params())
 
         out_view = None
         if peer is not None and hi > lo and not keep_local:
@@ -380,6 +428,18 @@ class VisZephyrB200MetaForCausalLM(ABC):
         if hi <= lo:
             return torch.empty((0, embed.shape[1]), dtype=torch.bfloat16, device=dev)
         L_text = max(info["text_len"][:ctx["n_images"]])
+        if proj.needs_autograd(embed):
+            # training: the text rows come from embed_tokens under autograd (the reference's own expression,
+            # :163-189), so a trainable embedding table receives its gradient through the projector too
+            rows = []
+            for b in range(lo, hi):
+                ids_b = ctx["ids"][b]
+                e = torch.nn.functional.embedding(ids_b[ids_b != IMAGE_TOKEN_INDEX], embed)
+                rows.append(torch.nn.functional.pad(e, (0, 0, 0, L_text - e.shape[0])))
+            tile_sample = torch.repeat_interleave(torch.arange(hi - lo), torch.tensor(tiles_per_image[lo:hi])).to(dev)
+            from .projector_train import qformer_train_forward
+            vis_local = qformer_train_forward(proj, feats, torch.stack(rows), tile_sample)
+            return vis_local.reshape(-1, vis_local.shape[-1])
         text_rows = sum(info["text_len"][lo:hi])
         text_emb, text_off = text_gather(ctx["ids"], embed, ctx["plan"], text_rows, lo, hi)
         if text_emb.dtype != torch.bfloat16:
@@ -404,9 +464,15 @@ class VisZephyrB200MetaForCausalLM(ABC):
         if newline is not None:
             newline = newline.detach().to(device=dev, dtype=embed.dtype).contiguous()
         pad_left = getattr(self.config, "tokenizer_padding_side", "right") == "left"
-        out_embeds, out_labels, out_mask, out_pos = splice_scatter(
-            ctx["ids"], ctx["labels"], embed, vis, newline, ctx["slots"], ctx["prefix"], ctx["n_images"],
-            ctx["total_vis_rows"], ctx["plan"], info["Lmax"], pad_left)
+        newline_p = getattr(model, "image_newline", None)
+        if torch.is_grad_enabled() and (vis.requires_grad or embed.requires_grad or
+                                        (newline_p is not None and newline_p.requires_grad)):
+            out_embeds, out_labels, out_mask, out_pos = _SpliceFn.apply(
+                vis, embed, newline_p if newline_p is not None else None, ctx, info["Lmax"], pad_left)
+        else:
+            out_embeds, out_labels, out_mask, out_pos = splice_scatter(
+                ctx["ids"], ctx["labels"], embed, vis, newline, ctx["slots"], ctx["prefix"], ctx["n_images"],
+                ctx["total_vis_rows"], ctx["plan"], info["Lmax"], pad_left)
         new_mask = None
         if attention_mask is not None:
             new_mask = out_mask.to(dtype=attention_mask.dtype)

@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .projector_train import qformer_train_forward
 from .vision_tower import Workspace
 
 NUM_QUERIES, WIDTH, KV_WIDTH, HEADS, BLOCKS, FFN = 32, 4096, 5120, 8, 8, 8192
@@ -95,6 +96,15 @@ class TextPack:
     n_samples: int
     L: int
     tile_sample: torch.Tensor    # int32 [T]
+
+    def dense(self) -> torch.Tensor:
+        """[n_samples, L, 4096]: every sample's rows, zero padded to L (the reference's own layout,
+        vis_zephyr_arch.py:178-189, before the per-tile expand).  Host round trip for the offsets."""
+        off = self.text_off.tolist()
+        out = torch.zeros((self.n_samples, self.L, self.text_emb.shape[1]), dtype=self.text_emb.dtype, device=self.text_emb.device)
+        for s in range(self.n_samples):
+            out[s, :off[s + 1] - off[s]] = self.text_emb[off[s]:off[s + 1]]
+        return out
 
 
 class QFormerB200(nn.Module):
@@ -174,13 +184,19 @@ class QFormerB200(nn.Module):
                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """feats bf16 [T,576,5120] -> bf16 [T,32,4096]."""
         lib = _lib.load()
-        if torch.is_grad_enabled() and (feats.requires_grad or (text is not None and text.text_emb.requires_grad)
-                                        or any(p.requires_grad for p in self.parameters())):
-            # the kernels run on detached, packed weights: the result has no grad_fn, so training would
-            # silently stop updating mm_projector (train/train.py:817-836).  Refuse instead.
-            raise _lib.VzError(
-                "QFormerB200.forward is inference-only: call it under torch.no_grad() or freeze the projector "
-                "(requires_grad_(False)); the backward of the B200 path is not built (SURVEY.md 8(f) rank 4)")
+        if self.needs_autograd(feats):
+            # the inference kernels run on detached, packed weights and keep no activations: with gradients on
+            # (stage-1 / stage-2 training, train/train.py:817-836) take the autograd path instead
+            if feats_normed:
+                raise _lib.VzError("training path needs un-normalised features (pre_norm is a trained parameter): "
+                                   "call the tower without pre_norm")
+            dense, tile_sample = None, None
+            if text is not None:
+                dense, tile_sample = text.dense(), text.tile_sample
+            res = qformer_train_forward(self, feats, dense, tile_sample)
+            if out is not None:
+                raise _lib.VzError("out= (peer-store transport) is an inference feature; training uses the autograd path")
+            return res
         self._ensure_packed()
         if not feats.is_cuda:
             raise _lib.VzError("QFormerB200 runs on CUDA only (no CPU fallback)")
@@ -209,11 +225,24 @@ class QFormerB200(nn.Module):
         _lib.check(st, "vz_qformer_forward")
         return out
 
+    def needs_autograd(self, *inputs) -> bool:
+        """True when a caller expects gradients through this forward (any parameter or input requires grad
+        while grad mode is on): the training path (projector_train.py) is taken then."""
+        if not torch.is_grad_enabled():
+            return False
+        return any(isinstance(t, torch.Tensor) and t.requires_grad for t in inputs) or \
+            any(p.requires_grad for p in self.parameters())
+
     def forward(self, features, text_embeddings=None):
         """Reference signature (builder.py:72): features [T,576,5120], text_embeddings [T,L,4096]
         (already expanded per tile and zero padded) or None.  Every tile is treated as its own
         sample here; prepare_inputs_labels_for_multimodal uses forward_packed instead, which
-        shares the text K/V between the tiles of a sample."""
+        shares the text K/V between the tiles of a sample.  With gradients required it runs the autograd
+        path (same math, tcgen05 GEMMs for every Linear and for the cross-attention, forward and backward)."""
+        if self.needs_autograd(features, text_embeddings):
+            if not features.is_cuda:
+                raise _lib.VzError("QFormerB200 runs on CUDA only (no CPU fallback)")
+            return qformer_train_forward(self, features, text_embeddings, None).to(features.dtype)
         in_dtype = features.dtype
         text = None
         if text_embeddings is not None:
