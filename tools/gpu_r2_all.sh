@@ -3,7 +3,7 @@
 # an ncu launch list of the single-image call.  Logs under gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > gpurun_out/smi.txt
-for f in test_gpu_pixels test_gpu_kernels test_gpu_attention test_gpu_splice test_text_inputs test_gpu_e2e test_gpu_llm test_gpu_multi; do
+for f in test_gpu_pixels test_visual_prompts test_gpu_kernels test_gpu_attention test_gpu_splice test_text_inputs test_gpu_e2e test_gpu_llm test_gpu_train test_gpu_multi; do
   timeout 900 python -m pytest tests/$f.py -m gpu -q -s > gpurun_out/r2_$f.log 2>&1
   echo "$f rc=$?" >> gpurun_out/r2_summary.txt
   tail -3 gpurun_out/r2_$f.log | head -2
