@@ -168,7 +168,9 @@ typedef struct {
   int off_x, off_y;    /* where the resized image is pasted on the (black) canvas                 */
   int tile_x, tile_y;  /* origin of this 336x336 tile on the canvas                               */
   int tab_h, tab_v;    /* offsets (in int32 words) of the axis tables inside `tables`             */
-  int hview;           /* vz_preprocess2: index of the horizontal view (image, tab_h) this tile reads */
+  int hview;           /* vz_preprocess2 / 3: index of the horizontal view (image, tab_h) this tile reads */
+  int tab_v_dp;        /* vz_preprocess3: word offset (multiple of 4) of the vertical dp4a table       */
+  int reserved;
 } vz_tile_desc;
 
 /* vz_preprocess2: one entry per distinct (image, horizontal table) pair.  Its horizontally resampled
@@ -178,8 +180,15 @@ typedef struct {
   int tab_h;           /* word offset of the horizontal axis table                                */
   int out_w;           /* width after the horizontal pass                                         */
   int rows;            /* rows of the canvas = rows of the intermediate                           */
-  long long offset;    /* in pixels                                                               */
+  long long offset;    /* first 32-bit word of this view's intermediate in `scratch` (multiple of 4) */
+  int tab_h_dp;        /* vz_preprocess3: word offset (multiple of 4) of the horizontal dp4a table     */
+  int reserved;
 } vz_hview_desc;
+
+/* dp4a axis table (vz_preprocess3), 32-bit words, every section 16-byte aligned, built on the host from the
+ * table above (anyres.resample_table_dp): [0] = G groups of four taps per output, [1] = n outputs, [2..3] = 0;
+ * abase[n4] = window start aligned down to 4 (n4 = n rounded up to 4); ngrp[n4] = groups output i needs;
+ * coef[n][G] as uint4 = (low, middle, signed high) byte limbs of taps abase + 4g .. + 3 (zero padded), 0.     */
 
 /* Axis table layout (int32 words), built on the host exactly like Pillow's precompute_coeffs
  * (Resample.c) for (in_size -> out_size):  [0]=ksize, [1]=out_size, then out_size words xmin,
@@ -211,15 +220,18 @@ int vz_preprocess2(const vz_image_desc* images, int n_images, const vz_prim* pri
 
 /* The default form whenever something is resampled: same interface and same bits as vz_preprocess2, with the
  * tap loops on the 4-way byte dot product (coefficients split into three byte limbs, windows aligned down to
- * four pixels / four rows).  The intermediate in `scratch` is PLANAR: per view, [channel][ceil(rows / 4)][out_w]
- * 32-bit words, one word = four vertically consecutive u8 pixels of one channel, first word at `offset`;
- * scratch_words >= the largest offset + 3 * ceil(rows / 4) * out_w.  max_span_px = the widest source window
- * any 128 consecutive output columns of any view need.  VZ_ERR_UNSUPPORTED for ksize > 58 (use vz_preprocess2). */
+ * four pixels / four rows; dp4a tables, see vz_hview_desc).  The intermediate in `scratch` is, per view,
+ * [ceil(rows / 4)][out_w] uint4 = (R word, G word, B word, 0), one word = four vertically consecutive u8 pixels
+ * of one channel, first word at `offset`; scratch_words >= the largest offset + 4 * ceil(rows / 4) * out_w.
+ * max_span_px = the widest source window any 128 consecutive output columns of any view need; max_groups = the
+ * largest G of the plan's dp4a tables; max_band_groups = the most 4-row groups the window of any 14-row output
+ * band spans.  VZ_ERR_UNSUPPORTED when G > 16 (ksize > 58) or a band window does not fit shared memory
+ * (scale > ~7): use vz_preprocess2 then.                                                                     */
 int vz_preprocess3(const vz_image_desc* images, int n_images, const vz_prim* prims, int n_prims,
                    const vz_hview_desc* hviews, int n_hviews, const vz_tile_desc* tiles, int n_tiles,
                    const int32_t* tables, const float* lut768, int out_mode, void* out, void* scratch,
-                   long long scratch_words, int max_span_px, int max_rows, int max_out_w, int max_ksize,
-                   void* stream);
+                   long long scratch_words, int max_span_px, int max_rows, int max_out_w, int max_groups,
+                   int max_band_groups, void* stream);
 
 /* The identity form (BASELINE config 2): every tile is the whole of a 336 x 336 image (no resampling, no
  * canvas): blend the visual prompts, normalise, patchify, four pixels per thread with 32- / 128-bit loads.

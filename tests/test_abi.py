@@ -46,8 +46,8 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.GemmArgs) == 5 * 8 + 13 * 4 + 4 + 5 * 8 + 2 * 8 + 2 * 4 + 8 + 4 + 4 + 2 * 8 + 8
     assert ctypes.sizeof(_lib.ImageDesc) == 48
     assert ctypes.sizeof(_lib.Prim) == 32
-    assert ctypes.sizeof(_lib.TileDesc) == 40
-    assert ctypes.sizeof(_lib.HViewDesc) == 24
+    assert ctypes.sizeof(_lib.TileDesc) == 48
+    assert ctypes.sizeof(_lib.HViewDesc) == 32
     assert ctypes.sizeof(_lib.SlotDesc) == 48
     assert ctypes.sizeof(_lib.VitWeights) == 5 * 8 + 24 * 10 * 8
     assert ctypes.sizeof(_lib.QfWeights) == 5 * 8 + 8 * 20 * 8

@@ -49,12 +49,12 @@ class Prim(C.Structure):
 class TileDesc(C.Structure):
     _fields_ = [("image", C.c_int), ("out_w", C.c_int), ("out_h", C.c_int), ("off_x", C.c_int),
                 ("off_y", C.c_int), ("tile_x", C.c_int), ("tile_y", C.c_int), ("tab_h", C.c_int),
-                ("tab_v", C.c_int), ("hview", C.c_int)]
+                ("tab_v", C.c_int), ("hview", C.c_int), ("tab_v_dp", C.c_int), ("reserved", C.c_int)]
 
 
 class HViewDesc(C.Structure):
     _fields_ = [("image", C.c_int), ("tab_h", C.c_int), ("out_w", C.c_int), ("rows", C.c_int),
-                ("offset", C.c_longlong)]
+                ("offset", C.c_longlong), ("tab_h_dp", C.c_int), ("reserved", C.c_int)]
 
 
 class VitLayer(C.Structure):
@@ -111,7 +111,7 @@ SYMBOLS = {
     "vz_layernorm_bf16": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, C.c_float, _vp]),
     "vz_preprocess": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _vp]),
     "vz_preprocess2": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, C.c_longlong, _i, _i, _i, _i, _vp]),
-    "vz_preprocess3": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, C.c_longlong, _i, _i, _i, _i, _vp]),
+    "vz_preprocess3": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, C.c_longlong, _i, _i, _i, _i, _i, _vp]),
     "vz_preprocess_identity": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "vz_patchify": (_i, [_vp, _i, _i, _vp, _vp]),
     "vz_vit_workspace_bytes": (_sz, [_i]),

@@ -167,23 +167,85 @@ def resample_table(in_size: int, out_size: int, filt: str = "lanczos") -> np.nda
     return np.concatenate([np.array([ksize, out_size], np.int32), xmin, cnt, kk.reshape(-1)])
 
 
+@lru_cache(maxsize=512)
+def resample_table_dp(in_size: int, out_size: int, filt: str = "lanczos") -> np.ndarray:
+    """The same axis table in the form the dp4a kernels read (vz_preprocess3, layout in include/vz_b200.h):
+    every window aligned DOWN to a multiple of four source pixels, the coefficients shifted to match and split
+    into byte limbs c = c0 + 256 c1 + 65536 c2 (c0, c1 unsigned, c2 signed), four taps per 32-bit word."""
+    t = resample_table(in_size, out_size, filt)
+    ks, n = int(t[0]), int(t[1])
+    xmin, cnt = t[2:2 + n].astype(np.int64), t[2 + n:2 + 2 * n].astype(np.int64)
+    kk = t[2 + 2 * n:].reshape(n, ks).astype(np.int64)
+    G = (ks + 6) >> 2
+    sh = xmin & 3
+    slots = np.zeros((n, 4 * G), np.int64)
+    cols = sh[:, None] + np.arange(ks)[None, :]
+    live = np.arange(ks)[None, :] < cnt[:, None]
+    rows = np.broadcast_to(np.arange(n)[:, None], cols.shape)
+    slots[rows[live], cols[live]] = kk[live]
+    limbs = np.stack([slots & 255, (slots >> 8) & 255, (slots >> 16) & 255, np.zeros_like(slots)], axis=1)   # [n,4,4G]
+    b = limbs.reshape(n, 4, G, 4).astype(np.uint32)
+    words = b[..., 0] | (b[..., 1] << 8) | (b[..., 2] << 16) | (b[..., 3] << 24)                             # [n,4,G]
+    coef = np.ascontiguousarray(words.transpose(0, 2, 1)).reshape(-1)                                        # [n][G][4]
+    n4 = (n + 3) & ~3
+    abase = np.zeros(n4, np.int64)
+    abase[:n] = xmin & ~3
+    ngrp = np.zeros(n4, np.int64)
+    ngrp[:n] = (cnt + sh + 3) >> 2
+    head = np.array([G, n, 0, 0], np.int64)
+    out = np.concatenate([head, abase, ngrp]).astype(np.uint32)
+    return np.concatenate([out, coef.astype(np.uint32)]).view(np.int32)
+
+
+def band_window_groups(in_size: int, out_size: int, filt: str, origin: int, band: int = 14, n_bands: int = 24) -> int:
+    """most 4-row groups of the intermediate that the taps of one `band`-row output band touch, for a tile whose
+    first row is output row `origin` of the axis (rows outside [0, out_size) read nothing)"""
+    t = resample_table(in_size, out_size, filt)
+    n = int(t[1])
+    xmin, cnt = t[2:2 + n].astype(np.int64), t[2 + n:2 + 2 * n].astype(np.int64)
+    lo, hi = xmin >> 2, (xmin + cnt + 3) >> 2
+    worst = 1
+    for b in range(n_bands):
+        a, e = max(origin + b * band, 0), min(origin + (b + 1) * band, n)
+        if e > a:
+            worst = max(worst, int(hi[a:e].max() - lo[a:e].min()))
+    return worst
+
+
 class TablePool:
-    """Packs the axis tables of a batch into one int32 buffer and hands out word offsets."""
+    """Packs the axis tables of a batch into one int32 buffer and hands out word offsets (every chunk starts on
+    a 16-byte boundary: the dp4a tables are read with 128-bit loads)."""
 
     def __init__(self):
         self._off = {}
         self._chunks: List[np.ndarray] = []
         self._words = 0
         self.max_ksize = 1
+        self.max_groups = 1
+
+    def _add(self, key, t: np.ndarray) -> int:
+        pad = (-t.size) % 4
+        if pad:
+            t = np.concatenate([t, np.zeros(pad, np.int32)])
+        self._off[key] = self._words
+        self._chunks.append(t)
+        self._words += t.size
+        return self._off[key]
+
+    def offset_dp(self, in_size: int, out_size: int, filt: str = "lanczos") -> int:
+        key = (in_size, out_size, filt, "dp")
+        if key not in self._off:
+            t = resample_table_dp(in_size, out_size, filt)
+            self.max_groups = max(self.max_groups, int(t[0]))
+            return self._add(key, t)
+        return self._off[key]
 
     def offset(self, in_size: int, out_size: int, filt: str = "lanczos") -> int:
         key = (in_size, out_size, filt)
         if key not in self._off:
             t = resample_table(in_size, out_size, filt)
-            self._off[key] = self._words
-            self._chunks.append(t)
-            self._words += t.size
             self.max_ksize = max(self.max_ksize, int(t[0]))
+            return self._add(key, t)
         return self._off[key]
 
     def pack(self) -> np.ndarray:

@@ -13,11 +13,15 @@
 //     canvas padding happen on the way), every window is aligned DOWN to a multiple of four pixels and the
 //     coefficient bytes are shifted to match (zero padded), so a thread's taps are aligned 32-bit words of a
 //     plane; its 3 x G coefficient words stay in registers for all rows of the CTA.
-//   * the u8 intermediate is stored as I[channel][row / 4][x]: one word = FOUR VERTICALLY consecutive pixels
-//     of one channel, which is what the vertical pass needs for its own dp4a (windows aligned down to four
-//     rows).  A horizontal-pass thread computes four rows of one column and writes whole words, coalesced in x.
-// The identity form (no resampling: the fixed 336 x 336 inputs of config 2) stays in vz_preprocess.cu.
+//   * the u8 intermediate is stored as I[row / 4][x] = uint4 (R word, G word, B word, 0): one word = FOUR
+//     VERTICALLY consecutive pixels of one channel, which is what the vertical pass needs for its own dp4a
+//     (windows aligned down to four rows).  A horizontal-pass thread computes four rows of one column and
+//     writes one uint4, coalesced in x; the vertical pass stages a band's window with 128-bit loads.
+//   * coefficient limbs come from a host-built table (anyres.resample_table_dp), one uint4 per (output, group).
+// The identity form (no resampling: the fixed 336 x 336 inputs of config 2) is pre_identity_kernel below.
 #include "vz_common.cuh"
+
+#include <stdlib.h>
 
 namespace vz {
 namespace {
@@ -66,19 +70,43 @@ __device__ __forceinline__ bool rect_covers(const vz_prim& p, int x, int y) {
   return hl || vl;
 }
 
+// Host-built dp4a axis table (anyres.resample_table_dp), 32-bit words, every section 16-byte aligned:
+//   [0] = G (groups of four taps per output index), [1] = n (output size), [2..3] = 0
+//   abase[n4]  aligned start of each window (xmin & ~3), n4 = n rounded up to 4
+//   ngrp[n4]   groups output i really needs ( ceil((count + (xmin & 3)) / 4) )
+//   coef[n][G] uint4 = (c0 bytes, c1 bytes, c2 bytes, 0) of taps abase + 4g .. abase + 4g + 3 (zero padded)
+struct DpTable {
+  int G, n;
+  const int32_t* abase;
+  const int32_t* ngrp;
+  const uint4* coef;
+};
+__device__ __forceinline__ DpTable dp_table(const int32_t* tables, int off) {
+  const int32_t* t = tables + off;
+  DpTable d;
+  d.G = t[0]; d.n = t[1];
+  const int n4 = (d.n + 3) & ~3;
+  d.abase = t + 4;
+  d.ngrp = d.abase + n4;
+  d.coef = reinterpret_cast<const uint4*>(d.ngrp + n4);
+  return d;
+}
+
 struct HArgs {
   const vz_image_desc* images;
   const vz_prim* prims;
   const vz_hview_desc* hviews;
   const int32_t* tables;
   uint32_t* scratch;
-  int raw_stride;     // bytes per staged source row (multiple of 16)
   int plane_words;    // 32-bit words per plane row
-  int rows_per_cta;   // multiple of 8
+  int rows_per_cta;   // 8 or 16
 };
 
 // ------------------------------------------------------------------------------------------------
 // Horizontal pass.  CTA = rows_per_cta canvas rows x 128 output columns of one (image, table) view.
+// Nothing is staged: the de-interleave step reads the interleaved source straight from global memory
+// (four aligned 32-bit loads per four pixels, re-aligned by funnel shifts), so a CTA needs only its three
+// byte planes in shared memory and many CTAs share an SM.
 // ------------------------------------------------------------------------------------------------
 template <int GMAX>
 __global__ void __launch_bounds__(HT) pre_h_dp_kernel(const HArgs a) {
@@ -89,80 +117,25 @@ __global__ void __launch_bounds__(HT) pre_h_dp_kernel(const HArgs a) {
   if (x0 >= hv.out_w || y0 >= hv.rows) return;
   const vz_image_desc im = a.images[hv.image];
   const int nrows = min(RB, hv.rows - y0);
-  const int32_t* th = a.tables + hv.tab_h;
-  const int ksh = th[0];
-  const int32_t* h_min = th + 2;
-  const int32_t* h_cnt = h_min + hv.out_w;
-  const int32_t* h_kk = h_cnt + hv.out_w;
-  const int ngc = (ksh + 6) >> 2;            // groups of four taps any column of this view can need (<= GMAX)
-
-  uint32_t* s_co = reinterpret_cast<uint32_t*>(dp_smem);                  // [GMAX][3][HX] limb words of this CTA's columns
-  uint8_t* s_raw = dp_smem + (size_t)GMAX * 3 * HX * 4;                   // [RB][raw_stride] interleaved source bytes
-  uint32_t* s_pl = reinterpret_cast<uint32_t*>(s_raw + (size_t)RB * a.raw_stride);   // [3][RB][plane_words]
+  const DpTable th = dp_table(a.tables, hv.tab_h_dp);
+  const int G = th.G;                                                 // <= GMAX (checked by the launcher)
+  uint32_t* s_pl = reinterpret_cast<uint32_t*>(dp_smem);             // [3][RB][plane_words]
   __shared__ vz_prim s_prims[MAX_PRIMS];
-  __shared__ int s_phase[64];
   const int n_prims = im.prim_count < MAX_PRIMS ? im.prim_count : MAX_PRIMS;
   for (int i = tid; i < n_prims; i += HT) s_prims[i] = a.prims[im.prim_begin + i];
+  if (n_prims != 0) __syncthreads();   // (uniform) the blend below reads the instance list
 
   const int xl = tid & (HX - 1), q = tid >> 7;
   const int x = x0 + xl;
   const bool valid = x < hv.out_w;
   const int xlast = min(x0 + HX - 1, hv.out_w - 1);
-  const int sx0 = h_min[x0], sx1 = h_min[xlast] + h_cnt[xlast];     // canvas columns this CTA's outputs read
-  const int base = sx0 & ~3;                                         // plane byte 0 = canvas column `base`
-  const int nvec = (sx1 - base + 3) >> 2;                            // plane words that carry data
-
-  // ---- coefficient limbs of this thread's column, shifted to its aligned window ---------------
-  for (int i = tid; i < GMAX * 3 * HX; i += HT) s_co[i] = 0u;
-  __syncthreads();
-  int wb = 0;
-  if (tid < HX && valid) {
-    const int xm = h_min[x], cnt = h_cnt[x], sh = xm & 3;
-    uint8_t* cb = reinterpret_cast<uint8_t*>(s_co);
-    for (int k = 0; k < cnt; ++k) {
-      const int c = h_kk[x * ksh + k];
-      const int slot = k + sh, g = slot >> 2, b = slot & 3;
-      cb[((g * 3 + 0) * HX + xl) * 4 + b] = (uint8_t)(c & 255);
-      cb[((g * 3 + 1) * HX + xl) * 4 + b] = (uint8_t)((c >> 8) & 255);
-      cb[((g * 3 + 2) * HX + xl) * 4 + b] = (uint8_t)((c >> 16) & 255);
-    }
-  }
-  if (valid) wb = ((h_min[x] & ~3) - base) >> 2;
-
-  // ---- stage the raw source rows (cp.async, 16-byte chunks at their global phase) -------------
-  const uint8_t* img_end = im.src + (size_t)im.W * im.H * 3;
-  const int rx0 = max(base - im.pad_x, 0), rx1 = min(sx1 - im.pad_x, im.W);   // real image columns of the window
-  auto row_phase = [&](int sy) -> int {   // where canvas column `base` of this row sits in its raw buffer
-    const int yr = sy - im.pad_y;
-    if (yr < 0 || yr >= im.H || rx1 <= rx0) return 0;
-    const uintptr_t g = reinterpret_cast<uintptr_t>(im.src + ((size_t)yr * im.W + rx0) * 3);
-    return (int)((g - (uintptr_t)((rx0 + im.pad_x - base) * 3)) & 15);
-  };
-  if (tid < RB) s_phase[tid] = tid < nrows ? row_phase(y0 + tid) : 0;
-  __syncthreads();
-  for (int r = 0; r < nrows; ++r) {
-    const int yr = y0 + r - im.pad_y;
-    if (yr < 0 || yr >= im.H || rx1 <= rx0) continue;
-    const uint8_t* srow = im.src + ((size_t)yr * im.W + rx0) * 3;
-    const int a16 = (int)(reinterpret_cast<uintptr_t>(srow) & 15);
-    const uint8_t* g0 = srow - a16;
-    uint8_t* d0 = s_raw + (size_t)r * a.raw_stride + s_phase[r] + (rx0 + im.pad_x - base) * 3 - a16;   // 16-byte aligned
-    const int nv16 = ((rx1 - rx0) * 3 + a16 + 15) >> 4;
-    for (int i = tid; i < nv16; i += HT) {
-      const uint8_t* g = g0 + 16 * i;
-      const long left = img_end - g;
-      cp_async_16_partial(d0 + 16 * i, g, left >= 16 ? 16 : (left > 0 ? (int)left : 0));
-    }
-  }
-  cp_async_commit();
-  // this thread's coefficient words -> registers (static indices) while the copies fly
-  uint32_t co[GMAX][3];
+  const int base = th.abase[x0];                                      // plane byte 0 = canvas column `base` (multiple of 4)
+  const int nvec = ((th.abase[xlast] - base) >> 2) + th.ngrp[xlast];  // plane words that carry data
+  // this thread's coefficient words (registers, static indices) and its first plane word
+  uint4 co[GMAX];
 #pragma unroll
-  for (int g = 0; g < GMAX; ++g)
-#pragma unroll
-    for (int l = 0; l < 3; ++l) co[g][l] = s_co[(g * 3 + l) * HX + xl];
-  cp_async_wait<0>();
-  __syncthreads();
+  for (int g = 0; g < GMAX; ++g) co[g] = (valid && g < G) ? __ldg(th.coef + (size_t)x * G + g) : make_uint4(0u, 0u, 0u, 0u);
+  const int wb = valid ? (th.abase[x] - base) >> 2 : 0;
 
   // ---- de-interleave (+ canvas padding, + visual prompts) into byte planes, four pixels per thread ----
   const uint32_t bgw = im.bg & 0xffffffu;
@@ -171,34 +144,35 @@ __global__ void __launch_bounds__(HT) pre_h_dp_kernel(const HArgs a) {
     const int cx = base + 4 * v, yr = y0 + r - im.pad_y;
     const bool row_real = yr >= 0 && yr < im.H;
     const int xr0 = cx - im.pad_x;
-    uint32_t R, G, B;
+    uint32_t R, Gc, B;
     if (row_real && xr0 >= 0 && xr0 + 3 < im.W && n_prims == 0) {
-      const int b0 = s_phase[r] + 12 * v;
-      const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_raw + (size_t)r * a.raw_stride) + (b0 >> 2);
-      const uint32_t sh = (uint32_t)(b0 & 3) * 8u;
-      const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+      const uint8_t* p = im.src + ((size_t)yr * im.W + xr0) * 3;      // 12 bytes from here, any alignment
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+      const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3) * 8u;
+      const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+      const uint32_t w3 = sh ? __ldg(wp + 3) : 0u;                    // holds bytes of these pixels iff p is unaligned
       const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh);
       // a0 = R0 G0 B0 R1 | a1 = G1 B1 R2 G2 | a2 = B2 R3 G3 B3   (byte 0 first)
       R = __byte_perm(__byte_perm(a0, a1, 0x0630), a2, 0x5210);
-      G = __byte_perm(__byte_perm(a0, a1, 0x0741), a2, 0x6210);
+      Gc = __byte_perm(__byte_perm(a0, a1, 0x0741), a2, 0x6210);
       B = __byte_perm(__byte_perm(a0, a1, 0x0052), a2, 0x7410);
     } else {
-      R = G = B = 0u;
-      const uint8_t* rawrow = s_raw + (size_t)r * a.raw_stride + s_phase[r] + 12 * v;
+      R = Gc = B = 0u;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int xr = xr0 + i;
         int rr, gg, bb;
         if (row_real && xr >= 0 && xr < im.W) {
-          rr = rawrow[3 * i]; gg = rawrow[3 * i + 1]; bb = rawrow[3 * i + 2];
+          const uint8_t* p = im.src + ((size_t)yr * im.W + xr) * 3;
+          rr = __ldg(p); gg = __ldg(p + 1); bb = __ldg(p + 2);
           for (int pi = 0; pi < n_prims; ++pi) {
-            const vz_prim& p = s_prims[pi];
+            const vz_prim& pr = s_prims[pi];
             uint32_t ov;
-            if (p.type == VZ_PRIM_LAYER) {
-              ov = __ldg(reinterpret_cast<const uint32_t*>(im.layers) + ((size_t)p.layer * im.H + yr) * im.W + xr);
+            if (pr.type == VZ_PRIM_LAYER) {
+              ov = __ldg(reinterpret_cast<const uint32_t*>(im.layers) + ((size_t)pr.layer * im.H + yr) * im.W + xr);
             } else {
-              if (!rect_covers(p, xr, yr)) continue;
-              ov = p.rgba;
+              if (!rect_covers(pr, xr, yr)) continue;
+              ov = pr.rgba;
             }
             const int al = (int)(ov >> 24);
             rr = blend_over(rr, (int)(ov & 0xff), al);
@@ -208,18 +182,18 @@ __global__ void __launch_bounds__(HT) pre_h_dp_kernel(const HArgs a) {
         } else {   // canvas padding (expand2square, mm_utils.py:16-35)
           rr = (int)(bgw & 0xff); gg = (int)((bgw >> 8) & 0xff); bb = (int)((bgw >> 16) & 0xff);
         }
-        R |= (uint32_t)rr << (8 * i); G |= (uint32_t)gg << (8 * i); B |= (uint32_t)bb << (8 * i);
+        R |= (uint32_t)rr << (8 * i); Gc |= (uint32_t)gg << (8 * i); B |= (uint32_t)bb << (8 * i);
       }
     }
     s_pl[(0 * RB + r) * a.plane_words + v] = R;
-    s_pl[(1 * RB + r) * a.plane_words + v] = G;
+    s_pl[(1 * RB + r) * a.plane_words + v] = Gc;
     s_pl[(2 * RB + r) * a.plane_words + v] = B;
   }
   __syncthreads();
 
-  // ---- filter: thread = (column x, four consecutive rows), one intermediate word per channel ----
-  const int RQ = (hv.rows + 3) >> 2;
+  // ---- filter: thread = (column x, four consecutive rows), one intermediate uint4 (R, G, B words) ----
   const int nrq = (nrows + 3) >> 2;
+  uint4* inter = reinterpret_cast<uint4*>(a.scratch + hv.offset);
   for (int rq = q; rq < nrq; rq += 2) {
     uint32_t o[3] = {0u, 0u, 0u};
 #pragma unroll
@@ -233,23 +207,18 @@ __global__ void __launch_bounds__(HT) pre_h_dp_kernel(const HArgs a) {
           int a2 = 0;
 #pragma unroll
           for (int g = 0; g < GMAX; ++g) {
-            if (g < ngc) {
+            if (g < G) {
               const uint32_t p = pw[g];
-              a0 = dp4a_uu(p, co[g][0], a0);
-              a1 = dp4a_uu(p, co[g][1], a1);
-              a2 = dp4a_us(p, co[g][2], a2);
+              a0 = dp4a_uu(p, co[g].x, a0);
+              a1 = dp4a_uu(p, co[g].y, a1);
+              a2 = dp4a_us(p, co[g].z, a2);
             }
           }
           o[c] |= finish8(a0, a1, a2) << (8 * rr);
         }
       }
     }
-    if (valid) {
-      uint32_t* dst = a.scratch + hv.offset + (size_t)((y0 >> 2) + rq) * hv.out_w + x;
-      dst[0] = o[0];
-      dst[(size_t)RQ * hv.out_w] = o[1];
-      dst[(size_t)2 * RQ * hv.out_w] = o[2];
-    }
+    if (valid) inter[(size_t)((y0 >> 2) + rq) * hv.out_w + x] = make_uint4(o[0], o[1], o[2], 0u);
   }
 }
 
@@ -261,94 +230,102 @@ struct VArgs {
   const uint32_t* scratch;
   void* out;
   int out_mode;
-  int gv;             // groups of four taps per output row the coefficient table is laid out for
+  int gmax;           // largest G of any vertical table of the plan (sizes the coefficient slice)
+  int win_groups;     // most row groups any band window spans (sizes the staged window)
 };
 
 // ------------------------------------------------------------------------------------------------
-// Vertical pass + LUT + im2col of one 14-row band of one tile.  Thread x gathers, per band row, the words
-// I[c][j0 + g][rx] of its column (coalesced in x, L1 / L2 resident) and runs 9 dp4a per group.
+// Vertical pass + LUT + im2col of one 14-row band of one tile.  The band's window of the intermediate
+// (win x 336 uint4, win = row groups the 14 rows touch, 9 for a 1.5x downscale) is staged ONCE in shared
+// memory with coalesced 128-bit loads; thread x then runs 9 dp4a per (row, group) from shared memory, keeps
+// the 14 x 3 result bytes in registers, and the staging area is reused for the im2col transpose.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(VT) pre_v_dp_kernel(const VArgs a) {
   extern __shared__ __align__(16) uint8_t dp_smem[];
   const int band = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
   const vz_tile_desc td = a.tiles[t];
   const vz_hview_desc hv = a.hviews[td.hview];
-  const int32_t* tv = a.tables + td.tab_v;
-  const int ksv = tv[0];
-  const int32_t* v_min = tv + 2;
-  const int32_t* v_cnt = v_min + td.out_h;
-  const int32_t* v_kk = v_cnt + td.out_h;
+  const DpTable tv = dp_table(a.tables, td.tab_v_dp);
+  const int G = tv.G;
   const int stage_bytes = (a.out_mode == VZ_OUT_CHW_F32) ? 3 * BAND * TILE * 4 : 24 * VZ_PATCH_K * 2;
-  uint8_t* s_stage = dp_smem;
-  uint32_t* s_vc = reinterpret_cast<uint32_t*>(dp_smem + stage_bytes);   // [BAND][gv][4]: limb words c0, c1, c2, 0
-  int32_t* s_vj0 = reinterpret_cast<int32_t*>(s_vc + BAND * a.gv * 4);
-  int32_t* s_vng = s_vj0 + BAND;
+  const int win_bytes = a.win_groups * TILE * 16;
+  uint8_t* s_stage = dp_smem;                                              // aliases the window (used after it)
+  uint4* s_win = reinterpret_cast<uint4*>(dp_smem);                       // [win][336]
+  uint4* s_vc = reinterpret_cast<uint4*>(dp_smem + (stage_bytes > win_bytes ? stage_bytes : win_bytes));   // [BAND][gmax]
+  int32_t* s_vj0 = reinterpret_cast<int32_t*>(s_vc + BAND * a.gmax);
+  int32_t* s_vng = s_vj0 + 16;
   const int ry0 = td.tile_y + band * BAND - td.off_y;   // resized-image row of band row 0
-  for (int i = tid; i < BAND * a.gv * 4; i += VT) s_vc[i] = 0u;
   if (tid < BAND) {
     const int ry = ry0 + tid;
     const bool ok = ry >= 0 && ry < td.out_h;
-    const int vm = ok ? v_min[ry] : 0, cnt = ok ? v_cnt[ry] : 0;
-    s_vj0[tid] = vm >> 2;
-    s_vng[tid] = cnt > 0 ? (cnt + (vm & 3) + 3) >> 2 : 0;
+    s_vj0[tid] = ok ? tv.abase[ry] >> 2 : 0;
+    s_vng[tid] = ok ? tv.ngrp[ry] : 0;
   }
-  if (a.out_mode == VZ_OUT_PATCHES_BF16) {
-    __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(s_stage);
-    for (int i = tid; i < 24 * 4; i += VT) sp[(i >> 2) * VZ_PATCH_K + 588 + (i & 3)] = __float2bfloat16_rn(0.f);
-  }
-  __syncthreads();
-  {
-    uint8_t* cb = reinterpret_cast<uint8_t*>(s_vc);
-    for (int i = tid; i < BAND * ksv; i += VT) {
-      const int y = i / ksv, k = i - y * ksv;
-      const int ry = ry0 + y;
-      if (ry < 0 || ry >= td.out_h || k >= v_cnt[ry]) continue;
-      const int c = v_kk[ry * ksv + k];
-      const int slot = k + (v_min[ry] & 3), g = slot >> 2, b = slot & 3;
-      uint8_t* w = cb + (size_t)((y * a.gv + g) * 4) * 4 + b;
-      w[0] = (uint8_t)(c & 255);
-      w[4] = (uint8_t)((c >> 8) & 255);
-      w[8] = (uint8_t)((c >> 16) & 255);
-    }
+  for (int i = tid; i < BAND * G; i += VT) {
+    const int y = i / G, g = i - y * G;
+    const int ry = ry0 + y;
+    s_vc[y * a.gmax + g] = (ry >= 0 && ry < td.out_h) ? __ldg(tv.coef + (size_t)ry * G + g) : make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
-  const int x = tid;
+  int jlo = 0x7fffffff, jhi = 0;
+#pragma unroll
+  for (int y = 0; y < BAND; ++y) {
+    const int ng = s_vng[y], j0 = s_vj0[y];
+    if (ng > 0) { jlo = min(jlo, j0); jhi = max(jhi, j0 + ng); }
+  }
+  const int nwin = jhi > jlo ? jhi - jlo : 0;            // <= a.win_groups (host-computed bound)
+  const uint4* inter = reinterpret_cast<const uint4*>(a.scratch + hv.offset);
+  for (int i = tid; i < nwin * TILE; i += VT) {
+    const int g = i / TILE, xx = i - g * TILE;
+    const int rxx = td.tile_x + xx - td.off_x;
+    s_win[i] = (rxx >= 0 && rxx < td.out_w) ? __ldg(inter + (size_t)(jlo + g) * hv.out_w + rxx) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  const int x = tid < TILE ? tid : 0;
   const int rx = td.tile_x + x - td.off_x;
   const bool col_ok = tid < TILE && rx >= 0 && rx < td.out_w;
-  const int RQ = (hv.rows + 3) >> 2;
-  const size_t plane = (size_t)RQ * hv.out_w;
-  const uint32_t* col = a.scratch + hv.offset + (col_ok ? rx : 0);
-  const int px = x / 14, kx = x - px * 14;
-#pragma unroll 2
+  uint32_t vr[4] = {0u, 0u, 0u, 0u}, vg[4] = {0u, 0u, 0u, 0u}, vb[4] = {0u, 0u, 0u, 0u};   // 14 result bytes per channel
+#pragma unroll
   for (int y = 0; y < BAND; ++y) {
     const int ng = col_ok ? s_vng[y] : 0;
-    const uint32_t* src = col + (size_t)s_vj0[y] * hv.out_w;
-    const uint4* cw = reinterpret_cast<const uint4*>(s_vc + (size_t)y * a.gv * 4);
+    const uint4* win = s_win + (size_t)(s_vj0[y] - jlo) * TILE + x;
+    const uint4* cw = s_vc + y * a.gmax;
     uint32_t r0 = 0u, r1 = 0u, g0 = 0u, g1 = 0u, b0 = 0u, b1 = 0u;
     int r2 = 0, g2 = 0, b2 = 0;
     for (int g = 0; g < ng; ++g) {
       const uint4 c = cw[g];
-      const uint32_t pr = __ldg(src + (size_t)g * hv.out_w);
-      const uint32_t pg = __ldg(src + plane + (size_t)g * hv.out_w);
-      const uint32_t pb = __ldg(src + 2 * plane + (size_t)g * hv.out_w);
-      r0 = dp4a_uu(pr, c.x, r0); r1 = dp4a_uu(pr, c.y, r1); r2 = dp4a_us(pr, c.z, r2);
-      g0 = dp4a_uu(pg, c.x, g0); g1 = dp4a_uu(pg, c.y, g1); g2 = dp4a_us(pg, c.z, g2);
-      b0 = dp4a_uu(pb, c.x, b0); b1 = dp4a_uu(pb, c.y, b1); b2 = dp4a_us(pb, c.z, b2);
+      const uint4 p = win[(size_t)g * TILE];
+      r0 = dp4a_uu(p.x, c.x, r0); r1 = dp4a_uu(p.x, c.y, r1); r2 = dp4a_us(p.x, c.z, r2);
+      g0 = dp4a_uu(p.y, c.x, g0); g1 = dp4a_uu(p.y, c.y, g1); g2 = dp4a_us(p.y, c.z, g2);
+      b0 = dp4a_uu(p.z, c.x, b0); b1 = dp4a_uu(p.z, c.y, b1); b2 = dp4a_us(p.z, c.z, b2);
     }
+    if (ng > 0) {
+      vr[y >> 2] |= finish8(r0, r1, r2) << (8 * (y & 3));
+      vg[y >> 2] |= finish8(g0, g1, g2) << (8 * (y & 3));
+      vb[y >> 2] |= finish8(b0, b1, b2) << (8 * (y & 3));
+    }
+  }
+  __syncthreads();   // everybody is done with the window: the staging area takes its place
+  if (a.out_mode == VZ_OUT_PATCHES_BF16) {
+    __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(s_stage);
+    for (int i = tid; i < 24 * 4; i += VT) sp[(i >> 2) * VZ_PATCH_K + 588 + (i & 3)] = __float2bfloat16_rn(0.f);
     if (tid < TILE) {
-      const int v0 = ng > 0 ? (int)finish8(r0, r1, r2) : 0, v1 = ng > 0 ? (int)finish8(g0, g1, g2) : 0,
-                v2 = ng > 0 ? (int)finish8(b0, b1, b2) : 0;
-      if (a.out_mode == VZ_OUT_PATCHES_BF16) {
-        __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(s_stage) + px * VZ_PATCH_K + y * 14 + kx;
-        sp[0] = __float2bfloat16_rn(a.lut[v0]);
-        sp[196] = __float2bfloat16_rn(a.lut[256 + v1]);
-        sp[392] = __float2bfloat16_rn(a.lut[512 + v2]);
-      } else {
-        float* sf = reinterpret_cast<float*>(s_stage) + y * TILE + x;   // [3][BAND][336]
-        sf[0] = a.lut[v0];
-        sf[BAND * TILE] = a.lut[256 + v1];
-        sf[2 * BAND * TILE] = a.lut[512 + v2];
+      const int px = x / 14, kx = x - px * 14;
+#pragma unroll
+      for (int y = 0; y < BAND; ++y) {
+        __nv_bfloat16* q = sp + px * VZ_PATCH_K + y * 14 + kx;
+        q[0] = __float2bfloat16_rn(a.lut[(vr[y >> 2] >> (8 * (y & 3))) & 0xff]);
+        q[196] = __float2bfloat16_rn(a.lut[256 + ((vg[y >> 2] >> (8 * (y & 3))) & 0xff)]);
+        q[392] = __float2bfloat16_rn(a.lut[512 + ((vb[y >> 2] >> (8 * (y & 3))) & 0xff)]);
       }
+    }
+  } else if (tid < TILE) {
+    float* sf = reinterpret_cast<float*>(s_stage) + x;   // [3][BAND][336]
+#pragma unroll
+    for (int y = 0; y < BAND; ++y) {
+      sf[y * TILE] = a.lut[(vr[y >> 2] >> (8 * (y & 3))) & 0xff];
+      sf[(BAND + y) * TILE] = a.lut[256 + ((vg[y >> 2] >> (8 * (y & 3))) & 0xff)];
+      sf[(2 * BAND + y) * TILE] = a.lut[512 + ((vb[y >> 2] >> (8 * (y & 3))) & 0xff)];
     }
   }
   __syncthreads();
@@ -494,32 +471,32 @@ int launch_h(const HArgs& h, dim3 grid, size_t smem, cudaStream_t st) {
 extern "C" int vz_preprocess3(const vz_image_desc* images, int n_images, const vz_prim* prims, int n_prims,
                               const vz_hview_desc* hviews, int n_hviews, const vz_tile_desc* tiles, int n_tiles,
                               const int32_t* tables, const float* lut768, int out_mode, void* out, void* scratch,
-                              long long scratch_words, int max_span_px, int max_rows, int max_out_w, int max_ksize,
-                              void* stream) {
+                              long long scratch_words, int max_span_px, int max_rows, int max_out_w, int max_groups,
+                              int max_band_groups, void* stream) {
   using namespace vz;
   if (!images || !hviews || !tiles || !tables || !lut768 || !out || !scratch) return VZ_ERR_BAD_ARG;
   if (n_images <= 0 || n_hviews <= 0 || n_tiles <= 0 || scratch_words <= 0) return VZ_ERR_BAD_ARG;
   if (n_prims > 0 && !prims) return VZ_ERR_BAD_ARG;
   if (out_mode != VZ_OUT_PATCHES_BF16 && out_mode != VZ_OUT_CHW_F32) return VZ_ERR_BAD_ARG;
-  if (max_span_px <= 0 || max_rows <= 0 || max_out_w <= 0 || max_ksize <= 0 || !aligned16(out) || !aligned16(scratch))
-    return VZ_ERR_BAD_ARG;
+  if (max_span_px <= 0 || max_rows <= 0 || max_out_w <= 0 || max_groups <= 0 || max_band_groups <= 0) return VZ_ERR_BAD_ARG;
+  if (!aligned16(out) || !aligned16(scratch) || !aligned16(tables)) return VZ_ERR_BAD_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int gmax = (max_ksize + 6) >> 2;     // groups of four taps after aligning a window down to 4
-  if (gmax > 16) return VZ_ERR_UNSUPPORTED;  // ksize > 58 (scale > 9.5): use vz_preprocess2
-  const int G = gmax <= 2 ? 2 : gmax <= 4 ? 4 : gmax <= 6 ? 6 : gmax <= 8 ? 8 : gmax <= 12 ? 12 : 16;
+  if (max_groups > 16) return VZ_ERR_UNSUPPORTED;   // ksize > 58 (scale > 9.5): use vz_preprocess2
+  const int G = max_groups <= 2 ? 2 : max_groups <= 4 ? 4 : max_groups <= 6 ? 6 : max_groups <= 8 ? 8 : max_groups <= 12 ? 12 : 16;
+  // ---- vertical pass geometry first: the whole call is refused if its window cannot be staged ----
+  const int stage_bytes = (out_mode == VZ_OUT_CHW_F32) ? 3 * BAND * TILE * 4 : 24 * VZ_PATCH_K * 2;
+  const size_t win_bytes = (size_t)max_band_groups * TILE * 16;
+  const size_t smem_v = (win_bytes > (size_t)stage_bytes ? win_bytes : (size_t)stage_bytes) + (size_t)BAND * max_groups * 16 + 128;
+  if (smem_v > 200 * 1024) return VZ_ERR_UNSUPPORTED;
   // ---- horizontal pass ----
   HArgs h;
   h.images = images; h.prims = prims; h.hviews = hviews; h.tables = tables;
   h.scratch = reinterpret_cast<uint32_t*>(scratch);
-  const int span = max_span_px + 4;                                   // + alignment of the window start
-  h.raw_stride = ((span * 3 + 16 + 16 + 15) / 16) * 16;               // + phase + the 16 bytes the last funnel shift reads
-  h.plane_words = ((span + 3) >> 2) + G + 1;                          // + groups a narrower column does not need
-  int rb = 32;
-  size_t smem_h = 0;
-  for (;; rb >>= 1) {
-    smem_h = (size_t)G * 3 * HX * 4 + (size_t)rb * h.raw_stride + (size_t)3 * rb * h.plane_words * 4;
-    if (smem_h <= 200 * 1024 || rb == 8) break;
-  }
+  h.plane_words = ((max_span_px + 4 + 3) >> 2) + G + 1;   // window aligned down to 4 + groups a narrower column skips
+  static const int rb_env = []() { const char* e = getenv("VZ_PRE_RB"); return e ? atoi(e) : 0; }();
+  int rb = (rb_env == 8 || rb_env == 16 || rb_env == 32) ? rb_env : 16;
+  size_t smem_h = (size_t)3 * rb * h.plane_words * 4;
+  while (smem_h > 96 * 1024 && rb > 8) { rb >>= 1; smem_h = (size_t)3 * rb * h.plane_words * 4; }
   if (smem_h > 200 * 1024) return VZ_ERR_UNSUPPORTED;
   h.rows_per_cta = rb;
   dim3 grid_h((max_out_w + HX - 1) / HX, (max_rows + rb - 1) / rb, n_hviews);
@@ -536,9 +513,8 @@ extern "C" int vz_preprocess3(const vz_image_desc* images, int n_images, const v
   // ---- vertical pass + normalise + patchify ----
   VArgs v;
   v.hviews = hviews; v.tiles = tiles; v.tables = tables; v.lut = lut768;
-  v.scratch = reinterpret_cast<const uint32_t*>(scratch); v.out = out; v.out_mode = out_mode; v.gv = gmax;
-  const int stage_bytes = (out_mode == VZ_OUT_CHW_F32) ? 3 * BAND * TILE * 4 : 24 * VZ_PATCH_K * 2;
-  const size_t smem_v = (size_t)stage_bytes + (size_t)BAND * gmax * 16 + 2 * BAND * 4 + 16;
+  v.scratch = reinterpret_cast<const uint32_t*>(scratch); v.out = out; v.out_mode = out_mode;
+  v.gmax = max_groups; v.win_groups = max_band_groups;
   VZ_ENSURE_DYN_SMEM(pre_v_dp_kernel, 200 * 1024);
   dim3 grid_v(24, n_tiles);
   {

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .anyres import TILE, TablePool, anyres_views, fixed_view, resample_table, single_view
+from .anyres import TILE, TablePool, anyres_views, band_window_groups, fixed_view, resample_table, single_view
 
 OPENAI_CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 OPENAI_CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
@@ -94,6 +94,8 @@ class PreprocessPlan:
     scratch_pixels: int = 0
     max_span_px: int = 1
     max_span128_px: int = 1
+    max_groups: int = 1          # largest G of the dp4a tables
+    max_band_groups: int = 1     # most 4-row groups a 14-row output band's window spans
     all_identity: bool = False   # every tile = the whole of a 336 x 336 image (vz_preprocess_identity)
     max_rows: int = 1
     max_out_w: int = 1
@@ -120,6 +122,7 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
     max_w, algo = 1, 0
     hview_index, hview_list, scratch_px, max_span, max_rows, max_out_w, max_span128 = {}, [], 0, 1, 1, 1, 1
     all_identity = True
+    max_band_groups = 1
     for i, im in enumerate(images):
         if im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3 or not im.is_cuda:
             raise ValueError("images must be uint8 CUDA tensors of shape [H, W, 3]")
@@ -186,15 +189,18 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
             filt = v.get("filt", "lanczos")
             t.tab_h = pool.offset(cW, v["out_w"], filt)
             t.tab_v = pool.offset(cH, v["out_h"], filt)
+            t.tab_v_dp = pool.offset_dp(cH, v["out_h"], filt)
+            max_band_groups = max(max_band_groups, _band_groups(cH, v["out_h"], filt, v["tile_y"] - v["off_y"]))
             hk = (i, t.tab_h)
             if hk not in hview_index:
                 hview_index[hk] = len(hview_list)
                 hvd = _lib.HViewDesc()
                 hvd.image, hvd.tab_h, hvd.out_w, hvd.rows, hvd.offset = i, t.tab_h, v["out_w"], cH, scratch_px
+                hvd.tab_h_dp = pool.offset_dp(cW, v["out_w"], filt)
                 hview_list.append(hvd)
-                # room for both intermediate layouts: RGBX [rows][out_w] (vz_preprocess2) and planar
-                # [3][ceil(rows / 4)][out_w] (vz_preprocess3)
-                scratch_px += max(cH, 3 * ((cH + 3) // 4)) * v["out_w"]
+                # room for both intermediate layouts: RGBX [rows][out_w] words (vz_preprocess2) and
+                # [ceil(rows / 4)][out_w] uint4 (vz_preprocess3); every view starts on a 16-byte boundary
+                scratch_px += (4 * ((cH + 3) // 4) * v["out_w"] + 3) // 4 * 4
                 max_span = max(max_span, _max_span(cW, v["out_w"], filt))
                 max_span128 = max(max_span128, _max_span(cW, v["out_w"], filt, 128))
                 max_rows, max_out_w = max(max_rows, cH), max(max_out_w, v["out_w"])
@@ -218,10 +224,19 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
     plan.max_span_px, plan.max_rows, plan.max_out_w = max_span, max_rows, max_out_w
     plan.max_span128_px = max_span128
     plan.all_identity = all_identity
+    plan.max_groups, plan.max_band_groups = pool.max_groups, max_band_groups
     plan.h2d_bytes = (plan.images_dev.numel() + plan.tiles_dev.numel() + plan.tables_dev.numel() * 4 + plan.hviews_dev.numel() +
                       (plan.prims_dev.numel() if plan.prims_dev is not None else 0) + 768 * 4)
     plan.algorithmic_bytes = algo
     return plan
+
+
+DP_MAX_BAND_GROUPS = 36      # 36 * 336 * 16 B = 194 KB: what the vertical dp4a pass can stage per band
+
+
+@lru_cache(maxsize=4096)
+def _band_groups(in_size: int, out_size: int, filt: str, origin: int) -> int:
+    return band_window_groups(in_size, out_size, filt, origin)
 
 
 @lru_cache(maxsize=512)
@@ -260,12 +275,12 @@ def run_plan(plan: PreprocessPlan, out_mode: str = "patches", out: Optional[torc
     if plan.max_ksize > 1 and form != "fused":
         if plan.scratch is None or plan.scratch.numel() < plan.scratch_pixels:
             plan.scratch = torch.empty(plan.scratch_pixels, dtype=torch.int32, device=dev)
-        if form == "dp" and (plan.max_ksize + 6) // 4 <= 16:
+        if form == "dp" and plan.max_groups <= 16 and plan.max_band_groups <= DP_MAX_BAND_GROUPS:
             st = lib.vz_preprocess3(_lib.ptr(plan.images_dev), plan.n_images, _lib.ptr(plan.prims_dev), plan.n_prims,
                                     _lib.ptr(plan.hviews_dev), plan.n_hviews, _lib.ptr(plan.tiles_dev), T,
                                     _lib.ptr(plan.tables_dev), _lib.ptr(plan.lut_dev), mode, _lib.ptr(out),
                                     _lib.ptr(plan.scratch), plan.scratch_pixels, plan.max_span128_px, plan.max_rows,
-                                    plan.max_out_w, plan.max_ksize, _lib.stream_ptr())
+                                    plan.max_out_w, plan.max_groups, plan.max_band_groups, _lib.stream_ptr())
             _lib.check(st, "vz_preprocess3")
             return out
         st = lib.vz_preprocess2(_lib.ptr(plan.images_dev), plan.n_images, _lib.ptr(plan.prims_dev), plan.n_prims,
