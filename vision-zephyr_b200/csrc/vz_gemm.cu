@@ -8,6 +8,8 @@
 // q/k/v/out/fc1/fc2, K7 the stacked cross-attention K/V projection, K8 the Q-Former linears).
 #include "vz_common.cuh"
 
+#include <unordered_map>
+
 #include <stdlib.h>
 
 #include <atomic>
@@ -622,11 +624,39 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // 3-D bf16 tensor map: dim0 = K (contiguous), dim1 = rows, dim2 = batch; box = {64, box_rows, 1}.
+// A descriptor is a pure function of (address, shape, strides, box), and a forward pass asks for the same few
+// hundred of them on every call (weights and workspace slices do not move), so they are cached per calling
+// thread: the single-image step spent more host time in cuTensorMapEncodeTiled (356 calls) than in launches.
+struct TmapKey {
+  const void* base;
+  long long bstride;
+  int rows, cols, ld, box_rows, batch;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && bstride == o.bstride && rows == o.rows && cols == o.cols && ld == o.ld &&
+           box_rows == o.box_rows && batch == o.batch;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    h ^= (size_t)k.rows * 0xC2B2AE3D27D4EB4Full + (size_t)k.cols * 0x165667B19E3779F9ull + (size_t)k.ld * 31 +
+         (size_t)k.box_rows * 131 + (size_t)k.batch * 1313 + (size_t)k.bstride * 0x27D4EB2F165667C5ull;
+    return h ^ (h >> 29);
+  }
+};
+
 int make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows, int batch,
               long long bstride) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return VZ_ERR_CUDA;
   if (batch <= 1) { batch = 1; bstride = (long long)rows * ld; }
+  static const bool use_cache = []() { const char* e = getenv("VZ_TMAP_CACHE"); return !(e && e[0] == '0'); }();
+  thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  const TmapKey key{base, bstride, rows, cols, ld, box_rows, batch};
+  if (use_cache) {
+    auto it = cache.find(key);
+    if (it != cache.end()) { *tm = it->second; return VZ_OK; }
+  }
   cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
   cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)bstride * 2};
   cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
@@ -634,9 +664,21 @@ int make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
+    // a thread that has made no runtime call yet (PyTorch's autograd worker entering a backward) has no
+    // current driver context: let the runtime bind the primary context of the current device, then retry
+    cudaFree(nullptr);
+    r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) {
     g_last_cuda_error = 100000 + (int)r;
     return VZ_ERR_CUDA;
+  }
+  if (use_cache) {
+    if (cache.size() > 8192) cache.clear();     // a caller that keeps changing buffers: start over
+    cache.emplace(key, *tm);
   }
   return VZ_OK;
 }
@@ -739,6 +781,12 @@ int encode_tmap_2d_bf16(CUtensorMap* tm, const void* base, long long rows, int c
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
+    cudaFree(nullptr);
+    r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) {
     g_last_cuda_error = 100000 + (int)r;
     return VZ_ERR_CUDA;
