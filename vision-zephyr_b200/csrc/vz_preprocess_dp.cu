@@ -45,12 +45,18 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
   asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
-// limbs -> Pillow's clip8((ss + 2^21) >> 22); the sums wrap modulo 2^32, the true total fits in int32
+// limbs -> Pillow's clip8((ss + 2^21) >> 22); the sums wrap modulo 2^32, the true total fits in int32.
+// Two multiply-adds recombine the limbs, one shift, one saturating convert clamps to [0, 255].
 __device__ __forceinline__ uint32_t finish8(uint32_t a0, uint32_t a1, int a2) {
-  const uint32_t t = a0 + (a1 << 8) + ((uint32_t)a2 << 16) + (1u << (PREC - 1));
-  int v = (int)t >> PREC;
-  v = v < 0 ? 0 : (v > 255 ? 255 : v);
-  return (uint32_t)v;
+  const uint32_t t = (uint32_t)a2 * 65536u + (a1 * 256u + (a0 + (1u << (PREC - 1))));
+  const int v = (int)t >> PREC;
+  uint32_t d;
+  asm("cvt.sat.u8.s32 %0, %1;" : "=r"(d) : "r"(v));
+  return d;
+}
+// byte k of `word` := the low byte of v (k is a constant after unrolling: one PRMT)
+__device__ __forceinline__ uint32_t put_byte_rt(uint32_t word, uint32_t v, int k) {
+  return __byte_perm(word, v, k == 0 ? 0x3214 : k == 1 ? 0x3240 : k == 2 ? 0x3410 : 0x4210);
 }
 
 // Pillow AlphaComposite.c with an opaque destination
@@ -92,6 +98,41 @@ __device__ __forceinline__ DpTable dp_table(const int32_t* tables, int off) {
   return d;
 }
 
+// The horizontal filter of one thread: column x, row quads q, q + 2, ...; GG groups of four taps (compile time).
+template <int GG>
+__device__ __forceinline__ void h_filter(const uint32_t* __restrict__ pl, const uint4* __restrict__ cop, int G, bool valid,
+                                         int RB, int plane_words, int nrows, int q, uint4* __restrict__ inter, int rq0,
+                                         int out_w, int x) {
+  uint4 co[GG];
+#pragma unroll
+  for (int g = 0; g < GG; ++g) co[g] = (valid && g < G) ? __ldg(cop + g) : make_uint4(0u, 0u, 0u, 0u);
+  const int nrq = (nrows + 3) >> 2;
+  for (int rq = q; rq < nrq; rq += 2) {
+    uint32_t o[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int r = rq * 4 + rr;
+      if (r < nrows) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const uint32_t* pw = pl + (c * RB + r) * plane_words;
+          uint32_t a0 = 0u, a1 = 0u;
+          int a2 = 0;
+#pragma unroll
+          for (int g = 0; g < GG; ++g) {
+            const uint32_t p = pw[g];
+            a0 = dp4a_uu(p, co[g].x, a0);
+            a1 = dp4a_uu(p, co[g].y, a1);
+            a2 = dp4a_us(p, co[g].z, a2);
+          }
+          o[c] = put_byte_rt(o[c], finish8(a0, a1, a2), rr);
+        }
+      }
+    }
+    if (valid) inter[(size_t)(rq0 + rq) * out_w + x] = make_uint4(o[0], o[1], o[2], 0u);
+  }
+}
+
 struct HArgs {
   const vz_image_desc* images;
   const vz_prim* prims;
@@ -131,95 +172,75 @@ __global__ void __launch_bounds__(HT) pre_h_dp_kernel(const HArgs a) {
   const int xlast = min(x0 + HX - 1, hv.out_w - 1);
   const int base = th.abase[x0];                                      // plane byte 0 = canvas column `base` (multiple of 4)
   const int nvec = ((th.abase[xlast] - base) >> 2) + th.ngrp[xlast];  // plane words that carry data
-  // this thread's coefficient words (registers, static indices) and its first plane word
-  uint4 co[GMAX];
-#pragma unroll
-  for (int g = 0; g < GMAX; ++g) co[g] = (valid && g < G) ? __ldg(th.coef + (size_t)x * G + g) : make_uint4(0u, 0u, 0u, 0u);
-  const int wb = valid ? (th.abase[x] - base) >> 2 : 0;
+  const int wb = valid ? (th.abase[x] - base) >> 2 : 0;   // this thread's first plane word
 
-  // ---- de-interleave (+ canvas padding, + visual prompts) into byte planes, four pixels per thread ----
+  // ---- de-interleave (+ canvas padding, + visual prompts) into byte planes: one warp per row, four pixels per lane ----
   const uint32_t bgw = im.bg & 0xffffffu;
-  for (int it = tid; it < nrows * nvec; it += HT) {
-    const int r = it / nvec, v = it - r * nvec;
-    const int cx = base + 4 * v, yr = y0 + r - im.pad_y;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int r = warp; r < nrows; r += HT / 32) {
+    const int yr = y0 + r - im.pad_y;
     const bool row_real = yr >= 0 && yr < im.H;
-    const int xr0 = cx - im.pad_x;
-    uint32_t R, Gc, B;
-    if (row_real && xr0 >= 0 && xr0 + 3 < im.W && n_prims == 0) {
-      const uint8_t* p = im.src + ((size_t)yr * im.W + xr0) * 3;      // 12 bytes from here, any alignment
-      const uint32_t* wp = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
-      const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3) * 8u;
-      const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
-      const uint32_t w3 = sh ? __ldg(wp + 3) : 0u;                    // holds bytes of these pixels iff p is unaligned
-      const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh);
-      // a0 = R0 G0 B0 R1 | a1 = G1 B1 R2 G2 | a2 = B2 R3 G3 B3   (byte 0 first)
-      R = __byte_perm(__byte_perm(a0, a1, 0x0630), a2, 0x5210);
-      Gc = __byte_perm(__byte_perm(a0, a1, 0x0741), a2, 0x6210);
-      B = __byte_perm(__byte_perm(a0, a1, 0x0052), a2, 0x7410);
-    } else {
-      R = Gc = B = 0u;
+    const uint8_t* rowp = im.src + (size_t)(row_real ? yr : 0) * im.W * 3;
+    for (int v = lane; v < nvec; v += 32) {
+      const int xr0 = base + 4 * v - im.pad_x;
+      uint32_t R, Gc, B;
+      if (row_real && xr0 >= 0 && xr0 + 3 < im.W && n_prims == 0) {
+        const uint8_t* p = rowp + (size_t)xr0 * 3;                       // 12 bytes from here, any alignment
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3) * 8u;
+        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+        const uint32_t w3 = sh ? __ldg(wp + 3) : 0u;                    // holds bytes of these pixels iff p is unaligned
+        const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh);
+        // a0 = R0 G0 B0 R1 | a1 = G1 B1 R2 G2 | a2 = B2 R3 G3 B3   (byte 0 first)
+        R = __byte_perm(__byte_perm(a0, a1, 0x0630), a2, 0x5210);
+        Gc = __byte_perm(__byte_perm(a0, a1, 0x0741), a2, 0x6210);
+        B = __byte_perm(__byte_perm(a0, a1, 0x0052), a2, 0x7410);
+      } else {
+        R = Gc = B = 0u;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int xr = xr0 + i;
-        int rr, gg, bb;
-        if (row_real && xr >= 0 && xr < im.W) {
-          const uint8_t* p = im.src + ((size_t)yr * im.W + xr) * 3;
-          rr = __ldg(p); gg = __ldg(p + 1); bb = __ldg(p + 2);
-          for (int pi = 0; pi < n_prims; ++pi) {
-            const vz_prim& pr = s_prims[pi];
-            uint32_t ov;
-            if (pr.type == VZ_PRIM_LAYER) {
-              ov = __ldg(reinterpret_cast<const uint32_t*>(im.layers) + ((size_t)pr.layer * im.H + yr) * im.W + xr);
-            } else {
-              if (!rect_covers(pr, xr, yr)) continue;
-              ov = pr.rgba;
+        for (int i = 0; i < 4; ++i) {
+          const int xr = xr0 + i;
+          int rr, gg, bb;
+          if (row_real && xr >= 0 && xr < im.W) {
+            const uint8_t* p = rowp + (size_t)xr * 3;
+            rr = __ldg(p); gg = __ldg(p + 1); bb = __ldg(p + 2);
+            for (int pi = 0; pi < n_prims; ++pi) {
+              const vz_prim& pr = s_prims[pi];
+              uint32_t ov;
+              if (pr.type == VZ_PRIM_LAYER) {
+                ov = __ldg(reinterpret_cast<const uint32_t*>(im.layers) + ((size_t)pr.layer * im.H + yr) * im.W + xr);
+              } else {
+                if (!rect_covers(pr, xr, yr)) continue;
+                ov = pr.rgba;
+              }
+              const int al = (int)(ov >> 24);
+              rr = blend_over(rr, (int)(ov & 0xff), al);
+              gg = blend_over(gg, (int)((ov >> 8) & 0xff), al);
+              bb = blend_over(bb, (int)((ov >> 16) & 0xff), al);
             }
-            const int al = (int)(ov >> 24);
-            rr = blend_over(rr, (int)(ov & 0xff), al);
-            gg = blend_over(gg, (int)((ov >> 8) & 0xff), al);
-            bb = blend_over(bb, (int)((ov >> 16) & 0xff), al);
+          } else {   // canvas padding (expand2square, mm_utils.py:16-35)
+            rr = (int)(bgw & 0xff); gg = (int)((bgw >> 8) & 0xff); bb = (int)((bgw >> 16) & 0xff);
           }
-        } else {   // canvas padding (expand2square, mm_utils.py:16-35)
-          rr = (int)(bgw & 0xff); gg = (int)((bgw >> 8) & 0xff); bb = (int)((bgw >> 16) & 0xff);
+          R |= (uint32_t)rr << (8 * i); Gc |= (uint32_t)gg << (8 * i); B |= (uint32_t)bb << (8 * i);
         }
-        R |= (uint32_t)rr << (8 * i); Gc |= (uint32_t)gg << (8 * i); B |= (uint32_t)bb << (8 * i);
       }
+      s_pl[(0 * RB + r) * a.plane_words + v] = R;
+      s_pl[(1 * RB + r) * a.plane_words + v] = Gc;
+      s_pl[(2 * RB + r) * a.plane_words + v] = B;
     }
-    s_pl[(0 * RB + r) * a.plane_words + v] = R;
-    s_pl[(1 * RB + r) * a.plane_words + v] = Gc;
-    s_pl[(2 * RB + r) * a.plane_words + v] = B;
   }
   __syncthreads();
 
-  // ---- filter: thread = (column x, four consecutive rows), one intermediate uint4 (R, G, B words) ----
-  const int nrq = (nrows + 3) >> 2;
+  // ---- filter: thread = (column x, four consecutive rows), one intermediate uint4 (R, G, B words).  The loop
+  // is instantiated for the view's group count rounded up within the kernel's class (a 1.5x downscale next to
+  // a 3x one in the same launch should not pay for the longer filter) ----
   uint4* inter = reinterpret_cast<uint4*>(a.scratch + hv.offset);
-  for (int rq = q; rq < nrq; rq += 2) {
-    uint32_t o[3] = {0u, 0u, 0u};
-#pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      const int r = rq * 4 + rr;
-      if (r < nrows) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const uint32_t* pw = s_pl + (c * RB + r) * a.plane_words + wb;
-          uint32_t a0 = 0u, a1 = 0u;
-          int a2 = 0;
-#pragma unroll
-          for (int g = 0; g < GMAX; ++g) {
-            if (g < G) {
-              const uint32_t p = pw[g];
-              a0 = dp4a_uu(p, co[g].x, a0);
-              a1 = dp4a_uu(p, co[g].y, a1);
-              a2 = dp4a_us(p, co[g].z, a2);
-            }
-          }
-          o[c] |= finish8(a0, a1, a2) << (8 * rr);
-        }
-      }
-    }
-    if (valid) inter[(size_t)((y0 >> 2) + rq) * hv.out_w + x] = make_uint4(o[0], o[1], o[2], 0u);
-  }
+  const uint4* cop = th.coef + (size_t)(valid ? x : 0) * G;
+  const uint32_t* pl = s_pl + wb;
+  if (GMAX > 4 && G <= (GMAX + 1) / 2 + (GMAX > 8 ? 2 : 1))
+    h_filter<(GMAX + 1) / 2 + (GMAX > 8 ? 2 : 1)>(pl, cop, G, valid, RB, a.plane_words, nrows, q, inter, (y0 >> 2), hv.out_w, x);
+  else
+    h_filter<GMAX>(pl, cop, G, valid, RB, a.plane_words, nrows, q, inter, (y0 >> 2), hv.out_w, x);
 }
 
 struct VArgs {
