@@ -340,8 +340,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
         float4* slot = p.sk_ws + (size_t)(worker * NR + (int)rank) * SK_SLOT4;
+        // rows of this warp's lane quarter that exist (the Q-Former's 32-row problems leave three quarters of a
+        // tile empty: nothing to hand over for them, and the finishing worker does not read them either)
+        const bool live = m_blk * TILE_M + (int)rank * BM + q * 32 < p.M;
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
+        for (int c = half; live && c < BN / 32; c += 2) {
           if (n_blk * BN + c * 32 >= p.N) break;  // warp-uniform
           uint32_t r[32];
           tmem_ld_32x32b_x32(t_row + c * 32, r);
@@ -374,6 +377,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         while (sk_last + 1 < n_workers && (U * (sk_last + 1)) / n_workers < tile_end) ++sk_last;
       }
       const int m_base = m_blk * TILE_M + (int)rank * BM + q * 32;
+      if (m_base >= p.M) {
+        // this warp's 32 rows lie beyond M: keep the accumulator hand-shake going, touch nothing else
+        mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (TWO) mbar_arrive_cluster(&tempty_bar[acc], 0);
+          else mbar_arrive(&tempty_bar[acc]);
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       const float* bias_b = p.bias ? p.bias + (size_t)bz * p.bias_bstride : nullptr;
       const __nv_bfloat16* res_b = RES ? p.residual + (size_t)bz * p.r_bstride : nullptr;
       __nv_bfloat16* out_b = p.out + (size_t)bz * p.o_bstride;
