@@ -320,6 +320,32 @@ def bench_c5(dev, lut, steps, llm_layers=32):
         assert out.logits.shape[0] == B and torch.isfinite(out.logits.float()).all()
         ms_total = event_time(prefill, max(3, steps // 4), warmup=1)
         ms_llm = event_time(llm_only, max(3, steps // 4), warmup=1)
+        # SURVEY 8(f) rank 3, the hand-over half of it: the splice's per-sample lengths let the LLM skip the padding
+        # altogether -- the real rows are packed into ONE sequence with restarting position ids, which HF Mistral
+        # runs as variable-length attention (flash-attn 2, library code).  Best effort: reported when the installed
+        # flash-attn runs on this GPU.
+        packed = {"error": None}
+        try:
+            keep = r[2].bool()
+            emb_p = r[4][keep].unsqueeze(0)
+            pos_p = (torch.cumsum(keep.long(), 1) - 1)[keep].unsqueeze(0)
+            last = torch.cumsum(keep.sum(1), 0) - 1
+            model.set_attn_implementation("flash_attention_2")
+
+            def llm_packed():
+                return model(inputs_embeds=emb_p, position_ids=pos_p, use_cache=False, logits_to_keep=last)
+
+            o2 = llm_packed()
+            assert o2.logits.shape[:2] == (1, B) and torch.isfinite(o2.logits.float()).all()
+            packed["llm_only_ms"] = event_time(llm_packed, max(3, steps // 4), warmup=1)
+            packed["tokens"] = int(emb_p.shape[1])
+        except Exception as e:
+            packed["error"] = f"{type(e).__name__}: {e}"[:300]
+        finally:
+            try:
+                model.set_attn_implementation("sdpa")
+            except Exception:
+                pass
     # the scatter alone at this geometry (HBM-bound): bytes = SURVEY 8(d)(4)
     from vision_zephyr_b200 import arch
     ctx = model._plan_splice(ids, mask, labels, [TILES_PER_IMAGE] * B, sizes)
@@ -347,6 +373,7 @@ def bench_c5(dev, lut, steps, llm_layers=32):
     return {"path_ms_per_step": ms_path, "path_images_per_s": B / ms_path * 1e3,
             "prefill_ms_total": ms_total, "llm_only_ms": ms_llm, "path_share_of_prefill": ms_path / ms_total,
             "spliced_tokens": real, "padded_tokens": B * Lmax, "prefill_tokens_per_s": real / ms_total * 1e3,
+            "packed_varlen_prefill": packed,
             "Lmax": Lmax, "L_text": max(lens) - 1, "text_lens": lens, "gpu_launches_per_step": launches,
             "llm_build_s": build_s,
             "splice_scatter": {"bound": "hbm", "achieved": sc_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
