@@ -283,10 +283,14 @@ typedef struct {
   vz_vit_layer layers[VZ_VIT_LAYERS];
 } vz_vit_weights;
 
+/* workspace of vz_vit_forward: a ring of six hidden-state buffers (the fusion takes each group's mean as soon
+ * as the group is complete); keep_hidden = 1 sizes it for hidden_out != NULL (all 25 states kept, tests). */
 size_t vz_vit_workspace_bytes(int T);
+size_t vz_vit_workspace_bytes_ex(int T, int keep_hidden);
 
 /* CLIP self-attention alone (HF CLIPAttention): qkv bf16 [T*577, 3072] (q | k | v, 16 heads x 64)
- * -> out bf16 [T*577, 1024].  impl: 1 = tcgen05/TMEM kernel, 0 = legacy mma.sync kernel, -1 = default. */
+ * -> out bf16 [T*577, 1024].  impl: 1 or -1 = the tcgen05/TMEM kernel; 0 (the first, mma.sync implementation)
+ * returns VZ_ERR_UNSUPPORTED: that kernel is test infrastructure now (libvz_b200_testonly.so).             */
 int vz_vit_attention(const void* qkv, void* out, int T, int impl, void* stream);
 
 /* patches: bf16 [T*576,592].  fused_out: bf16 [T*576,5120] =
@@ -294,7 +298,7 @@ int vz_vit_attention(const void* qkv, void* out, int T, int impl, void* stream);
  * If norm_g/norm_b are non-NULL the QFormer.pre_norm LayerNorm(5120)
  * (multimodal_projector/builder.py:68,74) is applied in the same kernel.
  * hidden_out (optional, may be NULL): bf16 [25][T*577,1024] copy-out of all hidden states
- * (tests only).                                                                                */
+ * (tests only; the workspace must then be sized with vz_vit_workspace_bytes_ex(T, 1)).           */
 int vz_vit_forward(const vz_vit_weights* w, const void* patches, int T, void* fused_out,
                    const float* norm_g, const float* norm_b, void* hidden_out, void* workspace,
                    size_t workspace_bytes, int force_simple_gemm, void* stream);

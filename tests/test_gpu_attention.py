@@ -133,7 +133,16 @@ def test_vit_attention_kernels_match_torch(impl):
     qkv = _rand((T * 577, 3072), 1.0, 31)
     qkv[:, :2048] *= 1.7          # sharper softmax
     out = torch.full((T * 577, 1024), float("nan"), dtype=torch.bfloat16, device="cuda")
-    L.check(lib.vz_vit_attention(L.ptr(qkv), L.ptr(out), T, impl, L.stream_ptr()), "vit attention")
+    if impl == 1:
+        L.check(lib.vz_vit_attention(L.ptr(qkv), L.ptr(out), T, 1, L.stream_ptr()), "vit attention")
+    else:
+        # the first (mma.sync) implementation: an independent cross-check kept OUT of the product library
+        import ctypes
+        import os
+        assert lib.vz_vit_attention(L.ptr(qkv), L.ptr(out), T, 0, L.stream_ptr()) == -2      # VZ_ERR_UNSUPPORTED
+        tl = ctypes.CDLL(os.path.join(os.path.dirname(L.LIB_PATH), "libvz_b200_testonly.so"))
+        tl.vz_test_vit_attention_legacy.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_int, ctypes.c_void_p]
+        L.check(tl.vz_test_vit_attention_legacy(L.ptr(qkv), L.ptr(out), T, L.stream_ptr()), "legacy vit attention")
     torch.cuda.synchronize()
     q, k, v = (qkv.float().view(T, 577, 3, 16, 64)[:, :, i].transpose(1, 2) for i in range(3))
     ref = torch.softmax((q @ k.transpose(-1, -2)) * 0.125, dim=-1) @ v

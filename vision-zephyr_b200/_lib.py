@@ -115,6 +115,7 @@ SYMBOLS = {
     "vz_preprocess_identity": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "vz_patchify": (_i, [_vp, _i, _i, _vp, _vp]),
     "vz_vit_workspace_bytes": (_sz, [_i]),
+    "vz_vit_workspace_bytes_ex": (_sz, [_i, _i]),
     "vz_vit_attention": (_i, [_vp, _vp, _i, _i, _vp]),
     "vz_vit_forward": (_i, [C.POINTER(VitWeights), _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "vz_qformer_workspace_bytes": (_sz, [_i, _i, _i]),

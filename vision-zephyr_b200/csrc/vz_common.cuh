@@ -74,13 +74,13 @@ int row_stats_launch(const void* x, int ldx, int M, int D, float* stats, cudaStr
 int layernorm_launch(const void* x, int ldx, const float* g, const float* b, void* out, int ldo,
                      int M, int D, float eps, const int32_t* row_map, int rows_per_map,
                      cudaStream_t st);
-int fuse_launch(const void* const* hs21, int T, const float* g, const float* b, void* out,
-                cudaStream_t st);
+int group_mean_launch(const void* const* hs5, int T, void* means, int group, cudaStream_t st);
+int fuse_tail_launch(const void* means, const void* last, int T, const float* g, const float* b, void* out,
+                     cudaStream_t st);
 int cls_rows_launch(const void* cls, const void* pos, void* emb, int T, cudaStream_t st);
 int gather_rows_launch(const void* in, void* out, int M, int row_bytes, const int32_t* row_map,
                        int rows_per, cudaStream_t st);
 int softmax_rows_launch(const float* s, void* p, int rows, int n, float scale, cudaStream_t st);
-int vit_attn_launch(const void* qkv, void* out, int T, cudaStream_t st);
 int vit_attn_tc_launch(const void* qkv, void* out, int T, cudaStream_t st);
 int encode_tmap_2d_bf16(CUtensorMap* tm, const void* base, long long rows, int cols, int ld, int box_cols, int box_rows);
 int encode_tmap_3d_bf16(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows, int batch, long long bstride);

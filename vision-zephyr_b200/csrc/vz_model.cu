@@ -79,7 +79,8 @@ int gemm_batched(const void* A, int lda, long long sa, const void* W, int ldw, l
 }
 
 struct VitWs {
-  void* hs[VZ_VIT_LAYERS + 1];
+  void* hs[VZ_VIT_LAYERS + 1];   // keep_all: 25 buffers; else a ring of 6 (hs[i] lives in slot i % 6)
+  void* means;                   // bf16 [P][4][1024]: the four group means of the fusion
   void *qkv, *attn, *mid, *h;
   float *statsA, *statsB;  // [M][<=16][2] partial row statistics (LayerNorm fused into the GEMMs)
   void* sk;                // stream-K scratch of the GEMMs
@@ -87,13 +88,20 @@ struct VitWs {
   size_t total;
 };
 
-VitWs vit_layout(void* base, int T) {
+// The fusion needs hidden_states[4..24] in groups of five; each group's mean is taken as soon as its last layer
+// is done, so a ring of SIX hidden-state buffers is enough (five of a group + the one being written): 0.28 GB
+// instead of 1.18 GB at 40 tiles.  keep_all (tests: hidden_out) keeps all 25, contiguous.
+constexpr int kHsRing = 6;
+
+VitWs vit_layout(void* base, int T, bool keep_all) {
   Bump b{reinterpret_cast<uint8_t*>(base), 0, 0};
   const size_t M = (size_t)T * VZ_VIT_TOKENS;
   VitWs w;
-  // hidden states are contiguous so tests can copy them out in one go
-  uint8_t* hs0 = reinterpret_cast<uint8_t*>(b.take((VZ_VIT_LAYERS + 1) * M * VZ_VIT_WIDTH * kB16));
-  for (int i = 0; i <= VZ_VIT_LAYERS; ++i) w.hs[i] = base ? hs0 + (size_t)i * M * VZ_VIT_WIDTH * kB16 : nullptr;
+  const int nbuf = keep_all ? VZ_VIT_LAYERS + 1 : kHsRing;
+  uint8_t* hs0 = reinterpret_cast<uint8_t*>(b.take((size_t)nbuf * M * VZ_VIT_WIDTH * kB16));
+  for (int i = 0; i <= VZ_VIT_LAYERS; ++i)
+    w.hs[i] = base ? hs0 + (size_t)(keep_all ? i : i % kHsRing) * M * VZ_VIT_WIDTH * kB16 : nullptr;
+  w.means = b.take((size_t)T * VZ_VIT_PATCHES * 4 * VZ_VIT_WIDTH * kB16);
   w.qkv = b.take(M * 3 * VZ_VIT_WIDTH * kB16);
   w.attn = b.take(M * VZ_VIT_WIDTH * kB16);
   w.mid = b.take(M * VZ_VIT_WIDTH * kB16);
@@ -148,20 +156,19 @@ QfWs qf_layout(void* base, int T, int n_samples, int text_rows) {
 
 using namespace vz;
 
-// impl: 1 = tcgen05 kernel, 0 = legacy mma.sync kernel, -1 = default (tcgen05 unless the
-// environment variable VZ_VIT_ATTN_LEGACY=1 is set; bring-up switch only)
+// impl: 1 or -1 = the tcgen05 kernel.  (impl 0 used to select the first, mma.sync implementation; that kernel now
+// lives in libvz_b200_testonly.so as a cross-check for the tests and is not reachable from this library.)
 extern "C" int vz_vit_attention(const void* qkv, void* out, int T, int impl, void* stream) {
   if (!qkv || !out || T <= 0) return VZ_ERR_BAD_ARG;
   if (!aligned16(qkv) || !aligned16(out)) return VZ_ERR_BAD_ARG;
-  if (impl < 0) {
-    static const int legacy = []() { const char* e = getenv("VZ_VIT_ATTN_LEGACY"); return (e && e[0] == '1') ? 1 : 0; }();
-    impl = legacy ? 0 : 1;
-  }
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return impl ? vit_attn_tc_launch(qkv, out, T, st) : vit_attn_launch(qkv, out, T, st);
+  if (impl == 0) return VZ_ERR_UNSUPPORTED;
+  return vit_attn_tc_launch(qkv, out, T, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" size_t vz_vit_workspace_bytes(int T) { return T > 0 ? vit_layout(nullptr, T).total : 0; }
+extern "C" size_t vz_vit_workspace_bytes(int T) { return T > 0 ? vit_layout(nullptr, T, false).total : 0; }
+extern "C" size_t vz_vit_workspace_bytes_ex(int T, int keep_hidden) {
+  return T > 0 ? vit_layout(nullptr, T, keep_hidden != 0).total : 0;
+}
 
 extern "C" size_t vz_qformer_workspace_bytes(int T, int n_samples, int text_rows) {
   return T > 0 ? qf_layout(nullptr, T, n_samples, text_rows < 0 ? 0 : text_rows).total : 0;
@@ -173,7 +180,7 @@ extern "C" int vz_vit_forward(const vz_vit_weights* w, const void* patches, int 
   if (!w || !patches || !fused_out || !workspace || T <= 0) return VZ_ERR_BAD_ARG;
   if ((norm_g == nullptr) != (norm_b == nullptr)) return VZ_ERR_BAD_ARG;
   if (!aligned16(workspace) || !aligned16(patches) || !aligned16(fused_out)) return VZ_ERR_BAD_ARG;
-  const VitWs ws = vit_layout(workspace, T);
+  const VitWs ws = vit_layout(workspace, T, hidden_out != nullptr);
   if (ws.total > workspace_bytes) return VZ_ERR_WORKSPACE;
   const Ctx st{reinterpret_cast<cudaStream_t>(stream), ws.sk, ws.sk_bytes};
   VZ_CUDA_CHECK(cudaMemsetAsync(ws.sk, 0, 8192, st));   // stream-K hand-over flags (epoch 0 = nothing there)
@@ -206,9 +213,14 @@ extern "C" int vz_vit_forward(const vz_vit_weights* w, const void* patches, int 
     VZ_TRY(gemm_ln(ws.h, VZ_VIT_MLP, L.w_fc2, VZ_VIT_MLP, M, D, VZ_VIT_MLP, L.b_fc2, VZ_ACT_NONE, ws.mid, D,
                    ws.hs[l + 1], D, nullptr, 0, nullptr, ws.statsA, np_gemm, simple, st));
     npA = np_gemm;
+    // hidden_states[-21:] = h4..h24 in groups of five: the mean of h4..h8 (h9..h13, h14..h18, h19..h23) is
+    // taken right after the group's last state exists, before the ring overwrites its first
+    const int done = l + 1;
+    if (done >= 8 && done <= 23 && (done - 8) % 5 == 0)
+      VZ_TRY(group_mean_launch(&ws.hs[done - 4], T, ws.means, (done - 8) / 5, st));
   }
-  // hidden_states[-21:], CLS dropped, 4 x mean-of-5 + last (+ pre_norm)
-  VZ_TRY(fuse_launch(&ws.hs[4], T, norm_g, norm_b, fused_out, st));
+  // cat(4 means, h24), CLS dropped (+ pre_norm)
+  VZ_TRY(fuse_tail_launch(ws.means, ws.hs[VZ_VIT_LAYERS], T, norm_g, norm_b, fused_out, st));
   if (hidden_out) {
     VZ_CUDA_CHECK(cudaMemcpyAsync(hidden_out, ws.hs[0], (size_t)(VZ_VIT_LAYERS + 1) * M * D * kB16,
                                   cudaMemcpyDeviceToDevice, st));

@@ -82,45 +82,52 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
 }
 
 // ------------------------------------------------------------------------------------------
-// Fusion (+ optional QFormer.pre_norm): per patch row, 4 x mean-of-5 hidden states + last layer,
-// concatenated on channels -> 5120, rounded to bf16 like the reference's bf16 torch.mean
-// (gating_fusion.py:36-48), CLS row dropped (vision_encoder.py:68), then LayerNorm(5120)
-// (multimodal_projector/builder.py:74) when gamma != NULL.
-// 128 threads: thread owns channels [8*tid, 8*tid+8) of every group.
+// Fusion (+ optional QFormer.pre_norm) in two kernels: group_mean_kernel (one launch per group of five hidden
+// states, as soon as the group is complete) and fuse_tail_kernel (concatenate on channels -> 5120, CLS row
+// dropped (vision_encoder.py:68), LayerNorm(5120)).  128 threads per patch row.
 // ------------------------------------------------------------------------------------------
-struct FuseArgs {
-  const __nv_bfloat16* hs[21];  // hidden_states[4..24], each [T*577,1024]
+struct Mean5Args {
+  const __nv_bfloat16* hs[5];   // five consecutive hidden states, each [T*577,1024]
 };
 
+// mean of five consecutive hidden states (CLS dropped), rounded to bf16 like the reference's bf16 stack().mean()
+// (gating_fusion.py:36-44), written to columns [1024 grp, 1024 grp + 1024) of means[T*576][4096].  Runs as soon as
+// the group's last layer is done, so only six hidden states are alive at any time.
 __global__ void __launch_bounds__(128)
-fuse_kernel(const FuseArgs a, const float* __restrict__ g, const float* __restrict__ b,
-            __nv_bfloat16* __restrict__ out, float eps) {
-  __shared__ float red[32];
+group_mean_kernel(const Mean5Args a, __nv_bfloat16* __restrict__ means, int grp) {
   const int row = blockIdx.x;  // t*576 + p
   const int t = row / VZ_VIT_PATCHES, pidx = row - t * VZ_VIT_PATCHES;
   const size_t src = ((size_t)t * VZ_VIT_TOKENS + 1 + pidx) * VZ_VIT_WIDTH + threadIdx.x * 8;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const uint4 w = *reinterpret_cast<const uint4*>(a.hs[j] + src);
+    float f[8];
+    unpack8(w, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += f[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] *= 0.2f;
+  *reinterpret_cast<uint4*>(means + (size_t)row * (4 * VZ_VIT_WIDTH) + grp * VZ_VIT_WIDTH + threadIdx.x * 8) = pack8(acc);
+}
+
+// cat(4 group means, last hidden state) -> [T*576, 5120], with QFormer.pre_norm (LayerNorm(5120),
+// multimodal_projector/builder.py:74) applied when gamma != NULL.  128 threads: thread owns channels
+// [8*tid, 8*tid+8) of every group.
+__global__ void __launch_bounds__(128)
+fuse_tail_kernel(const __nv_bfloat16* __restrict__ means, const __nv_bfloat16* __restrict__ last,
+                 const float* __restrict__ g, const float* __restrict__ b, __nv_bfloat16* __restrict__ out, float eps) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;  // t*576 + p
+  const int t = row / VZ_VIT_PATCHES, pidx = row - t * VZ_VIT_PATCHES;
   float v[5][8];
 #pragma unroll
-  for (int grp = 0; grp < 4; ++grp) {
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const uint4 w = *reinterpret_cast<const uint4*>(a.hs[grp * 5 + j] + src);
-      float f[8];
-      unpack8(w, f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += f[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      v[grp][i] = __bfloat162float(__float2bfloat16_rn(acc[i] * 0.2f));
-  }
-  {
-    const uint4 w = *reinterpret_cast<const uint4*>(a.hs[20] + src);
-    unpack8(w, v[4]);
-  }
+  for (int grp = 0; grp < 4; ++grp)
+    unpack8(*reinterpret_cast<const uint4*>(means + (size_t)row * (4 * VZ_VIT_WIDTH) + grp * VZ_VIT_WIDTH + threadIdx.x * 8), v[grp]);
+  unpack8(*reinterpret_cast<const uint4*>(last + ((size_t)t * VZ_VIT_TOKENS + 1 + pidx) * VZ_VIT_WIDTH + threadIdx.x * 8), v[4]);
   __nv_bfloat16* o = out + (size_t)row * VZ_FUSED_WIDTH + threadIdx.x * 8;
   if (g == nullptr) {
 #pragma unroll
@@ -288,13 +295,23 @@ int layernorm_launch(const void* x, int ldx, const float* g, const float* b, voi
   return VZ_OK;
 }
 
-int fuse_launch(const void* const* hs21, int T, const float* g, const float* b, void* out,
-                cudaStream_t st) {
-  FuseArgs a;
-  for (int i = 0; i < 21; ++i) a.hs[i] = reinterpret_cast<const __nv_bfloat16*>(hs21[i]);
-  // algorithmic bytes: 21 hidden-state rows of 1024 bf16 read + one fused row of 5120 bf16 written, per patch
-  ProfScope prof(VZ_PROF_FUSE, (double)T * VZ_VIT_PATCHES * (21.0 * VZ_VIT_WIDTH + VZ_FUSED_WIDTH) * 2.0, st);
-  fuse_kernel<<<T * VZ_VIT_PATCHES, 128, 0, st>>>(a, g, b, reinterpret_cast<__nv_bfloat16*>(out), 1e-5f);
+int group_mean_launch(const void* const* hs5, int T, void* means, int group, cudaStream_t st) {
+  Mean5Args a;
+  for (int i = 0; i < 5; ++i) a.hs[i] = reinterpret_cast<const __nv_bfloat16*>(hs5[i]);
+  // algorithmic bytes: five hidden-state rows of 1024 bf16 read + one mean slice written, per patch
+  ProfScope prof(VZ_PROF_FUSE, (double)T * VZ_VIT_PATCHES * 6.0 * VZ_VIT_WIDTH * 2.0, st);
+  group_mean_kernel<<<T * VZ_VIT_PATCHES, 128, 0, st>>>(a, reinterpret_cast<__nv_bfloat16*>(means), group);
+  VZ_LAUNCH_CHECK();
+  return VZ_OK;
+}
+
+int fuse_tail_launch(const void* means, const void* last, int T, const float* g, const float* b, void* out,
+                     cudaStream_t st) {
+  // algorithmic bytes: 4 mean slices + the last hidden state read, one fused row of 5120 bf16 written, per patch
+  ProfScope prof(VZ_PROF_FUSE, (double)T * VZ_VIT_PATCHES * (5.0 * VZ_VIT_WIDTH + VZ_FUSED_WIDTH) * 2.0, st);
+  fuse_tail_kernel<<<T * VZ_VIT_PATCHES, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(means),
+                                                       reinterpret_cast<const __nv_bfloat16*>(last), g, b,
+                                                       reinterpret_cast<__nv_bfloat16*>(out), 1e-5f);
   VZ_LAUNCH_CHECK();
   return VZ_OK;
 }

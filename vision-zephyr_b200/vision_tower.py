@@ -206,7 +206,7 @@ class CLIPVisionTowerB200(nn.Module):
         T = patches.shape[0] // PATCHES
         dev = patches.device
         fused = torch.empty((T, PATCHES, 5 * WIDTH), dtype=torch.bfloat16, device=dev)
-        nbytes = lib.vz_vit_workspace_bytes(T)
+        nbytes = lib.vz_vit_workspace_bytes_ex(T, 1 if return_hidden else 0)
         ws = self._ws.get(nbytes, dev)
         hidden = torch.empty((LAYERS + 1, T, TOKENS, WIDTH), dtype=torch.bfloat16, device=dev) if return_hidden else None
         g = b = None
