@@ -10,9 +10,15 @@
  * Conventions
  *   - extern "C", plain pointers and sizes, no torch / C++ types.
  *   - every pointer is a DEVICE pointer unless its name ends in _h (host).
- *   - every launch goes to the cudaStream_t passed last (as void*); no entry point allocates,
- *     synchronises or keeps mutable global state, so the library is re-entrant
- *     (reference threading note: vis_zephyr/serve/api.py:161-177).
+ *   - every launch goes to the cudaStream_t passed last (as void*); no entry point allocates or
+ *     synchronises, and every buffer an entry point writes is handed in by the caller (outputs, workspace,
+ *     stream-K scratch).  Two calls may therefore run concurrently on two streams PROVIDED THEY ARE GIVEN
+ *     DISJOINT WORKSPACES -- activations, LayerNorm statistics and the stream-K hand-over slots all live
+ *     there.  The Python layer keys its workspaces by (device, stream) for exactly that reason
+ *     (vision_tower.Workspace; reference threading note: vis_zephyr/serve/api.py:161-177).  Process-wide state
+ *     inside the library is limited to monotonic tickets and caches that are safe to share: the launch
+ *     counter, the stream-K epoch counter (an atomic ticket, unique per launch), the per-THREAD tensor-map
+ *     cache, the per-device `max dynamic shared memory` flags, and the optional profiling hook.
  *   - return value: 0 = ok, <0 = vz_status; vz_status_string() names it.
  *   - bf16 tensors are row-major; "ld" arguments are leading dimensions in ELEMENTS.
  */

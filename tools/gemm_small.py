@@ -49,6 +49,10 @@ def run(name, M, N, K, act, res, sk, cold, reps=30):
     return ts[len(ts) // 2] * 1e3
 
 
+if len(sys.argv) > 1:      # one shape, stream-K on, a few launches: the target of an ncu capture
+    sel = [x for x in SHAPES if x[0] == sys.argv[1]][0]
+    print(sel, run(*sel, True, True, reps=3))
+    sys.exit(0)
 print(f"{'shape':12s} {'M':>4s} {'N':>6s} {'K':>5s}  cold: no-SK / SK (us)   warm: no-SK / SK (us)   W-stream floor (us)")
 for (name, M, N, K, act, res) in SHAPES:
     r = [run(name, M, N, K, act, res, sk, cold) for cold in (True, False) for sk in (False, True)]
