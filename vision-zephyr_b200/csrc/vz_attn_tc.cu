@@ -70,6 +70,16 @@ __device__ __forceinline__ float ex2_poly(float x) {
 }
 // (template parameter PE of the kernel: every PE-th exponential; 0 = all exponentials on the MUFU pipe)
 
+// PE == 2: PACKED exponentials.  P is handed to the tensor core as bf16 anyway, so the exponent is rounded to
+// bf16 BEFORE the exponential and one MUFU instruction produces the two bf16 probabilities of a key pair
+// (ex2.approx.ftz.bf16x2): half the MUFU instructions per key block and no conversion afterwards.  The row sum is
+// taken from the same bf16 values the P V product consumes.
+__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // exp2 may run up to 2^8 above the value it would have with the exact running maximum before the
@@ -143,9 +153,15 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& s, uint32_t g, int j
   for (int i = 0; i < NCOL; i += 2) {
     // keys beyond NVALID are masked: probability 0 without spending an exponential on them
     const float x0 = fmaf(__uint_as_float(v[i]), s.sl2, -m_sl2), x1 = fmaf(__uint_as_float(v[i + 1]), s.sl2, -m_sl2);
-    constexpr int PE1 = PE > 0 ? PE : 1;
-    const bool poly0 = PE > 0 && NCOL == 64 && (i % PE1) == PE1 - 1;      // compile-time after unrolling
-    const bool poly1 = PE > 0 && NCOL == 64 && ((i + 1) % PE1) == PE1 - 1;
+    if constexpr (PE == 2 && NCOL == 64 && NVALID == NCOL) {
+      const uint32_t pb = ex2_bf16x2(pack_bf16x2(x0, x1));
+      pk[i >> 1] = pb;
+      ls4[(i >> 1) % NCH] += __uint_as_float(pb << 16) + __uint_as_float(pb & 0xffff0000u);
+      continue;
+    }
+    constexpr int PE1 = PE > 2 ? PE : 1;
+    const bool poly0 = PE > 2 && NCOL == 64 && (i % PE1) == PE1 - 1;      // compile-time after unrolling
+    const bool poly1 = PE > 2 && NCOL == 64 && ((i + 1) % PE1) == PE1 - 1;
     const float p0 = i < NVALID ? (poly0 ? ex2_poly(x0) : ex2_approx(x0)) : 0.f;
     const float p1 = i + 1 < NVALID ? (poly1 ? ex2_poly(x1) : ex2_approx(x1)) : 0.f;
     ls4[(i >> 1) % NCH] += p0 + p1;
@@ -457,7 +473,8 @@ int vit_attn_tc_launch(const void* qkv, void* out, int T, cudaStream_t st) {
   VZ_TRY(encode_tmap_2d_bf16(&tmKV, qkv, (long long)T * TOK, 3 * VZ_VIT_WIDTH, 3 * VZ_VIT_WIDTH, HD, BKV));
   // output as [tile][577 rows][1024]: a 32-row store box that runs past a tile's last row is clipped by the TMA
   VZ_TRY(encode_tmap_3d_bf16(&tmO, out, TOK, VZ_VIT_WIDTH, VZ_VIT_WIDTH, 32, T, (long long)TOK * VZ_VIT_WIDTH));
-  // share of the exponentials computed on the FMA pipe (VZ_ATTN_POLY = 0 | 4 | 8: none, every 4th, every 8th)
+  // VZ_ATTN_POLY = 0: every exponential an fp32 MUFU op | 2: packed bf16x2 exponentials | 4, 8: every 4th / 8th
+  // exponential as a polynomial on the FMA pipe
   static const int poly = []() { const char* e = getenv("VZ_ATTN_POLY"); return e ? atoi(e) : VZ_ATTN_POLY_DEFAULT; }();
   int dev = 0, num_sms = 0;
   VZ_CUDA_CHECK(cudaGetDevice(&dev));
@@ -467,7 +484,10 @@ int vit_attn_tc_launch(const void* qkv, void* out, int T, cudaStream_t st) {
   const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
   // algorithmic FLOPs: QK^T and PV, 2 * 577 * 577 * 64 each, per (tile, head)
   ProfScope prof(VZ_PROF_VIT_ATTN, 4.0 * TOK * TOK * HD * VZ_VIT_HEADS * T, st);
-  if (poly == 4) {
+  if (poly == 2) {
+    VZ_ENSURE_DYN_SMEM(vit_attn_tc_kernel<2>, SMEM_TOTAL);
+    vit_attn_tc_kernel<2><<<grid, THREADS, SMEM_TOTAL, st>>>(tmQ, tmKV, tmO, 0.125f, n_items);
+  } else if (poly == 4) {
     VZ_ENSURE_DYN_SMEM(vit_attn_tc_kernel<4>, SMEM_TOTAL);
     vit_attn_tc_kernel<4><<<grid, THREADS, SMEM_TOTAL, st>>>(tmQ, tmKV, tmO, 0.125f, n_items);
   } else if (poly == 8) {
