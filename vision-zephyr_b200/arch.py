@@ -357,7 +357,9 @@ class VisZephyrB200MetaForCausalLM(ABC):
         train = proj.needs_autograd(embed)
         feats = None
         if hi > lo:
-            feats = vision_tower.encode_patches(patches, pre_norm=None if train else proj.pre_norm_params())
+            # (small batches replay a CUDA graph; the features are consumed by the projector right below)
+            feats = vision_tower.encode_patches(patches, pre_norm=None if train else proj.pre_norm_params(),
+                                                graph=not train and peer is None)
 
         out_view = None
         if peer is not None and hi > lo and not keep_local:
@@ -449,7 +451,8 @@ class VisZephyrB200MetaForCausalLM(ABC):
         text = TextPack(text_emb, text_off, text_rows, hi - lo, L_text, tile_sample)
         if out_view is not None:
             out_view = out_view.view(sum(tiles_per_image[lo:hi]), proj.num_queries, -1)
-        vis_local = proj.forward_packed(feats, text, feats_normed=True, out=out_view)      # [T,32,4096] bf16
+        # (graph replay for small batches; its static output is consumed by the scatter before the next call)
+        vis_local = proj.forward_packed(feats, text, feats_normed=True, out=out_view, graph=out_view is None)      # [T,32,4096] bf16
         return vis_local.reshape(-1, vis_local.shape[-1])
 
     def _splice(self, ctx, vis, position_ids, attention_mask, past_key_values, labels):

@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from . import _lib
 from .projector_train import qformer_train_forward
-from .vision_tower import Workspace
+from .vision_tower import GraphCache, Workspace
 
 NUM_QUERIES, WIDTH, KV_WIDTH, HEADS, BLOCKS, FFN = 32, 4096, 5120, 8, 8, 8192
 
@@ -121,6 +121,7 @@ class QFormerB200(nn.Module):
         self.norm = _Norm(WIDTH)
         self.force_simple_gemm = os.environ.get("VZ_FORCE_SIMPLE_GEMM") == "1"
         self._ws = Workspace()
+        self._graphs = GraphCache()
         self._packed: Dict[str, torch.Tensor] = {}
         self._packed_key = None
         self._w: Optional[_lib.QfWeights] = None
@@ -181,8 +182,19 @@ class QFormerB200(nn.Module):
 
     # -- compute --------------------------------------------------------------------------------
     def forward_packed(self, feats: torch.Tensor, text: Optional[TextPack], feats_normed: bool = False,
-                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """feats bf16 [T,576,5120] -> bf16 [T,32,4096]."""
+                       out: Optional[torch.Tensor] = None, graph: bool = False) -> torch.Tensor:
+        """feats bf16 [T,576,5120] -> bf16 [T,32,4096].  graph=True (callers that consume the result at once):
+        small batches replay a captured CUDA graph keyed by the text geometry (tiles, samples, rows, L)."""
+        if (graph and out is None and feats.is_cuda and feats.dtype == torch.bfloat16 and not self.needs_autograd(feats)
+                and GraphCache.usable(feats.shape[0])):
+            self._ensure_packed()
+            if text is None:
+                return self._graphs.run(("qf", self._packed["lq"].data_ptr(), feats_normed), [feats.contiguous()],
+                                        lambda f: self.forward_packed(f, None, feats_normed))
+            key = ("qf", self._packed["lq"].data_ptr(), feats_normed, text.text_rows, text.n_samples, text.L)
+            return self._graphs.run(
+                key, [feats.contiguous(), text.text_emb, text.text_off, text.tile_sample],
+                lambda f, e, o, ts: self.forward_packed(f, TextPack(e, o, text.text_rows, text.n_samples, text.L, ts), feats_normed))
         lib = _lib.load()
         if self.needs_autograd(feats):
             # the inference kernels run on detached, packed weights and keep no activations: with gradients on
