@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from . import _lib
 from .projector_train import qformer_train_forward
-from .vision_tower import GraphCache, Workspace
+from .vision_tower import PACK_GENERATION, GraphCache, Workspace
 
 NUM_QUERIES, WIDTH, KV_WIDTH, HEADS, BLOCKS, FFN = 32, 4096, 5120, 8, 8, 8192
 
@@ -173,6 +173,9 @@ class QFormerB200(nn.Module):
         w.learned_queries = P["lq"].data_ptr()
         w.pre_g, w.pre_b = P["pre_g"].data_ptr(), P["pre_b"].data_ptr()
         w.norm_g, w.norm_b = P["norm_g"].data_ptr(), P["norm_b"].data_ptr()
+        self._graphs.clear()                 # captured graphs hold the previous buffers' addresses
+        self._pack_generation = next(PACK_GENERATION)
+        P["pre_g"]._vz_generation = self._pack_generation   # read by the tower's graph key (pre_norm rides in its fusion kernel)
         self._packed, self._w, self._packed_key = P, w, key
 
     def pre_norm_params(self):
@@ -189,9 +192,9 @@ class QFormerB200(nn.Module):
                 and GraphCache.usable(feats.shape[0])):
             self._ensure_packed()
             if text is None:
-                return self._graphs.run(("qf", self._packed["lq"].data_ptr(), feats_normed), [feats.contiguous()],
+                return self._graphs.run(("qf", self._pack_generation, feats_normed), [feats.contiguous()],
                                         lambda f: self.forward_packed(f, None, feats_normed))
-            key = ("qf", self._packed["lq"].data_ptr(), feats_normed, text.text_rows, text.n_samples, text.L)
+            key = ("qf", self._pack_generation, feats_normed, text.text_rows, text.n_samples, text.L)
             return self._graphs.run(
                 key, [feats.contiguous(), text.text_emb, text.text_off, text.tile_sample],
                 lambda f, e, o, ts: self.forward_packed(f, TextPack(e, o, text.text_rows, text.n_samples, text.L, ts), feats_normed))

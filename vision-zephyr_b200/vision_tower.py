@@ -11,6 +11,7 @@ Same constructor arguments, same attributes/properties, same forward() input for
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 import os
 import threading
 from collections import OrderedDict
@@ -81,6 +82,7 @@ class Workspace:
 
 GRAPH_MAX_TILES = int(os.environ.get("VZ_GRAPH_MAX_TILES", "8"))
 _capture_lock = threading.Lock()
+PACK_GENERATION = itertools.count(1)   # process-wide: identifies one packing of one module's weights
 
 
 class GraphCache:
@@ -94,6 +96,11 @@ class GraphCache:
         self.capacity = capacity
         self._entries: "OrderedDict[tuple, dict]" = OrderedDict()
         self._lock = threading.Lock()
+
+    def clear(self) -> None:
+        """drop every captured graph (the owner's weights were re-packed: the graphs hold their old addresses)"""
+        with self._lock:
+            self._entries.clear()
 
     @staticmethod
     def usable(n_tiles: int) -> bool:
@@ -234,6 +241,8 @@ class CLIPVisionTowerB200(nn.Module):
         return out
 
     def _rebuild_pointers(self):
+        self._graphs.clear()                 # captured graphs hold the previous buffers' addresses
+        self._pack_generation = next(PACK_GENERATION)
         P, w = self._packed, _lib.VitWeights()
         w.patch_w, w.class_emb, w.pos_emb = P["patch_w"].data_ptr(), P["class_emb"].data_ptr(), P["pos_emb"].data_ptr()
         w.pre_ln_g, w.pre_ln_b = P["pre_ln_g"].data_ptr(), P["pre_ln_b"].data_ptr()
@@ -263,7 +272,8 @@ class CLIPVisionTowerB200(nn.Module):
         the fusion kernel when pre_norm=(gamma_f32, beta_f32)).  graph=True (callers that consume the result at
         once): batches of up to VZ_GRAPH_MAX_TILES tiles replay a captured CUDA graph of the ~125 launches."""
         if graph and not return_hidden and GraphCache.usable(patches.shape[0] // PATCHES):
-            key = ("vit", self._packed["patch_w"].data_ptr(), pre_norm[0].data_ptr() if pre_norm is not None else 0)
+            # (generation counters, not addresses: the allocator may hand a re-packed weight the old address)
+            key = ("vit", self._pack_generation, getattr(pre_norm[0], "_vz_generation", 0) if pre_norm is not None else -1)
             return self._graphs.run(key, [patches], lambda p: self.encode_patches(p, pre_norm))
         if not self.is_loaded:
             raise RuntimeError("vision tower weights are not loaded (call load_model())")
