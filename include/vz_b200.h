@@ -421,6 +421,19 @@ int vz_splice_scatter(const int64_t* input_ids, const int64_t* labels, int B, in
                       int Lout, int pad_left, void* out_embeds, int64_t* out_labels,
                       uint8_t* out_mask, int64_t* out_pos, void* stream);
 
+/* The same scatter, also handing the FIRST LLM LAYER its RMSNorm statistic ("first layer's
+ * RMSNorm + QKV fused with the splice output", language_model/vis_zephyr.py:86-98): out_row_stats f32 [B*Lout][2]
+ * = (0, sum of squares) of every output row, taken while the row passes through the registers (bf16 rows only).
+ * Feeding it to vz_gemm_bf16 as ln_stats (ln_np = 1) with the RMSNorm gain folded into the stacked q/k/v weight makes
+ * that GEMM compute rmsnorm(x) Wqkv^T directly: a zero sum makes the fused-LayerNorm epilogue's mean term vanish
+ * and leaves rstd = rsqrt(sum of squares / K + eps).  out_row_stats == NULL: plain vz_splice_scatter.              */
+int vz_splice_scatter_rms(const int64_t* input_ids, const int64_t* labels, int B, int S,
+                          const void* embed_table, const void* vis, int ldv, const void* image_newline,
+                          int D, int elem_bytes, const vz_slot_desc* slots, int n_slots,
+                          const int32_t* slot_prefix, int total_vis_rows, const int32_t* tok_dest, const int32_t* slot_dest, const int32_t* lengths,
+                          int Lout, int pad_left, void* out_embeds, int64_t* out_labels,
+                          uint8_t* out_mask, int64_t* out_pos, float* out_row_stats, void* stream);
+
 /* "Next" row: the collator in front of the splice.
  * DataCollatorForSupervisedDataset (train/train.py:657-707) from packed ragged rows:
  * out_ids[b,s] = s < len_b ? flat_ids[offsets[b]+s] : pad_id, labels padded with IGNORE_INDEX, both

@@ -140,3 +140,40 @@ def test_projector_switches_to_the_autograd_path_when_gradients_are_on(llm):
         assert not y0.requires_grad and (y.float() - y0.float()).abs().max() < 0.1
     finally:
         proj.requires_grad_(False)
+
+
+def test_first_layer_rmsnorm_qkv_fused_with_the_splice(llm, golden_dir):
+    """SURVEY.md 8(f) rank 3, first half: the scatter's row statistics + ONE tcgen05 GEMM == HF Mistral's
+    input_layernorm followed by q_proj / k_proj / v_proj on the spliced rows (padding rows included)."""
+    from vision_zephyr_b200.language_model import FirstLayerQKV
+    g, pb, ids, mask, labels, sizes = _inputs(golden_dir)
+    layer = llm.get_model().layers[0]
+    with torch.no_grad():
+        layer.input_layernorm.weight.copy_(1 + 0.1 * torch.randn_like(layer.input_layernorm.weight))
+    llm.config.vz_first_layer_stats = True
+    try:
+        with torch.no_grad():
+            r = llm.prepare_inputs_labels_for_multimodal(ids, None, mask, None, labels, pb, sizes)
+    finally:
+        llm.config.vz_first_layer_stats = False
+    emb = r[4]
+    stats = emb.vz_row_sumsq
+    assert stats.shape == (emb.shape[0], emb.shape[1], 2) and float(stats[..., 0].abs().max()) == 0.0
+    ss_ref = emb.float().pow(2).sum(-1)
+    assert torch.allclose(stats[..., 1], ss_ref, rtol=1e-5, atol=1e-6)
+    q, k, v = FirstLayerQKV(layer)(emb)
+    with torch.no_grad():
+        x32 = emb.float()
+        eps = layer.input_layernorm.variance_epsilon
+        h = x32 * torch.rsqrt(x32.pow(2).mean(-1, keepdim=True) + eps) * layer.input_layernorm.weight.float()
+        att = layer.self_attn
+        refs = [h @ p.weight.float().t() for p in (att.q_proj, att.k_proj, att.v_proj)]
+    for name, got, ref in zip("qkv", (q, k, v), refs):
+        assert got.shape == ref.shape
+        err = (got.float() - ref).abs().max().item()
+        cos = torch.nn.functional.cosine_similarity(got.float().flatten(), ref.flatten(), dim=0).item()
+        print(f"fused first-layer {name}: max_abs {err:.4g} (ref max {ref.abs().max().item():.3g}) cos {cos:.6f}")
+        assert cos >= 0.9999 and err <= 0.02 * max(1.0, ref.abs().max().item())
+    # padding rows (all-zero embeddings) come out as exact zeros, like rmsnorm(0) W^T
+    pad = (r[2] == 0)
+    assert float(q[pad].abs().max()) == 0.0

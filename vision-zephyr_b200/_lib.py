@@ -125,6 +125,8 @@ SYMBOLS = {
     "vz_text_gather": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "vz_splice_scatter": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp,
                                _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "vz_splice_scatter_rms": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp,
+                                   _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vz_collate": (_i, [_vp, _vp, _vp, _i, _i, C.c_int64, _vp, _vp, _vp, _vp]),
     "vz_merge_rows": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
 }

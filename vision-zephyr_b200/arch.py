@@ -162,7 +162,9 @@ def text_gather(input_ids: torch.Tensor, embed_weight: torch.Tensor, plan: Splic
 
 
 def splice_scatter(input_ids, labels, embed_weight, vis, image_newline, slots_dev, slot_prefix, n_slots,
-                   total_vis_rows, plan: SplicePlan, Lout: int, pad_left: bool):
+                   total_vis_rows, plan: SplicePlan, Lout: int, pad_left: bool, row_stats: bool = False):
+    """row_stats=True (bf16 tables only): also returns, as a 5th tensor, f32 [B, Lout, 2] = (0, sum of squares) of
+    every output row -- the RMSNorm statistic of the first LLM layer (language_model.first_layer_qkv)."""
     lib = _lib.load()
     B, S = input_ids.shape
     D = embed_weight.shape[1]
@@ -172,12 +174,15 @@ def splice_scatter(input_ids, labels, embed_weight, vis, image_newline, slots_de
     out_mask = torch.empty((B, Lout), dtype=torch.uint8, device=dev)
     out_pos = torch.empty((B, Lout), dtype=torch.int64, device=dev)
     ldv = vis.stride(0) if vis is not None else D
-    _lib.check(lib.vz_splice_scatter(
+    stats = torch.empty((B, Lout, 2), dtype=torch.float32, device=dev) if row_stats else None
+    _lib.check(lib.vz_splice_scatter_rms(
         _lib.ptr(input_ids), _lib.ptr(labels), B, S, _lib.ptr(embed_weight), _lib.ptr(vis), int(ldv),
         _lib.ptr(image_newline), D, embed_weight.element_size(), _lib.ptr(slots_dev), n_slots,
         _lib.ptr(slot_prefix), int(total_vis_rows), _lib.ptr(plan.tok_dest), _lib.ptr(plan.slot_dest),
         _lib.ptr(plan.lengths), int(Lout), 1 if pad_left else 0, _lib.ptr(out_embeds), _lib.ptr(out_labels),
-        _lib.ptr(out_mask), _lib.ptr(out_pos), _lib.stream_ptr()), "vz_splice_scatter")
+        _lib.ptr(out_mask), _lib.ptr(out_pos), _lib.ptr(stats), _lib.stream_ptr()), "vz_splice_scatter")
+    if row_stats:
+        return out_embeds, out_labels, out_mask, out_pos, stats
     return out_embeds, out_labels, out_mask, out_pos
 
 
@@ -473,9 +478,13 @@ class VisZephyrB200MetaForCausalLM(ABC):
             out_embeds, out_labels, out_mask, out_pos = _SpliceFn.apply(
                 vis, embed, newline_p if newline_p is not None else None, ctx, info["Lmax"], pad_left)
         else:
-            out_embeds, out_labels, out_mask, out_pos = splice_scatter(
-                ctx["ids"], ctx["labels"], embed, vis, newline, ctx["slots"], ctx["prefix"], ctx["n_images"],
-                ctx["total_vis_rows"], ctx["plan"], info["Lmax"], pad_left)
+            want_stats = bool(getattr(self.config, "vz_first_layer_stats", False)) and embed.dtype == torch.bfloat16
+            res = splice_scatter(ctx["ids"], ctx["labels"], embed, vis, newline, ctx["slots"], ctx["prefix"],
+                                 ctx["n_images"], ctx["total_vis_rows"], ctx["plan"], info["Lmax"], pad_left, want_stats)
+            out_embeds, out_labels, out_mask, out_pos = res[:4]
+            if want_stats:
+                # rides on the tensor object: language_model.first_layer_qkv picks it up (config.vz_first_layer_stats)
+                out_embeds.vz_row_sumsq = res[4]
         new_mask = None
         if attention_mask is not None:
             new_mask = out_mask.to(dtype=attention_mask.dtype)

@@ -216,6 +216,7 @@ struct ScatterArgs {
   int Lout, pad_left;
   uint4* out_embeds; int64_t* out_labels; uint8_t* out_mask; int64_t* out_pos;
   int total_vis_rows;  // sum n_rows
+  float2* row_stats;   // optional [B*Lout]: (0, sum of squares) of every output row (bf16 rows only)
 };
 
 __device__ __forceinline__ void copy_row(uint4* dst, const uint4* src, int n, int lane) {
@@ -226,6 +227,26 @@ __device__ __forceinline__ void copy_row(uint4* dst, const uint4* src, int n, in
     dst[i] = a; dst[i + 32] = b; dst[i + 64] = c; dst[i + 96] = d;
   }
   for (; i < n; i += 32) dst[i] = __ldg(src + i);
+}
+
+// same copy, also returning the row's sum of squares (bf16 elements; identical on every lane): the statistic the
+// first LLM layer's RMSNorm needs, taken while the row passes through the registers anyway
+__device__ __forceinline__ float copy_row_sumsq(uint4* dst, const uint4* src, int n, int lane) {
+  float s = 0.f;
+  for (int i = lane; i < n; i += 32) {
+    const uint4 w = __ldg(src + i);
+    dst[i] = w;
+    const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float lo = __uint_as_float(u[k] << 16), hi = __uint_as_float(u[k] & 0xffff0000u);
+      s = fmaf(lo, lo, s);
+      s = fmaf(hi, hi, s);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
 }
 
 // One warp per work item; items = [B*S tokens] ++ [visual rows of all slots] ++ [B*Lout pad probes].
@@ -247,7 +268,13 @@ __global__ void __launch_bounds__(256) splice_scatter_kernel(const ScatterArgs a
       const int len = a.lengths[b];
       const int off = a.pad_left ? a.Lout - len : 0;
       const long orow = (long)b * a.Lout + off + d;
-      copy_row(a.out_embeds + orow * a.vec_per_row, a.table + (size_t)a.ids[item] * a.vec_per_row, a.vec_per_row, lane);
+      if (a.row_stats) {
+        const float ss = copy_row_sumsq(a.out_embeds + orow * a.vec_per_row, a.table + (size_t)a.ids[item] * a.vec_per_row,
+                                        a.vec_per_row, lane);
+        if (lane == 0) a.row_stats[orow] = make_float2(0.f, ss);
+      } else {
+        copy_row(a.out_embeds + orow * a.vec_per_row, a.table + (size_t)a.ids[item] * a.vec_per_row, a.vec_per_row, lane);
+      }
       if (lane == 0) {
         a.out_labels[orow] = a.labels ? a.labels[item] : (int64_t)VZ_IGNORE_INDEX;
         a.out_mask[orow] = 1;
@@ -273,7 +300,12 @@ __global__ void __launch_bounds__(256) splice_scatter_kernel(const ScatterArgs a
       const int off = a.pad_left ? a.Lout - len : 0;
       const long orow = (long)b * a.Lout + off + d;
       const uint4* src = srow >= 0 ? a.vis + (size_t)srow * a.ldv_vec : a.newline;
-      copy_row(a.out_embeds + orow * a.vec_per_row, src, a.vec_per_row, lane);
+      if (a.row_stats) {
+        const float ss = copy_row_sumsq(a.out_embeds + orow * a.vec_per_row, src, a.vec_per_row, lane);
+        if (lane == 0) a.row_stats[orow] = make_float2(0.f, ss);
+      } else {
+        copy_row(a.out_embeds + orow * a.vec_per_row, src, a.vec_per_row, lane);
+      }
       if (lane == 0) {
         a.out_labels[orow] = (int64_t)VZ_IGNORE_INDEX;
         a.out_mask[orow] = 1;
@@ -291,6 +323,7 @@ __global__ void __launch_bounds__(256) splice_scatter_kernel(const ScatterArgs a
         a.out_labels[p] = (int64_t)VZ_IGNORE_INDEX;
         a.out_mask[p] = 0;
         a.out_pos[p] = 0;
+        if (a.row_stats) a.row_stats[p] = make_float2(0.f, 0.f);
       }
     }
   }
@@ -353,6 +386,19 @@ extern "C" int vz_splice_scatter(const int64_t* input_ids, const int64_t* labels
                                  const int32_t* slot_dest, const int32_t* lengths, int Lout, int pad_left,
                                  void* out_embeds, int64_t* out_labels, uint8_t* out_mask, int64_t* out_pos,
                                  void* stream) {
+  return vz_splice_scatter_rms(input_ids, labels, B, S, embed_table, vis, ldv, image_newline, D, elem_bytes, slots,
+                               n_slots, slot_prefix, total_vis_rows, tok_dest, slot_dest, lengths, Lout, pad_left,
+                               out_embeds, out_labels, out_mask, out_pos, nullptr, stream);
+}
+
+extern "C" int vz_splice_scatter_rms(const int64_t* input_ids, const int64_t* labels, int B, int S,
+                                     const void* embed_table, const void* vis, int ldv, const void* image_newline,
+                                     int D, int elem_bytes, const vz_slot_desc* slots, int n_slots,
+                                     const int32_t* slot_prefix, int total_vis_rows, const int32_t* tok_dest,
+                                     const int32_t* slot_dest, const int32_t* lengths, int Lout, int pad_left,
+                                     void* out_embeds, int64_t* out_labels, uint8_t* out_mask, int64_t* out_pos,
+                                     float* out_row_stats, void* stream) {
+  if (out_row_stats && (elem_bytes != 2 || (reinterpret_cast<uintptr_t>(out_row_stats) & 7u))) return VZ_ERR_BAD_ARG;
   if (!input_ids || !embed_table || !tok_dest || !slot_dest || !lengths || !out_embeds || !out_labels ||
       !out_mask || !out_pos)
     return VZ_ERR_BAD_ARG;
@@ -376,6 +422,7 @@ extern "C" int vz_splice_scatter(const int64_t* input_ids, const int64_t* labels
   a.out_embeds = reinterpret_cast<uint4*>(out_embeds);
   a.out_labels = out_labels; a.out_mask = out_mask; a.out_pos = out_pos;
   a.total_vis_rows = n_slots > 0 ? total_vis_rows : 0;
+  a.row_stats = reinterpret_cast<float2*>(out_row_stats);
   const long items = (long)B * S + a.total_vis_rows + (long)B * Lout;
   int dev = 0, sms = 148;
   VZ_CUDA_CHECK(cudaGetDevice(&dev));

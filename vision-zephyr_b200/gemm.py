@@ -18,7 +18,8 @@ from . import _lib
 def gemm(A: torch.Tensor, W: torch.Tensor, *, M: int, N: int, K: int, lda: int, ldw: int, out: torch.Tensor, ldo: int,
          bias: Optional[torch.Tensor] = None, act: int = 0, w_is_kn: bool = False, batch: int = 1,
          a_bstride: int = 0, w_bstride: int = 0, o_bstride: int = 0, bias_bstride: int = 0,
-         out_f32: bool = False) -> torch.Tensor:
+         out_f32: bool = False, ln_stats: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None,
+         ln_np: int = 0, ln_eps: float = 0.0) -> torch.Tensor:
     """Raw call: pointers are the tensors' data_ptr() (views welcome), sizes / strides in ELEMENTS."""
     lib = _lib.load()
     g = _lib.GemmArgs()
@@ -30,8 +31,10 @@ def gemm(A: torch.Tensor, W: torch.Tensor, *, M: int, N: int, K: int, lda: int, 
     g.act, g.row_mode, g.rows_per, g.force_simple = act, 0, 0, 0
     g.batch, g.out_f32 = batch, 1 if out_f32 else 0
     g.a_bstride, g.w_bstride, g.o_bstride, g.r_bstride, g.bias_bstride = a_bstride, w_bstride, o_bstride, 0, bias_bstride
-    g.ln_stats = g.ln_colsum = g.stats_out = None
-    g.ln_np, g.ln_eps, g.stats_np = 0, 0.0, 0
+    g.ln_stats = ln_stats.data_ptr() if ln_stats is not None else None
+    g.ln_colsum = ln_colsum.data_ptr() if ln_colsum is not None else None
+    g.stats_out = None
+    g.ln_np, g.ln_eps, g.stats_np = ln_np, ln_eps, 0
     g.sk_ws, g.sk_ws_bytes = None, 0
     g.w_is_kn = 1 if w_is_kn else 0
     _lib.check(lib.vz_gemm_bf16(C.byref(g), _lib.stream_ptr()), f"vz_gemm_bf16 M={M} N={N} K={K} batch={batch} kn={w_is_kn}")

@@ -106,3 +106,40 @@ def random_mistral_config(num_hidden_layers: int = 32, **over) -> VisZephyrB200C
               mm_grid_pinpoints=DEFAULT_PINPOINTS, tokenizer_padding_side="right")
     kw.update(over)
     return VisZephyrB200Config(**kw)
+
+
+class FirstLayerQKV:
+    """SURVEY.md 8(f) rank 3, first half: "the first layer's RMSNorm + QKV fused with the splice output".
+
+    The scatter hands over every output row's sum of squares (config.vz_first_layer_stats = True ->
+    inputs_embeds.vz_row_sumsq, see vz_splice_scatter_rms); with the RMSNorm gain folded into the stacked
+    q / k / v weight, ONE tcgen05 GEMM then computes rmsnorm(x) [Wq; Wk; Wv]^T: the fused-LayerNorm epilogue of
+    vz_gemm_bf16 with a zero row sum is exactly rstd * (x W'^T), rstd = rsqrt(sum x^2 / K + eps).  No pass over the
+    spliced rows for the statistic, no normalised copy of them.  (What consumes q / k / v -- RoPE and the causal GQA
+    attention of language_model/vis_zephyr.py:86-98 -- stays HF Mistral: DESIGN.md section 7.)"""
+
+    def __init__(self, layer):
+        """layer: the HF MistralDecoderLayer whose input_layernorm / self_attn.{q,k,v}_proj are folded."""
+        att, norm = layer.self_attn, layer.input_layernorm
+        W = torch.cat([att.q_proj.weight, att.k_proj.weight, att.v_proj.weight], 0).detach().float()
+        self.weight = (W * norm.weight.detach().float()[None, :]).to(torch.bfloat16).contiguous()       # [6144, 4096]
+        self.colsum = self.weight.float().sum(1).contiguous()       # multiplied by a zero mean; kept valid
+        self.bias = torch.zeros(self.weight.shape[0], dtype=torch.float32, device=self.weight.device)
+        self.eps = float(getattr(norm, "variance_epsilon", getattr(norm, "eps", 1e-5)))
+        self.splits = [att.q_proj.weight.shape[0], att.k_proj.weight.shape[0], att.v_proj.weight.shape[0]]
+
+    def __call__(self, inputs_embeds: torch.Tensor, row_sumsq: Optional[torch.Tensor] = None):
+        """inputs_embeds bf16 [B, L, 4096] (+ its row statistics from the scatter) -> q, k, v as the layer's own
+        projections of input_layernorm(inputs_embeds) would give them, [B, L, n] each."""
+        from .gemm import gemm
+        stats = row_sumsq if row_sumsq is not None else getattr(inputs_embeds, "vz_row_sumsq", None)
+        if stats is None:
+            raise ValueError("row statistics missing: set config.vz_first_layer_stats = True before the splice")
+        B, L, K = inputs_embeds.shape
+        x = inputs_embeds.reshape(B * L, K)
+        N = self.weight.shape[0]
+        out = torch.empty((B * L, N), dtype=torch.bfloat16, device=x.device)
+        gemm(x, self.weight, M=B * L, N=N, K=K, lda=K, ldw=K, out=out, ldo=N, bias=self.bias,
+             ln_stats=stats.reshape(B * L, 2), ln_colsum=self.colsum, ln_np=1, ln_eps=self.eps)
+        q, k, v = out.view(B, L, N).split(self.splits, dim=-1)
+        return q, k, v
