@@ -346,6 +346,29 @@ def bench_c5(dev, lut, steps, llm_layers=32):
                 model.set_attn_implementation("sdpa")
             except Exception:
                 pass
+    # first LLM layer's RMSNorm + q/k/v projections: HF (RMSNorm kernel chain + three Linears) vs ONE tcgen05 GEMM fed by
+    # the scatter's row statistics (language_model.FirstLayerQKV; parity in tests/test_gpu_llm.py)
+    first_layer = {}
+    try:
+        from vision_zephyr_b200.language_model import FirstLayerQKV
+        layer0 = model.get_model().layers[0]
+        model.config.vz_first_layer_stats = True
+        with torch.no_grad():
+            r2 = path_only()
+        model.config.vz_first_layer_stats = False
+        fused = FirstLayerQKV(layer0)
+
+        def hf_qkv():
+            h = layer0.input_layernorm(r2[4])
+            return layer0.self_attn.q_proj(h), layer0.self_attn.k_proj(h), layer0.self_attn.v_proj(h)
+
+        with torch.no_grad():
+            first_layer = {"hf_rmsnorm_plus_3_linears_ms": event_time(hf_qkv, 10, warmup=3),
+                           "fused_gemm_ms": event_time(lambda: fused(r2[4]), 10, warmup=3),
+                           "rows": int(r2[4].shape[0] * r2[4].shape[1])}
+        del r2, fused
+    except Exception as e:
+        first_layer = {"error": f"{type(e).__name__}: {e}"[:300]}
     # the scatter alone at this geometry (HBM-bound): bytes = SURVEY 8(d)(4)
     from vision_zephyr_b200 import arch
     ctx = model._plan_splice(ids, mask, labels, [TILES_PER_IMAGE] * B, sizes)
@@ -373,7 +396,7 @@ def bench_c5(dev, lut, steps, llm_layers=32):
     return {"path_ms_per_step": ms_path, "path_images_per_s": B / ms_path * 1e3,
             "prefill_ms_total": ms_total, "llm_only_ms": ms_llm, "path_share_of_prefill": ms_path / ms_total,
             "spliced_tokens": real, "padded_tokens": B * Lmax, "prefill_tokens_per_s": real / ms_total * 1e3,
-            "packed_varlen_prefill": packed,
+            "packed_varlen_prefill": packed, "first_layer_qkv": first_layer,
             "Lmax": Lmax, "L_text": max(lens) - 1, "text_lens": lens, "gpu_launches_per_step": launches,
             "llm_build_s": build_s,
             "splice_scatter": {"bound": "hbm", "achieved": sc_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
