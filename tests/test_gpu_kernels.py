@@ -348,3 +348,67 @@ def test_gemm_weights_as_k_by_n(T, M, N, K):
     torch.cuda.synchronize()
     ref = torch.einsum("tmk,tkn->tmn", A.float(), Wkn.float()) + bias
     _check(out, ref, f"[K,N]-operand gemm T={T} {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N,K", [(32, 4096, 4096), (32, 12288, 4096), (64, 8192, 4096), (128, 4096, 8192), (37, 4096, 4096)])
+@pytest.mark.parametrize("variant", ["bias", "ln_gelu", "res_stats", "res_mod"])
+def test_gemm_split_k_single_m_tile(M, N, K, variant):
+    """single-m-tile, weight-streaming problems (the Q-Former at 1-4 tiles) with a scratch buffer: K is cut into
+    slices run as a batch of fp32 whole-tile products, a finish kernel adds them in order and applies the epilogue.
+    Every epilogue the orchestration uses there, against fp32 math and against the one-pass kernel."""
+    L, lib = _lib()
+    A, W = _rand((M, K), 1.0, 71), _rand((N, K), K ** -0.5, 72)
+    bias = torch.randn(N, device="cuda") * 0.3
+    ws, ws_all = _sk_ws()
+    R = stats_in = cs = None
+    act, row_mode, rows_per, np_in = 0, 0, 0, 0
+    if variant == "ln_gelu":
+        act, np_in = 2, 3
+        xf = A.float()
+        stats_in = torch.zeros((M, np_in, 2), dtype=torch.float32, device="cuda")
+        stats_in[:, 0, 0], stats_in[:, 0, 1] = xf.sum(1) * 0.25, (xf * xf).sum(1) * 0.5      # partials that add up
+        stats_in[:, 1, 0], stats_in[:, 1, 1] = xf.sum(1) * 0.75, (xf * xf).sum(1) * 0.25
+        stats_in[:, 2, 1] = (xf * xf).sum(1) * 0.25
+        cs = W.float().sum(1).contiguous()
+    elif variant == "res_stats":
+        R = _rand((M, N), 1.0, 73)
+    elif variant == "res_mod":
+        R, row_mode, rows_per = _rand((32, N), 1.0, 74), 2, 32
+    np_out = lib.vz_gemm_stats_partials(M, N) if variant == "res_stats" else 0
+    stats_out = torch.full((M, max(np_out, 1), 2), float("nan"), dtype=torch.float32, device="cuda")
+
+    def run(use_ws):
+        out = torch.zeros((M, N), dtype=torch.bfloat16, device="cuda")
+        g = L.GemmArgs()
+        g.A, g.W, g.out, g.bias = A.data_ptr(), W.data_ptr(), out.data_ptr(), bias.data_ptr()
+        g.residual = R.data_ptr() if R is not None else None
+        g.M, g.N, g.K, g.lda, g.ldw, g.ldo, g.ldr = M, N, K, K, K, N, (N if R is not None else 0)
+        g.act, g.row_mode, g.rows_per = act, row_mode, rows_per
+        if stats_in is not None:
+            g.ln_stats, g.ln_colsum, g.ln_np, g.ln_eps = stats_in.data_ptr(), cs.data_ptr(), np_in, 1e-5
+        if np_out:
+            g.stats_out, g.stats_np = stats_out.data_ptr(), np_out
+        if use_ws:
+            g.sk_ws, g.sk_ws_bytes = ws.data_ptr(), ws.numel()
+        L.check(lib.vz_gemm_bf16(C.byref(g), L.stream_ptr()), "vz_gemm_bf16")
+        torch.cuda.synchronize()
+        return out
+
+    y = A.float() @ W.float().t()
+    if variant == "ln_gelu":
+        xf = A.float()
+        mu, var = xf.mean(1, keepdim=True), xf.var(1, unbiased=False, keepdim=True)
+        y = torch.nn.functional.gelu(torch.rsqrt(var + 1e-5) * (y - mu * cs[None]) + bias)
+    else:
+        y = y + bias
+        if R is not None:
+            y = y + (R.float()[torch.arange(M, device="cuda") % 32] if variant == "res_mod" else R.float())
+    o1, o2 = run(True), run(True)
+    _check(o1, y, f"split-K gemm {M}x{N}x{K} {variant}")
+    assert torch.equal(o1, o2) and _canary_intact(ws_all)
+    if np_out:
+        s = stats_out.sum(1)
+        assert torch.allclose(s[:, 0], y.sum(1), rtol=1e-4, atol=2e-2) and torch.allclose(s[:, 1], (y * y).sum(1), rtol=1e-4, atol=2e-2)
+    o0 = run(False)                                           # the one-pass kernel (no scratch: whole tiles)
+    d = (o1.float() - o0.float()).abs().max().item()
+    assert d <= 2.0 ** -6 * max(y.abs().max().item(), 1.0), d
