@@ -352,10 +352,10 @@ def test_gemm_weights_as_k_by_n(T, M, N, K):
 
 @pytest.mark.parametrize("M,N,K", [(32, 4096, 4096), (32, 12288, 4096), (64, 8192, 4096), (128, 4096, 8192), (37, 4096, 4096)])
 @pytest.mark.parametrize("variant", ["bias", "ln_gelu", "res_stats", "res_mod"])
-def test_gemm_split_k_single_m_tile(M, N, K, variant):
-    """single-m-tile, weight-streaming problems (the Q-Former at 1-4 tiles) with a scratch buffer: K is cut into
-    slices run as a batch of fp32 whole-tile products, a finish kernel adds them in order and applies the epilogue.
-    Every epilogue the orchestration uses there, against fp32 math and against the one-pass kernel."""
+def test_gemm_single_m_tile_epilogues(M, N, K, variant):
+    """single-m-tile, weight-streaming problems (the Q-Former at 1-4 tiles: a short A box, three quarters of the
+    tile's lanes empty, every tile cut along K over all SMs by the stream-K schedule).  Every epilogue the
+    orchestration uses there, against fp32 math, run to run, and against the whole-tile schedule."""
     L, lib = _lib()
     A, W = _rand((M, K), 1.0, 71), _rand((N, K), K ** -0.5, 72)
     bias = torch.randn(N, device="cuda") * 0.3
@@ -404,11 +404,11 @@ def test_gemm_split_k_single_m_tile(M, N, K, variant):
         if R is not None:
             y = y + (R.float()[torch.arange(M, device="cuda") % 32] if variant == "res_mod" else R.float())
     o1, o2 = run(True), run(True)
-    _check(o1, y, f"split-K gemm {M}x{N}x{K} {variant}")
+    _check(o1, y, f"single-m-tile gemm {M}x{N}x{K} {variant}")
     assert torch.equal(o1, o2) and _canary_intact(ws_all)
     if np_out:
         s = stats_out.sum(1)
         assert torch.allclose(s[:, 0], y.sum(1), rtol=1e-4, atol=2e-2) and torch.allclose(s[:, 1], (y * y).sum(1), rtol=1e-4, atol=2e-2)
-    o0 = run(False)                                           # the one-pass kernel (no scratch: whole tiles)
+    o0 = run(False)                                           # no scratch: whole tiles only
     d = (o1.float() - o0.float()).abs().max().item()
     assert d <= 2.0 ** -6 * max(y.abs().max().item(), 1.0), d

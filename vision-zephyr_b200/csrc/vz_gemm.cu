@@ -101,6 +101,7 @@ struct GemmDev {
   // stream-K tail (see WorkIter): the first dp_tiles tiles are walked whole, round-robin; the k-blocks of
   // the last sk_tiles tiles are cut into one contiguous range per worker
   int dp_tiles, sk_tiles;
+  uint32_t stage_tx;       // bytes one pipeline stage receives (1-CTA form: the A box may have fewer than 128 rows)
   float4* sk_ws;           // per (worker, CTA rank): one 128 x BN fp32 partial accumulator
   uint32_t* sk_flags;      // per (worker, CTA rank, epilogue warp): epoch of the partial it holds
   uint32_t sk_epoch;
@@ -254,7 +255,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                n_blk * BN + (int)rank * (BN / 2), bz);
             }
           } else {
-            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx);
             tma_load_3d(&tmA, &full_bar[stage], sA + stage * C::A_BYTES, kb * BK, m_blk * BM, bz);
             if (BKN) {
 #pragma unroll
@@ -624,91 +625,6 @@ gemm_bf16_simple_kernel(const __nv_bfloat16* __restrict__ A, int lda,
   p.out[(size_t)out_row * p.ldo + n] = __float2bfloat16_rn(v);
 }
 
-// ------------------------------------------------------------------------------------------
-// Split-K finish (single-m-tile problems: the Q-Former at one to four tiles, M <= 128 rows).
-// The tcgen05 kernel has computed S partial products over disjoint K slices as a BATCH of fp32 outputs
-// ([S][M][N], whole tiles, no hand-over, no polling); this kernel adds them in slice order (deterministic) and
-// applies the epilogue the fused kernel would have applied.  One CTA per output row.
-// ------------------------------------------------------------------------------------------
-struct SplitKFinish {
-  const float* part;      // [S][M][N]
-  int S, M, N, K;
-  __nv_bfloat16* out; int ldo;
-  const float* bias;
-  const __nv_bfloat16* residual; int ldr; int res_mod;   // residual row = m % res_mod when res_mod > 0
-  int act;
-  const float* ln_stats; const float* ln_colsum; int ln_np; float ln_eps;
-  float* stats_out; int stats_np;
-};
-
-__global__ void __launch_bounds__(256) splitk_finish_kernel(const SplitKFinish p) {
-  __shared__ float red[2][8];
-  const int m = blockIdx.x, tid = threadIdx.x;
-  float mu = 0.f, rstd = 1.f;
-  if (p.ln_stats) {
-    float s1 = 0.f, s2 = 0.f;
-    for (int i = 0; i < p.ln_np; ++i) {
-      s1 += p.ln_stats[((size_t)m * p.ln_np + i) * 2];
-      s2 += p.ln_stats[((size_t)m * p.ln_np + i) * 2 + 1];
-    }
-    const float inv_k = 1.0f / (float)p.K;
-    mu = s1 * inv_k;
-    rstd = rsqrtf(fmaxf(s2 * inv_k - mu * mu, 0.f) + p.ln_eps);
-  }
-  const int rrow = p.res_mod > 0 ? m % p.res_mod : m;
-  float st1 = 0.f, st2 = 0.f;
-  for (int n = tid * 4; n < p.N; n += 256 * 4) {
-    float4 v = *reinterpret_cast<const float4*>(p.part + (size_t)m * p.N + n);
-    for (int s = 1; s < p.S; ++s) {
-      const float4 t = *reinterpret_cast<const float4*>(p.part + ((size_t)s * p.M + m) * p.N + n);
-      v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-    }
-    float f[4] = {v.x, v.y, v.z, v.w};
-    if (p.ln_stats) {
-      const float4 cs = *reinterpret_cast<const float4*>(p.ln_colsum + n), b = *reinterpret_cast<const float4*>(p.bias + n);
-      const float c[4] = {cs.x, cs.y, cs.z, cs.w}, bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) f[i] = fmaf(rstd, fmaf(-mu, c[i], f[i]), bb[i]);
-    } else if (p.bias) {
-      const float4 b = *reinterpret_cast<const float4*>(p.bias + n);
-      f[0] += b.x; f[1] += b.y; f[2] += b.z; f[3] += b.w;
-    }
-    if (p.act != VZ_ACT_NONE) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) f[i] = act_apply(f[i], p.act);
-    }
-    if (p.residual) {
-      const uint2 r = *reinterpret_cast<const uint2*>(p.residual + (size_t)rrow * p.ldr + n);
-      f[0] += __uint_as_float(r.x << 16); f[1] += __uint_as_float(r.x & 0xffff0000u);
-      f[2] += __uint_as_float(r.y << 16); f[3] += __uint_as_float(r.y & 0xffff0000u);
-    }
-    if (p.stats_out) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { st1 += f[i]; st2 = fmaf(f[i], f[i], st2); }
-    }
-    uint2 w;
-    w.x = pack_bf16x2(f[0], f[1]);
-    w.y = pack_bf16x2(f[2], f[3]);
-    *reinterpret_cast<uint2*>(p.out + (size_t)m * p.ldo + n) = w;
-  }
-  if (p.stats_out) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      st1 += __shfl_xor_sync(0xffffffffu, st1, o);
-      st2 += __shfl_xor_sync(0xffffffffu, st2, o);
-    }
-    if ((tid & 31) == 0) { red[0][tid >> 5] = st1; red[1][tid >> 5] = st2; }
-    __syncthreads();
-    if (tid == 0) {
-      float a = 0.f, b = 0.f;
-      for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; }
-      float2* dst = reinterpret_cast<float2*>(p.stats_out) + (size_t)m * p.stats_np;
-      dst[0] = make_float2(a, b);
-      for (int i = 1; i < p.stats_np; ++i) dst[i] = make_float2(0.f, 0.f);
-    }
-  }
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -789,11 +705,17 @@ template <int BN, int ACT, bool RES, bool LN, bool STATS, bool F32, bool TWO, bo
 int launch_tc(const vz_gemm_args& a, const GemmDev& p_in, int num_sms, cudaStream_t st) {
   using C = Cfg<BN, TWO>;
   CUtensorMap tmA, tmB;
-  VZ_TRY(make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM, a.batch, a.a_bstride));
+  // Single-m-tile problems (the Q-Former at 1-3 tiles: M = 32 .. 96 rows) are weight-streaming bound; a 128-row A
+  // box would spend as many TMA / shared-memory bytes on zero fill as on weights, so the box only covers the rows
+  // that exist, rounded up to a lane quarter (the rows above it are stale smem feeding TMEM lanes nobody reads).
+  static const int small_box = []() { const char* e = getenv("VZ_GEMM_ABOX"); return e ? atoi(e) : 1; }();
+  const int a_rows = (!TWO && small_box && a.M < BM) ? ((a.M + 31) / 32) * 32 : BM;
+  VZ_TRY(make_tmap(&tmA, a.A, a.M, a.K, a.lda, a_rows, a.batch, a.a_bstride));
   if (BKN) VZ_TRY(make_tmap(&tmB, a.W, a.K, a.N, a.ldw, 64, a.batch, a.w_bstride));   // [K, N]: 64 x 64 boxes
   else VZ_TRY(make_tmap(&tmB, a.W, a.N, a.K, a.ldw, TWO ? BN / 2 : BN, a.batch, a.w_bstride));
   VZ_ENSURE_DYN_SMEM((gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO, BKN>), C::SMEM_BYTES);
   GemmDev p = p_in;
+  p.stage_tx = (uint32_t)(a_rows * BK * 2 + C::B_BYTES);
   const long tiles = (long)p.num_m * p.num_n * p.batch;
   const int workers = TWO ? num_sms / 2 : num_sms;
   p.dp_tiles = (int)tiles;
@@ -906,11 +828,7 @@ int encode_tmap_3d_bf16(CUtensorMap* tm, const void* base, int rows, int cols, i
 namespace {
 // tile width the launcher will use for a problem (shared with the orchestration, which sizes the
 // LayerNorm partial-statistics buffers from it)
-thread_local int tl_bn_override = 0;   // set by the split-K dispatcher around its inner launch (128 or 256)
-
 int pick_tile_n(int M, int N, int batch, int num_sms) {
-  if (tl_bn_override == 256 && N % 256 == 0) return 256;
-  if (tl_bn_override == 128) return 128;
   static const int forced_bn = []() { const char* e = getenv("VZ_GEMM_BN"); return e ? atoi(e) : 0; }();
   const long num_m = (M + BM - 1) / BM;
   const long tiles256 = num_m * ((N + 255) / 256) * batch;
@@ -961,65 +879,6 @@ int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
     return VZ_ERR_BAD_ARG;
   if (a.out_f32 && (a.residual || a.row_mode != VZ_ROWS_PLAIN || (a.ldo & 3))) return VZ_ERR_UNSUPPORTED;
   if ((batch > 1 || a.out_f32) && a.force_simple) return VZ_ERR_UNSUPPORTED;
-
-  // ---- single m-tile, weight-streaming problems (M <= 128: the Q-Former at one to four tiles) -------------
-  // Cut K into S slices and run them as a BATCH of fp32 outputs over whole tiles (S x tiles fills the SMs with no
-  // partial-tile hand-over and no polling), then one small kernel adds the slices in order and applies the
-  // epilogue.  Replaces the stream-K schedule there: 27-36 us -> see profiles/r2_gemm_m32.md.
-  static const int splitk_on = []() { const char* e = getenv("VZ_GEMM_SPLITK"); return e ? atoi(e) : 1; }();
-  if (splitk_on && !a.force_simple && batch == 1 && !a.w_is_kn && !a.out_f32 && a.M <= BM && a.sk_ws &&
-      aligned16(a.sk_ws) && a.row_mode != VZ_ROWS_PATCH_EMBED && a.N % 128 == 0 && a.K % BK == 0 && (a.ldo & 3) == 0 &&
-      (!a.residual || (a.ldr & 3) == 0)) {
-    int dev = 0, num_sms = 0;
-    VZ_CUDA_CHECK(cudaGetDevice(&dev));
-    VZ_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    const int num_k = a.K / BK;
-    int best_s = 1, best_bn = 128;
-    double best_eff = 0.0;
-    for (int bn_try = 128; bn_try <= 256; bn_try *= 2) {
-      if (a.N % bn_try) continue;
-      for (int s_try = 2; s_try <= 8; s_try *= 2) {
-        if (num_k % s_try || num_k / s_try < 8) continue;
-        if ((size_t)s_try * a.M * a.N * sizeof(float) + kSkFlagBytes > a.sk_ws_bytes) continue;
-        const long t = (long)(a.N / bn_try) * s_try;
-        const long rounds = (t + num_sms - 1) / num_sms;
-        // fill of the SMs over whole rounds; on ties fewer rounds, then longer k-slices and narrower tiles
-        const double eff = (double)t / (double)(rounds * num_sms) - 0.02 * (double)rounds - 0.002 * s_try -
-                           (bn_try == 256 ? 0.001 : 0.0);
-        if (eff > best_eff) { best_eff = eff; best_s = s_try; best_bn = bn_try; }
-      }
-    }
-    // worth it when whole-tile scheduling alone would leave SMs idle or hand partial tiles over
-    if (best_s >= 2 && a.N / 128 < 2 * num_sms) {
-      float* part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a.sk_ws) + kSkFlagBytes);
-      vz_gemm_args g = a;
-      const int ks = a.K / best_s;
-      g.K = ks; g.batch = best_s;
-      g.a_bstride = ks; g.w_bstride = ks;
-      g.out = part; g.ldo = a.N; g.o_bstride = (long long)a.M * a.N; g.out_f32 = 1;
-      g.bias = nullptr; g.bias_bstride = 0; g.residual = nullptr; g.r_bstride = 0; g.ldr = 0;
-      g.act = VZ_ACT_NONE; g.row_mode = VZ_ROWS_PLAIN; g.rows_per = 0;
-      g.ln_stats = nullptr; g.ln_colsum = nullptr; g.ln_np = 0; g.stats_out = nullptr; g.stats_np = 0;
-      g.sk_ws = nullptr; g.sk_ws_bytes = 0;      // whole tiles only
-      tl_bn_override = best_bn;
-      const int rc = gemm_launch(g, st);
-      tl_bn_override = 0;
-      VZ_TRY(rc);
-      SplitKFinish f;
-      f.part = part; f.S = best_s; f.M = a.M; f.N = a.N; f.K = a.K;
-      f.out = reinterpret_cast<__nv_bfloat16*>(a.out); f.ldo = a.ldo;
-      f.bias = a.bias;
-      f.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual); f.ldr = a.ldr;
-      f.res_mod = a.row_mode == VZ_ROWS_RES_MOD ? a.rows_per : 0;
-      f.act = a.act;
-      f.ln_stats = a.ln_stats; f.ln_colsum = a.ln_colsum; f.ln_np = a.ln_np; f.ln_eps = a.ln_eps;
-      f.stats_out = a.stats_out; f.stats_np = a.stats_np;
-      if (a.ln_stats && (!a.ln_colsum || !a.bias || a.ln_np <= 0)) return VZ_ERR_BAD_ARG;
-      splitk_finish_kernel<<<a.M, 256, 0, st>>>(f);
-      VZ_LAUNCH_CHECK();
-      return VZ_OK;
-    }
-  }
 
   GemmDev p;
   p.out = reinterpret_cast<__nv_bfloat16*>(a.out);
