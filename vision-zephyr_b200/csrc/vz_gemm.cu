@@ -101,7 +101,6 @@ struct GemmDev {
   // stream-K tail (see WorkIter): the first dp_tiles tiles are walked whole, round-robin; the k-blocks of
   // the last sk_tiles tiles are cut into one contiguous range per worker
   int dp_tiles, sk_tiles;
-  uint32_t stage_tx;       // bytes one pipeline stage receives (1-CTA form: the A box may have fewer than 128 rows)
   float4* sk_ws;           // per (worker, CTA rank): one 128 x BN fp32 partial accumulator
   uint32_t* sk_flags;      // per (worker, CTA rank, epilogue warp): epoch of the partial it holds
   uint32_t sk_epoch;
@@ -255,7 +254,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                n_blk * BN + (int)rank * (BN / 2), bz);
             }
           } else {
-            mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx);
+            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
             tma_load_3d(&tmA, &full_bar[stage], sA + stage * C::A_BYTES, kb * BK, m_blk * BM, bz);
             if (BKN) {
 #pragma unroll
@@ -705,17 +704,11 @@ template <int BN, int ACT, bool RES, bool LN, bool STATS, bool F32, bool TWO, bo
 int launch_tc(const vz_gemm_args& a, const GemmDev& p_in, int num_sms, cudaStream_t st) {
   using C = Cfg<BN, TWO>;
   CUtensorMap tmA, tmB;
-  // Single-m-tile problems (the Q-Former at 1-3 tiles: M = 32 .. 96 rows) are weight-streaming bound; a 128-row A
-  // box would spend as many TMA / shared-memory bytes on zero fill as on weights, so the box only covers the rows
-  // that exist, rounded up to a lane quarter (the rows above it are stale smem feeding TMEM lanes nobody reads).
-  static const int small_box = []() { const char* e = getenv("VZ_GEMM_ABOX"); return e ? atoi(e) : 1; }();
-  const int a_rows = (!TWO && small_box && a.M < BM) ? ((a.M + 31) / 32) * 32 : BM;
-  VZ_TRY(make_tmap(&tmA, a.A, a.M, a.K, a.lda, a_rows, a.batch, a.a_bstride));
+  VZ_TRY(make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM, a.batch, a.a_bstride));
   if (BKN) VZ_TRY(make_tmap(&tmB, a.W, a.K, a.N, a.ldw, 64, a.batch, a.w_bstride));   // [K, N]: 64 x 64 boxes
   else VZ_TRY(make_tmap(&tmB, a.W, a.N, a.K, a.ldw, TWO ? BN / 2 : BN, a.batch, a.w_bstride));
   VZ_ENSURE_DYN_SMEM((gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO, BKN>), C::SMEM_BYTES);
   GemmDev p = p_in;
-  p.stage_tx = (uint32_t)(a_rows * BK * 2 + C::B_BYTES);
   const long tiles = (long)p.num_m * p.num_n * p.batch;
   const int workers = TWO ? num_sms / 2 : num_sms;
   p.dp_tiles = (int)tiles;
