@@ -92,7 +92,7 @@ class GraphCache:
     Replays copy the inputs into the static buffers and return the static output, which stays valid until the
     next replay of the same entry (callers inside this package consume it at once, in stream order)."""
 
-    def __init__(self, capacity: int = 16):
+    def __init__(self, capacity: int = 8):
         self.capacity = capacity
         self._entries: "OrderedDict[tuple, dict]" = OrderedDict()
         self._lock = threading.Lock()
