@@ -70,16 +70,6 @@ __device__ __forceinline__ float ex2_poly(float x) {
 }
 // (template parameter PE of the kernel: every PE-th exponential; 0 = all exponentials on the MUFU pipe)
 
-// PE == 2: PACKED exponentials.  P is handed to the tensor core as bf16 anyway, so the exponent is rounded to
-// bf16 BEFORE the exponential and one MUFU instruction produces the two bf16 probabilities of a key pair
-// (ex2.approx.ftz.bf16x2): half the MUFU instructions per key block and no conversion afterwards.  The row sum is
-// taken from the same bf16 values the P V product consumes.
-__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
-  uint32_t y;
-  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
-}
-
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // exp2 may run up to 2^8 above the value it would have with the exact running maximum before the
@@ -99,32 +89,7 @@ struct SoftmaxState {
   float m_used = -INFINITY;   // maximum the exponentials are currently taken against
   float l = 0.f;              // running row sum
   float sl2;                  // softmax scale * log2(e)
-  // stale-maximum variant: a rescale decided at the END of block j (after its exponentials were taken against
-  // the old maximum) is applied to O by block j + 1, once P_j V_j has retired
-  float alpha_pending = 1.f;
-  bool pending = false;
 };
-
-__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      :
-      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-
-// Stale-maximum form of a 64-key block (blocks 1 .. 8 of an item; VZ_ATTN_STALE=1).  The exponentials are taken
-// against the maximum known BEFORE the block, so they do not wait for the block's own maximum: the second half of
-// S is still on its way from TMEM while the first half runs through the MUFU, and each half of P is stored as
-// soon as it exists.  The block maximum is reduced on the side; if it exceeds the running one by more than 2^8
-// (rare after the first block) the rescale is NOTED and applied to O by the next block, after P_j V_j has retired --
-// P_j itself is in the old scale, like the O it is added to.  An exponent above 2^64 (a score 350 above
-// everything seen so far) would be the only way to overflow: such a block falls back to the exact order.
-template <int PE>
-__device__ __forceinline__ void softmax_block_stale(SoftmaxState& s, uint32_t g, int j, int r, uint32_t t_lane,
-                                                    uint32_t tmem_base, uint32_t tmem_o, uint64_t* bar_s_full,
-                                                    uint64_t* bar_s_free, uint64_t* bar_p_full, uint64_t* bar_pv_done);
 
 // One key block of the online softmax for query row r: NCOL score columns are read from TMEM, the
 // first NVALID are real keys (the rest of the tile's last block belongs to the next tile).
@@ -168,10 +133,7 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& s, uint32_t g, int j
     s.m_used = bm;
     s.l *= alpha;
   }
-  // a rescale noted by a stale-maximum block (l and m_used were updated there, O was not yet)
-  const bool pend = s.pending;
-  if (pend) { alpha *= s.alpha_pending; s.pending = false; s.alpha_pending = 1.f; }
-  const bool any_need = __any_sync(0xffffffffu, need || pend) && j > 0;
+  const bool any_need = __any_sync(0xffffffffu, need) && j > 0;
   const float m_sl2 = s.m_used * s.sl2;
   uint32_t pk[NCOL / 2];
   float ls4[NCH];
@@ -181,15 +143,9 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& s, uint32_t g, int j
   for (int i = 0; i < NCOL; i += 2) {
     // keys beyond NVALID are masked: probability 0 without spending an exponential on them
     const float x0 = fmaf(__uint_as_float(v[i]), s.sl2, -m_sl2), x1 = fmaf(__uint_as_float(v[i + 1]), s.sl2, -m_sl2);
-    if constexpr (PE == 2 && NCOL == 64 && NVALID == NCOL) {
-      const uint32_t pb = ex2_bf16x2(pack_bf16x2(x0, x1));
-      pk[i >> 1] = pb;
-      ls4[(i >> 1) % NCH] += __uint_as_float(pb << 16) + __uint_as_float(pb & 0xffff0000u);
-      continue;
-    }
-    constexpr int PE1 = PE > 2 ? PE : 1;
-    const bool poly0 = PE > 2 && NCOL == 64 && (i % PE1) == PE1 - 1;      // compile-time after unrolling
-    const bool poly1 = PE > 2 && NCOL == 64 && ((i + 1) % PE1) == PE1 - 1;
+    constexpr int PE1 = PE > 0 ? PE : 1;
+    const bool poly0 = PE > 0 && NCOL == 64 && (i % PE1) == PE1 - 1;      // compile-time after unrolling
+    const bool poly1 = PE > 0 && NCOL == 64 && ((i + 1) % PE1) == PE1 - 1;
     const float p0 = i < NVALID ? (poly0 ? ex2_poly(x0) : ex2_approx(x0)) : 0.f;
     const float p1 = i + 1 < NVALID ? (poly1 ? ex2_poly(x1) : ex2_approx(x1)) : 0.f;
     ls4[(i >> 1) % NCH] += p0 + p1;
@@ -219,112 +175,6 @@ __device__ __forceinline__ void softmax_block(SoftmaxState& s, uint32_t g, int j
   // P[r][0..NCOL) stays in tensor memory: the A operand of P V (lane = row, two bf16 per 32-bit column)
   if constexpr (NCOL == 64) tmem_st_32x32b_x32(tmem_base + t_lane + TMEM_P + b * P_COLS, pk);
   else tmem_st_32x32b_x8(tmem_base + t_lane + TMEM_P + b * P_COLS, pk);
-  tmem_st_wait();
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(&bar_p_full[b]);
-}
-
-template <int PE>
-__device__ __forceinline__ void softmax_block_stale(SoftmaxState& s, uint32_t g, int j, int r, uint32_t t_lane,
-                                                    uint32_t tmem_base, uint32_t tmem_o, uint64_t* bar_s_full,
-                                                    uint64_t* bar_s_free, uint64_t* bar_p_full, uint64_t* bar_pv_done) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t b = g & 1, use = g >> 1;
-  mbar_wait(&bar_s_full[b], use & 1, 600 + b);
-  tc_fence_after();
-  uint32_t v0[32], v1[32];
-  tmem_ld_32x32b_x32(tmem_base + t_lane + b * BKV, v0);
-  tmem_ld_wait();
-  tmem_ld_32x32b_x32(tmem_base + t_lane + b * BKV + 32, v1);     // in flight while the first half is processed
-  if (use > 0) mbar_wait(&bar_pv_done[b], (use - 1) & 1, 630 + b);   // P buffer b: previous tenant consumed
-  const float m_sl2 = s.m_used * s.sl2;
-  float bm4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, ls4[4] = {0.f, 0.f, 0.f, 0.f};
-  uint32_t pk[16];
-  auto half = [&](const uint32_t (&v)[32]) {
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      const float a0 = __uint_as_float(v[i]), a1 = __uint_as_float(v[i + 1]);
-      bm4[(i >> 1) & 3] = fmaxf(bm4[(i >> 1) & 3], fmaxf(a0, a1));
-      // (the clamp only matters for the overflow fallback below: results above 2^64 are discarded)
-      const float p0 = ex2_approx(fminf(fmaf(a0, s.sl2, -m_sl2), 100.f)), p1 = ex2_approx(fminf(fmaf(a1, s.sl2, -m_sl2), 100.f));
-      ls4[(i >> 1) & 3] += p0 + p1;
-      pk[i >> 1] = pack_bf16x2(p0, p1);
-    }
-  };
-  half(v0);
-  tmem_st_32x32b_x16(tmem_base + t_lane + TMEM_P + b * P_COLS, pk);
-  tmem_ld_wait();                                   // second half of S has arrived
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(&bar_s_free[b]);
-  half(v1);
-  float bm = fmaxf(fmaxf(bm4[0], bm4[1]), fmaxf(bm4[2], bm4[3]));
-  const float grow = (bm - s.m_used) * s.sl2;
-  if (__any_sync(0xffffffffu, grow > 64.f)) {
-    // absurd jump of the maximum: redo this block in the exact order (registers still hold S)
-    tmem_st_wait();
-    float alpha = 1.f;
-    if (grow > kRescaleLog2) { alpha = ex2_approx(-grow); s.m_used = bm; s.l *= alpha; }
-    if (s.pending) { alpha *= s.alpha_pending; s.pending = false; s.alpha_pending = 1.f; }
-    const float m2 = s.m_used * s.sl2;
-    float ls = 0.f;
-    uint32_t pq[32];
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      const float p0 = ex2_approx(fmaf(__uint_as_float(v0[i]), s.sl2, -m2)), p1 = ex2_approx(fmaf(__uint_as_float(v0[i + 1]), s.sl2, -m2));
-      const float q0 = ex2_approx(fmaf(__uint_as_float(v1[i]), s.sl2, -m2)), q1 = ex2_approx(fmaf(__uint_as_float(v1[i + 1]), s.sl2, -m2));
-      ls += (p0 + p1) + (q0 + q1);
-      pq[i >> 1] = pack_bf16x2(p0, p1);
-      pq[16 + (i >> 1)] = pack_bf16x2(q0, q1);
-    }
-    s.l += ls;
-    mbar_wait(&bar_pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1, 620);
-    tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tmem_ld_32x32b_x32(tmem_o + t_lane + c * 32, o);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-      tmem_st_32x32b_x32(tmem_o + t_lane + c * 32, o);
-    }
-    tmem_st_32x32b_x32(tmem_base + t_lane + TMEM_P + b * P_COLS, pq);
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bar_p_full[b]);
-    return;
-  }
-  tmem_st_32x32b_x16(tmem_base + t_lane + TMEM_P + b * P_COLS + 16, pk);
-  s.l += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
-  // a rescale noted by the PREVIOUS block is due now: O holds P_{j-1} V_{j-1} once that product has retired
-  const bool pend = s.pending;
-  if (__any_sync(0xffffffffu, pend)) {
-    const float alpha = pend ? s.alpha_pending : 1.f;
-    mbar_wait(&bar_pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1, 620);
-    tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tmem_ld_32x32b_x32(tmem_o + t_lane + c * 32, o);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-      tmem_st_32x32b_x32(tmem_o + t_lane + c * 32, o);
-    }
-    s.pending = false;
-    s.alpha_pending = 1.f;
-  }
-  // this block's own maximum: note the rescale for the next block (P_j stays in the old scale, like O)
-  if (grow > kRescaleLog2) {
-    const float alpha = ex2_approx(-grow);
-    s.m_used = bm;
-    s.l *= alpha;
-    s.alpha_pending = alpha;
-    s.pending = true;
-  }
   tmem_st_wait();
   tc_fence_before();
   __syncwarp();
@@ -577,13 +427,9 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       ++g;
       if (pend) epilogue(pq, ph, pt, n - 1, pl, pact);
       if (active) {
-        for (int j = 1; j < NKB - 1; ++j, ++g) {
-          if constexpr (PE == 1)
-            softmax_block_stale<PE>(stt, g, j, r, t_lane, tmem_base, tmem_o, bar_s_full, bar_s_free, bar_p_full, bar_pv_done);
-          else
-            softmax_block<BKV, BKV, PE>(stt, g, j, r, t_lane, tmem_base, tmem_o, bar_s_full, bar_s_free, bar_p_full,
-                                        bar_pv_done);
-        }
+        for (int j = 1; j < NKB - 1; ++j, ++g)
+          softmax_block<BKV, BKV, PE>(stt, g, j, r, t_lane, tmem_base, tmem_o, bar_s_full, bar_s_free, bar_p_full,
+                                  bar_pv_done);
         softmax_block<LAST_N, LAST_VALID, PE>(stt, g, NKB - 1, r, t_lane, tmem_base, tmem_o, bar_s_full, bar_s_free,
                                           bar_p_full, bar_pv_done);
         ++g;
@@ -611,9 +457,7 @@ int vit_attn_tc_launch(const void* qkv, void* out, int T, cudaStream_t st) {
   VZ_TRY(encode_tmap_2d_bf16(&tmKV, qkv, (long long)T * TOK, 3 * VZ_VIT_WIDTH, 3 * VZ_VIT_WIDTH, HD, BKV));
   // output as [tile][577 rows][1024]: a 32-row store box that runs past a tile's last row is clipped by the TMA
   VZ_TRY(encode_tmap_3d_bf16(&tmO, out, TOK, VZ_VIT_WIDTH, VZ_VIT_WIDTH, 32, T, (long long)TOK * VZ_VIT_WIDTH));
-  // VZ_ATTN_POLY = 0: every exponential an fp32 MUFU op | 1: the same with stale-maximum blocks (exponentials do not
-  // wait for the block maximum) | 2: packed bf16x2 exponentials | 4, 8: every 4th / 8th
-  // exponential as a polynomial on the FMA pipe
+  // share of the exponentials computed on the FMA pipe (VZ_ATTN_POLY = 0 | 4 | 8: none, every 4th, every 8th)
   static const int poly = []() { const char* e = getenv("VZ_ATTN_POLY"); return e ? atoi(e) : VZ_ATTN_POLY_DEFAULT; }();
   int dev = 0, num_sms = 0;
   VZ_CUDA_CHECK(cudaGetDevice(&dev));
@@ -623,13 +467,7 @@ int vit_attn_tc_launch(const void* qkv, void* out, int T, cudaStream_t st) {
   const int grid = n_items < 2 * num_sms ? n_items : 2 * num_sms;
   // algorithmic FLOPs: QK^T and PV, 2 * 577 * 577 * 64 each, per (tile, head)
   ProfScope prof(VZ_PROF_VIT_ATTN, 4.0 * TOK * TOK * HD * VZ_VIT_HEADS * T, st);
-  if (poly == 1) {   // stale-maximum softmax blocks
-    VZ_ENSURE_DYN_SMEM(vit_attn_tc_kernel<1>, SMEM_TOTAL);
-    vit_attn_tc_kernel<1><<<grid, THREADS, SMEM_TOTAL, st>>>(tmQ, tmKV, tmO, 0.125f, n_items);
-  } else if (poly == 2) {
-    VZ_ENSURE_DYN_SMEM(vit_attn_tc_kernel<2>, SMEM_TOTAL);
-    vit_attn_tc_kernel<2><<<grid, THREADS, SMEM_TOTAL, st>>>(tmQ, tmKV, tmO, 0.125f, n_items);
-  } else if (poly == 4) {
+  if (poly == 4) {
     VZ_ENSURE_DYN_SMEM(vit_attn_tc_kernel<4>, SMEM_TOTAL);
     vit_attn_tc_kernel<4><<<grid, THREADS, SMEM_TOTAL, st>>>(tmQ, tmKV, tmO, 0.125f, n_items);
   } else if (poly == 8) {
