@@ -166,6 +166,22 @@ def check(status: int, what: str):
         raise VzError(f"{what}: {msg}{extra}")
 
 
+def h2d(host, device, dtype=None):
+    """Small host array / CPU tensor -> device WITHOUT a stream sync.  A copy from pageable memory makes the driver
+    synchronise the stream first (the host then cannot run ahead of the GPU, and the GPU idles while the next
+    launches are being prepared); from a pinned staging buffer the copy is just another stream-ordered operation.
+    PyTorch's caching host allocator keeps the staging buffer alive until the copy has run."""
+    import numpy as np
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(host)) if isinstance(host, np.ndarray) else host
+    if dtype is not None:
+        t = t.to(dtype)
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        return t.to(dev)
+    return t.contiguous().pin_memory().to(dev, non_blocking=True)
+
+
 def ptr(t):
     """device pointer of a torch tensor (or None -> NULL)."""
     return None if t is None else C.c_void_p(t.data_ptr())

@@ -103,7 +103,7 @@ def _slots_to_device(descs: List[dict], device):
             setattr(arr[i], k, int(v))
         prefix[i + 1] = prefix[i] + d["n_rows"]
     raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
-    return (torch.from_numpy(raw).to(device), torch.from_numpy(prefix).to(device), int(prefix[-1]))
+    return (_lib.h2d(raw, device), _lib.h2d(prefix, device), int(prefix[-1]))
 
 
 class SplicePlan:
@@ -443,7 +443,7 @@ class VisZephyrB200MetaForCausalLM(ABC):
                 ids_b = ctx["ids"][b]
                 e = torch.nn.functional.embedding(ids_b[ids_b != IMAGE_TOKEN_INDEX], embed)
                 rows.append(torch.nn.functional.pad(e, (0, 0, 0, L_text - e.shape[0])))
-            tile_sample = torch.repeat_interleave(torch.arange(hi - lo), torch.tensor(tiles_per_image[lo:hi])).to(dev)
+            tile_sample = _lib.h2d(torch.repeat_interleave(torch.arange(hi - lo), torch.tensor(tiles_per_image[lo:hi])), dev)
             from .projector_train import qformer_train_forward
             vis_local = qformer_train_forward(proj, feats, torch.stack(rows), tile_sample)
             return vis_local.reshape(-1, vis_local.shape[-1])
@@ -451,8 +451,8 @@ class VisZephyrB200MetaForCausalLM(ABC):
         text_emb, text_off = text_gather(ctx["ids"], embed, ctx["plan"], text_rows, lo, hi)
         if text_emb.dtype != torch.bfloat16:
             text_emb = text_emb.to(torch.bfloat16)
-        tile_sample = torch.repeat_interleave(torch.arange(hi - lo, dtype=torch.int32),
-                                              torch.tensor(tiles_per_image[lo:hi])).to(dev)
+        tile_sample = _lib.h2d(torch.repeat_interleave(torch.arange(hi - lo, dtype=torch.int32),
+                                                       torch.tensor(tiles_per_image[lo:hi])), dev)
         text = TextPack(text_emb, text_off, text_rows, hi - lo, L_text, tile_sample)
         if out_view is not None:
             out_view = out_view.view(sum(tiles_per_image[lo:hi]), proj.num_queries, -1)

@@ -104,7 +104,7 @@ class PreprocessPlan:
 
 def _struct_array_to_dev(arr, device) -> torch.Tensor:
     raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
-    return torch.from_numpy(raw).to(device, non_blocking=True)
+    return _lib.h2d(raw, device)
 
 
 def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut: np.ndarray,
@@ -158,7 +158,7 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
             prim_list.append(pr)
         lay_dev = None
         if layers:
-            lay_dev = torch.from_numpy(np.stack(layers)).to(device, non_blocking=True)
+            lay_dev = _lib.h2d(np.stack(layers), device)
             keep.append(lay_dev)
         d = img_arr[i]
         d.src = im.data_ptr()
@@ -215,8 +215,8 @@ def build_plan(images: Sequence[torch.Tensor], views: Sequence[List[dict]], lut:
         images_dev=_struct_array_to_dev(img_arr, device),
         prims_dev=_struct_array_to_dev(prim_arr, device) if prim_list else None,
         tiles_dev=_struct_array_to_dev(tile_arr, device),
-        tables_dev=torch.from_numpy(tables).to(device, non_blocking=True),
-        lut_dev=torch.from_numpy(np.ascontiguousarray(lut, np.float32)).to(device, non_blocking=True),
+        tables_dev=_lib.h2d(tables, device),
+        lut_dev=_lib.h2d(np.ascontiguousarray(lut, np.float32), device),
         n_images=n_img, n_prims=len(prim_list), max_src_w=max_w, max_ksize=pool.max_ksize, keep=keep)
     hview_arr = (_lib.HViewDesc * len(hview_list))(*hview_list)
     plan.hviews_dev = _struct_array_to_dev(hview_arr, device)
