@@ -346,6 +346,55 @@ def bench_c5(dev, lut, steps, llm_layers=32):
                 model.set_attn_implementation("sdpa")
             except Exception:
                 pass
+    # SURVEY 8(f) rank 3, the kernel half: the decoder stack itself on packed rows (mistral_prefill.py: RMSNorm + q|k|v,
+    # o_proj + residual, SwiGLU gate|up, down_proj + residual as four tcgen05 GEMMs per layer, RoPE row kernel,
+    # flash-attn 2 varlen as the attention core), behind the same caller (config.vz_native_prefill)
+    native = {"error": None}
+    try:
+        with torch.no_grad():
+            ref_h = model.model(inputs_embeds=r[4], attention_mask=r[2], use_cache=False).last_hidden_state
+            model.config.vz_native_prefill = True
+            model.config.vz_first_layer_stats = True
+            t0 = time.time()
+            model.get_model().native_prefill()
+            native["fold_weights_s"] = time.time() - t0
+
+            def prefill_native():
+                return model(input_ids=ids, attention_mask=mask, images=pb, images_size=sizes, use_cache=False,
+                             logits_to_keep=1)
+
+            def llm_native():
+                return model(inputs_embeds=r[4], attention_mask=r[2], use_cache=False, logits_to_keep=1)
+
+            got_h = model.model(inputs_embeds=r[4], attention_mask=r[2], use_cache=False).last_hidden_state
+            keep = r[2].bool()
+            a, b = got_h[keep].float(), ref_h[keep].float()
+            cosr = torch.nn.functional.cosine_similarity(a, b, dim=-1)
+            native["parity_vs_hf"] = {"min_row_cosine": float(cosr.min()), "max_abs": float((a - b).abs().max()),
+                                      "ref_abs_max": float(b.abs().max()), "rows": int(a.shape[0])}
+            del ref_h, got_h, a, b
+            l0 = lib.vz_kernel_launches()
+            o3 = prefill_native()
+            native["gpu_launches_per_step"] = int(lib.vz_kernel_launches() - l0)
+            assert o3.logits.shape[0] == B and torch.isfinite(o3.logits.float()).all()
+            native["prefill_ms_total"] = event_time(prefill_native, max(3, steps // 4), warmup=1)
+            native["llm_only_ms"] = event_time(llm_native, max(3, steps // 4), warmup=1)
+            native["prefill_tokens_per_s"] = real / native["prefill_ms_total"] * 1e3
+            lib.vz_profile(1)
+            llm_native()
+            prof = _lib.profile_read()
+            lib.vz_profile(0)
+            n_g, ms_g, fl_g = prof["gemm_bf16_tcgen05"]
+            native["gemm"] = {"launches": int(n_g), "ms": ms_g, "tflops": fl_g / (ms_g * 1e-3) / 1e12,
+                              "frac_of_sustained_peak": fl_g / (ms_g * 1e-3) / 1e12 / pk.get("bf16_tflops_sustained", pk["bf16_tflops"])}
+            native["attention_core"] = "flash-attn 2 varlen (library)"
+    except Exception as e:
+        native["error"] = f"{type(e).__name__}: {e}"[:300]
+    finally:
+        model.config.vz_native_prefill = False
+        model.config.vz_first_layer_stats = False
+        model.get_model()._vz_prefill = None
+        torch.cuda.empty_cache()
     # first LLM layer's RMSNorm + q/k/v projections: HF (RMSNorm kernel chain + three Linears) vs ONE tcgen05 GEMM fed by
     # the scatter's row statistics (language_model.FirstLayerQKV; parity in tests/test_gpu_llm.py)
     first_layer = {}
@@ -396,7 +445,7 @@ def bench_c5(dev, lut, steps, llm_layers=32):
     return {"path_ms_per_step": ms_path, "path_images_per_s": B / ms_path * 1e3,
             "prefill_ms_total": ms_total, "llm_only_ms": ms_llm, "path_share_of_prefill": ms_path / ms_total,
             "spliced_tokens": real, "padded_tokens": B * Lmax, "prefill_tokens_per_s": real / ms_total * 1e3,
-            "packed_varlen_prefill": packed, "first_layer_qkv": first_layer,
+            "packed_varlen_prefill": packed, "native_prefill": native, "first_layer_qkv": first_layer,
             "Lmax": Lmax, "L_text": max(lens) - 1, "text_lens": lens, "gpu_launches_per_step": launches,
             "llm_build_s": build_s,
             "splice_scatter": {"bound": "hbm", "achieved": sc_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",

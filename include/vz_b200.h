@@ -56,7 +56,11 @@ int vz_version(void);
 /* Replaces every torch.nn.Linear / F.linear / conv-as-GEMM call on the path                   */
 /* (SURVEY.md 2.2 rows K4, K5, K7, K8).                                                        */
 /* ------------------------------------------------------------------------------------------ */
-enum { VZ_ACT_NONE = 0, VZ_ACT_QUICK_GELU = 1, VZ_ACT_GELU_ERF = 2 };
+/* VZ_ACT_SWIGLU: W holds gate / up rows interleaved in blocks of 64 (rows 128 j .. 128 j + 63 = gate rows
+ * 64 j .., rows 128 j + 64 .. 128 j + 127 = the matching up rows); the epilogue writes
+ * out[m, 64 j + i] = silu(gate) * up, i.e. N / 2 output columns (N % 128 == 0).  The MLP of the LLM behind the
+ * splice (HF MistralMLP: down_proj(act_fn(gate_proj(x)) * up_proj(x))) without a [M, 2 I] round trip.      */
+enum { VZ_ACT_NONE = 0, VZ_ACT_QUICK_GELU = 1, VZ_ACT_GELU_ERF = 2, VZ_ACT_SWIGLU = 3 };
 enum {
   VZ_ROWS_PLAIN = 0,       /* out row = m, residual row = m                                       */
   VZ_ROWS_PATCH_EMBED = 1, /* out row = m + m/rows_per + 1, residual row = 1 + m % rows_per
@@ -103,6 +107,9 @@ typedef struct {
   /* 1 = W is given as [K, ldw] row-major with N contiguous (out = A * W instead of A * W^T); N % 64 == 0,
    * plain epilogue (bias only).  Used for P * f in the cross-attention: no transposed copy of f.        */
   int w_is_kn;
+  /* 1 = the fused normalisation is an RMSNorm (HF MistralRMSNorm): rstd = rsqrt(sum x^2 / K + ln_eps), no mean;
+   * only the second component of ln_stats is read, ln_colsum is not needed and bias may be NULL.          */
+  int ln_rms;
 } vz_gemm_args;
 size_t vz_gemm_sk_workspace_bytes(void);
 
@@ -446,6 +453,28 @@ int vz_collate(const int64_t* flat_ids, const int64_t* flat_labels, const int32_
 int vz_merge_rows(const void* vis, int ldv, const void* image_newline, int D, int elem_bytes,
                   const vz_slot_desc* slots, int n_slots, const int32_t* out_row_base, void* out,
                   void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* (5) Row kernels of the LLM prefill behind the splice.  A Mistral decoder layer on     */
+/* packed rows is four vz_gemm_bf16 calls (RMSNorm folded into q|k|v and into gate|up: ln_rms; SwiGLU in the     */
+/* epilogue: VZ_ACT_SWIGLU; residual + next layer's row statistics in the o_proj / down_proj epilogues) around    */
+/* these kernels and a causal attention core.  The reference runs HF Mistral here                                */
+/* (language_model/vis_zephyr.py:86-98; train/zephyr_flash_attn_monkey_patch.py:86-136).                          */
+/* ------------------------------------------------------------------------------------------ */
+/* cos_sin f32 [M, half_dim, 2] = (cos, sin)(positions[m] * inv_freq[j]) rounded to bf16 values, as HF
+ * MistralRotaryEmbedding.forward returns them; one table per call, shared by all layers.                     */
+int vz_rope_table(const int32_t* positions, int M, const float* inv_freq, int half_dim, float* cos_sin, void* stream);
+/* apply_rotary_pos_emb in place: x bf16 [M, ld], heads h = 0 .. n_heads-1 at columns h * head_dim (the q and k
+ * heads of a packed q | k | v row), rotate_half pairing (j, j + head_dim / 2), bf16 rounding of every product. */
+int vz_rope_apply(void* x, int ld, int M, int n_heads, int head_dim, const float* cos_sin, void* stream);
+/* stats f32 [M, 2] = (sum, sum of squares) of every bf16 row x[m, 0:D]: the ln_stats of a vz_gemm_bf16 whose
+ * A operand did not come out of a stats_out epilogue (first decoder layer without the scatter's statistics).   */
+int vz_row_stats(const void* x, int ldx, int M, int D, float* stats, void* stream);
+/* Row copies between the padded [B, L] layout of the splice and the packed rows of the prefill:
+ * gather = 1: dst row i = src row map[i]; gather = 0: dst row map[i] = src row i; map[i] < 0 skips the row.
+ * row_bytes and both leading dimensions in BYTES, multiples of 16.                                            */
+int vz_rows_move(const void* src, long long lds_bytes, void* dst, long long ldd_bytes, const int32_t* map,
+                 int n_rows, int row_bytes, int gather, void* stream);
 
 #ifdef __cplusplus
 }

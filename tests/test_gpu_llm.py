@@ -177,3 +177,40 @@ def test_first_layer_rmsnorm_qkv_fused_with_the_splice(llm, golden_dir):
     # padding rows (all-zero embeddings) come out as exact zeros, like rmsnorm(0) W^T
     pad = (r[2] == 0)
     assert float(q[pad].abs().max()) == 0.0
+
+
+def test_native_prefill_behind_the_splice_matches_hf_and_feeds_hf_decode(llm, golden_dir):
+    """config.vz_native_prefill: the decoder stack of a sequence-starting, gradient-free forward runs on packed rows
+    (mistral_prefill.py); logits, loss and the KV cache HF's decode steps continue from agree with HF Mistral."""
+    g, pb, ids, mask, labels, sizes = _inputs(golden_dir)
+    cfg = llm.config
+    with torch.no_grad():
+        ref = llm(input_ids=ids, attention_mask=mask, labels=labels, images=pb, images_size=sizes, use_cache=True)
+        r = llm.prepare_inputs_labels_for_multimodal(ids, None, mask, None, labels, pb, sizes)
+    keep = r[2].bool()
+    launches0 = __import__("vision_zephyr_b200")._lib.load().vz_kernel_launches()
+    cfg.vz_native_prefill = True
+    cfg.vz_first_layer_stats = True
+    try:
+        with torch.no_grad():
+            got = llm(input_ids=ids, attention_mask=mask, labels=labels, images=pb, images_size=sizes, use_cache=True)
+            launches1 = __import__("vision_zephyr_b200")._lib.load().vz_kernel_launches()
+            # a decode step on top of each cache: HF Mistral both times (cached tokens > 0)
+            nxt = torch.full((2, 1), 5, dtype=torch.long, device="cuda")
+            m2 = torch.cat([r[2], torch.ones((2, 1), dtype=r[2].dtype, device="cuda")], 1)
+            pos = r[2].sum(1, keepdim=True)
+            d_ref = llm(input_ids=nxt, attention_mask=m2, position_ids=pos, past_key_values=ref.past_key_values, use_cache=True)
+            d_got = llm(input_ids=nxt, attention_mask=m2, position_ids=pos, past_key_values=got.past_key_values, use_cache=True)
+            toks = llm.generate(ids, images=pb, images_size=sizes, attention_mask=mask, max_new_tokens=4,
+                                do_sample=False, pad_token_id=2)
+    finally:
+        cfg.vz_native_prefill = False
+        cfg.vz_first_layer_stats = False
+    # the path + 2 layers x (4 GEMMs + rope) + table / gather / scatter kernels were this library's launches
+    assert launches1 - launches0 >= 237 + 2 * 5 + 3
+    a, b = got.logits[keep].float().cpu().numpy(), ref.logits[keep].float().cpu().numpy()
+    assert cos_rows(a, b).min() >= 0.999
+    assert abs(got.loss.item() - ref.loss.item()) <= 0.02 * abs(ref.loss.item())
+    a, b = d_got.logits[:, -1].float().cpu().numpy(), d_ref.logits[:, -1].float().cpu().numpy()
+    assert cos_rows(a, b).min() >= 0.999
+    assert toks.shape == (2, 4)

@@ -248,3 +248,25 @@ def test_initialize_vision_modules_mirrors_the_reference(tmp_path):
     assert names[0].startswith("model.mm_projector.")
     stripped = {k.split("mm_projector.")[1] for k in names}
     assert stripped == set(host.mm_projector.state_dict().keys())
+
+
+def test_gate_up_interleave_and_cpu_forward_stays_hf():
+    """mistral_prefill: the SwiGLU weight layout (blocks of 64 gate rows + the 64 matching up rows), and the
+    native-prefill switch of VisZephyrB200Model leaves CPU calls with HF Mistral (the engine has no CPU path)."""
+    from vision_zephyr_b200.mistral_prefill import MistralPrefillB200, interleave_gate_up
+    I, K = 192, 8
+    gate = torch.arange(I * K, dtype=torch.float32).reshape(I, K)
+    up = -gate
+    w = interleave_gate_up(gate, up)
+    assert w.shape == (2 * I, K)
+    for j in range(I // 64):
+        assert torch.equal(w[128 * j: 128 * j + 64], gate[64 * j: 64 * j + 64])
+        assert torch.equal(w[128 * j + 64: 128 * j + 128], up[64 * j: 64 * j + 64])
+    with pytest.raises(ValueError):
+        interleave_gate_up(gate[:100], up[:100])
+    from transformers import MistralConfig, MistralModel
+    cfg = MistralConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=1, num_attention_heads=2,
+                        num_key_value_heads=1, vocab_size=50, sliding_window=None)
+    m = MistralModel(cfg).eval()
+    with pytest.raises(vz._lib.VzError):
+        MistralPrefillB200(m)             # CPU weights: loud failure, no fallback inside the engine

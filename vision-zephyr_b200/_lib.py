@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
         ("r_bstride", C.c_longlong), ("bias_bstride", C.c_longlong),
         ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_np", C.c_int), ("ln_eps", C.c_float),
         ("stats_out", C.c_void_p), ("stats_np", C.c_int),
-        ("sk_ws", C.c_void_p), ("sk_ws_bytes", C.c_size_t), ("w_is_kn", C.c_int),
+        ("sk_ws", C.c_void_p), ("sk_ws_bytes", C.c_size_t), ("w_is_kn", C.c_int), ("ln_rms", C.c_int),
     ]
 
 
@@ -129,6 +129,10 @@ SYMBOLS = {
                                    _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vz_collate": (_i, [_vp, _vp, _vp, _i, _i, C.c_int64, _vp, _vp, _vp, _vp]),
     "vz_merge_rows": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "vz_rope_table": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    "vz_rope_apply": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "vz_row_stats": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "vz_rows_move": (_i, [_vp, C.c_longlong, _vp, C.c_longlong, _vp, _i, _i, _i, _vp]),
 }
 
 _lock = threading.Lock()

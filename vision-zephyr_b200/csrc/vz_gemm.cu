@@ -95,6 +95,7 @@ struct GemmDev {
   const float* ln_colsum;  // [N] sum_k W'[n,k]
   int ln_np;
   float ln_eps;
+  int ln_rms;              // 1 = RMSNorm: no mean (rstd = rsqrt(sum x^2 / K + eps)), colsum / bias not needed
   // ... and producer side: partial row statistics of THIS GEMM's output
   float* stats_out;        // [M][stats_np][2] or NULL
   int stats_np;
@@ -166,6 +167,12 @@ __device__ __forceinline__ float act_apply(float x, int act) {
     return fmaf(hx, t, hx);
   } else if (act == VZ_ACT_GELU_ERF) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  } else if (act == VZ_ACT_SWIGLU) {
+    // silu(x) = x * sigmoid(x) = 0.5 x (1 + tanh(0.5 x)); the caller multiplies by the "up" value
+    const float hx = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hx));
+    return fmaf(hx, t, hx);
   }
   return x;
 }
@@ -402,7 +409,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         float s1 = 0.f, s2 = 0.f;
         for (int i = 0; i < p.ln_np; ++i) { const float2 t = ps[i]; s1 += t.x; s2 += t.y; }
         const float inv_k = 1.0f / (float)p.K;
-        ln_mu = s1 * inv_k;
+        ln_mu = p.ln_rms ? 0.f : s1 * inv_k;
         ln_rstd = rsqrtf(fmaxf(s2 * inv_k - ln_mu * ln_mu, 0.f) + p.ln_eps);
       }
       float st1 = 0.f, st2 = 0.f;  // producer side: partial statistics of this lane's output row
@@ -441,58 +448,98 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2, ++cc) {
-        const int col0 = n_blk * BN + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint8_t* stg = sEpi + e * EPI_STAGE_BYTES + (cc & 1u) * 2048u;  // shadows the warp base on purpose
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_row + c * 32, r);
-        if (RES) {
-          const bool more = (c + 2 < BN / 32) && (col0 + 64 < p.N);
-          if (more) { prefetch_residual(col0 + 64, cc + 1); cp_async_wait<1>(); }
-          else cp_async_wait<0>();
-        }
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        for (int sw = sk_first; sw <= sk_last; ++sw) {   // stream-K: add the later workers' partial sums, in order
+      // stream-K: add the later workers' partial sums of chunk c_, in worker order
+      auto add_partials = [&](int c_, float* v_, bool first) {
+        for (int sw = sk_first; sw <= sk_last; ++sw) {
           const uint32_t* flag = p.sk_flags + (sw * NR + (int)rank) * kEpiWarps + e;
-          if (c == half) {   // first chunk of the tile: the partial may still be on its way
+          if (first) {   // first chunk of the tile: the partial may still be on its way
             uint32_t polls = 0;
             while (ld_acquire_u32(flag) != p.sk_epoch) {
               if (++polls > (1u << 28)) { printf("vz: stream-K hand-over timeout worker=%d from=%d\n", worker, sw); __trap(); }
             }
           }
-          const float4* src = p.sk_ws + (size_t)(sw * NR + (int)rank) * SK_SLOT4 + (size_t)((q * (BN / 32) + c) * 8) * 32 + lane;
+          const float4* src = p.sk_ws + (size_t)(sw * NR + (int)rank) * SK_SLOT4 + (size_t)((q * (BN / 32) + c_) * 8) * 32 + lane;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 t = __ldcg(src + j * 32);
-            v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+            v_[4 * j] += t.x; v_[4 * j + 1] += t.y; v_[4 * j + 2] += t.z; v_[4 * j + 3] += t.w;
           }
         }
-        if (LN) {
+      };
+      // fused normalisation + bias of the 32 columns starting at col_
+      auto norm_bias = [&](int col_, float* v_) {
+        if (LN && p.ln_rms) {
+          // RMSNorm(x) W^T == rstd * (x W'^T) (gain folded into W')
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v_[i] *= ln_rstd;
+          if (bias_b) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias_b + col_);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(b4 + i);
+              v_[4 * i + 0] += b.x; v_[4 * i + 1] += b.y; v_[4 * i + 2] += b.z; v_[4 * i + 3] += b.w;
+            }
+          }
+        } else if (LN) {
           // LN(x) W^T + b  ==  rstd * (x W'^T - mu * colsum(W')) + b'   (gamma folded into W', beta into b')
-          const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + col0);
-          const float4* b4 = reinterpret_cast<const float4*>(bias_b + col0);
+          const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + col_);
+          const float4* b4 = reinterpret_cast<const float4*>(bias_b + col_);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 cs = __ldg(c4 + i), b = __ldg(b4 + i);
-            v[4 * i + 0] = fmaf(ln_rstd, fmaf(-ln_mu, cs.x, v[4 * i + 0]), b.x);
-            v[4 * i + 1] = fmaf(ln_rstd, fmaf(-ln_mu, cs.y, v[4 * i + 1]), b.y);
-            v[4 * i + 2] = fmaf(ln_rstd, fmaf(-ln_mu, cs.z, v[4 * i + 2]), b.z);
-            v[4 * i + 3] = fmaf(ln_rstd, fmaf(-ln_mu, cs.w, v[4 * i + 3]), b.w);
+            v_[4 * i + 0] = fmaf(ln_rstd, fmaf(-ln_mu, cs.x, v_[4 * i + 0]), b.x);
+            v_[4 * i + 1] = fmaf(ln_rstd, fmaf(-ln_mu, cs.y, v_[4 * i + 1]), b.y);
+            v_[4 * i + 2] = fmaf(ln_rstd, fmaf(-ln_mu, cs.z, v_[4 * i + 2]), b.z);
+            v_[4 * i + 3] = fmaf(ln_rstd, fmaf(-ln_mu, cs.w, v_[4 * i + 3]), b.w);
           }
         } else if (bias_b) {
-          const float4* b4 = reinterpret_cast<const float4*>(bias_b + col0);
+          const float4* b4 = reinterpret_cast<const float4*>(bias_b + col_);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 b = __ldg(b4 + i);
-            v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            v_[4 * i + 0] += b.x; v_[4 * i + 1] += b.y; v_[4 * i + 2] += b.z; v_[4 * i + 3] += b.w;
           }
         }
-        if (ACT != VZ_ACT_NONE) {
+      };
+      constexpr bool SWI = ACT == VZ_ACT_SWIGLU;
+#pragma unroll 1
+      for (int c = half; c < BN / 32; c += 2, ++cc) {
+        // SwiGLU: every 128-column group of the tile is [gate 64 | up 64]; chunks 0, 1 of a group are consumed
+        // together with chunks 2, 3 (same warp: same parity) and produce 64 output columns per group
+        if (SWI && (c & 2)) continue;
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        const int ocol0 = SWI ? n_blk * (BN / 2) + (c >> 2) * 64 + (c & 1) * 32 : col0;   // output column of the chunk
+        uint8_t* stg = sEpi + e * EPI_STAGE_BYTES + (cc & 1u) * 2048u;  // shadows the warp base on purpose
+        float v[32];
+        {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + c * 32, r);
+          if (RES) {
+            const bool more = (c + 2 < BN / 32) && (col0 + 64 < p.N);
+            if (more) { prefetch_residual(col0 + 64, cc + 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        }
+        add_partials(c, v, c == half);
+        norm_bias(col0, v);
+        if (SWI) {
+          float u[32];
+          {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_row + (c + 2) * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) u[i] = __uint_as_float(r[i]);
+          }
+          add_partials(c + 2, u, false);
+          norm_bias(col0 + 64, u);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], ACT) * u[i];
+        } else if (ACT != VZ_ACT_NONE) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], ACT);
         }
@@ -546,7 +593,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         for (int i = 0; i < 4; ++i) {
           const int rr = 8 * i + co_r;
           const uint4 w = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((co_j ^ ((rr >> 1) & 3)) << 4));
-          if (co_ok[i]) *reinterpret_cast<uint4*>(out_b + co_out[i] + col0) = w;
+          if (co_ok[i]) *reinterpret_cast<uint4*>(out_b + co_out[i] + ocol0) = w;
         }
         __syncwarp();  // staging tile is reused by the next chunk
       }
@@ -613,9 +660,9 @@ gemm_bf16_simple_kernel(const __nv_bfloat16* __restrict__ A, int lda,
       s1 += p.ln_stats[((size_t)m * p.ln_np + i) * 2];
       s2 += p.ln_stats[((size_t)m * p.ln_np + i) * 2 + 1];
     }
-    const float mu = s1 / (float)p.K;
+    const float mu = p.ln_rms ? 0.f : s1 / (float)p.K;
     const float rstd = rsqrtf(fmaxf(s2 / (float)p.K - mu * mu, 0.f) + p.ln_eps);
-    v = rstd * (v - mu * p.ln_colsum[n]) + p.bias[n];
+    v = rstd * (v - (p.ln_rms ? 0.f : mu * p.ln_colsum[n])) + (p.bias ? p.bias[n] : 0.f);
   } else if (p.bias) {
     v += p.bias[n];
   }
@@ -767,6 +814,13 @@ int launch_bn(const vz_gemm_args& a, const GemmDev& p, int num_sms, cudaStream_t
 #define VZ_GO(ACT, RES, LN, ST, F32) return launch_tc<BN, ACT, RES, LN, ST, F32, TWO>(a, p, num_sms, st)
   if (f32) { if (act || res || ln || stt) return VZ_ERR_UNSUPPORTED; VZ_GO(0, false, false, false, true); }
   if (stt) { if (!res || act || ln) return VZ_ERR_UNSUPPORTED; VZ_GO(0, true, false, true, false); }
+  if (act == VZ_ACT_SWIGLU) {   // gate / up pairs of the LLM's MLP, RMSNorm fused or not
+    if (res || stt || f32 || BN == 192) return VZ_ERR_UNSUPPORTED;
+    if constexpr (BN != 192) {
+      if (ln) VZ_GO(3, false, true, false, false);
+      VZ_GO(3, false, false, false, false);
+    }
+  }
   if (ln) {
     if (res) return VZ_ERR_UNSUPPORTED;
     if (act == VZ_ACT_NONE) VZ_GO(0, false, true, false, false);
@@ -884,8 +938,13 @@ int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
   p.o_bstride = batch > 1 ? a.o_bstride : 0; p.r_bstride = batch > 1 ? a.r_bstride : 0;
   p.bias_bstride = batch > 1 ? a.bias_bstride : 0;
   p.ln_stats = a.ln_stats; p.ln_colsum = a.ln_colsum; p.ln_np = a.ln_np; p.ln_eps = a.ln_eps;
+  p.ln_rms = a.ln_rms != 0;
   p.stats_out = a.stats_out; p.stats_np = a.stats_np;
-  if (a.ln_stats && (!a.ln_colsum || !a.bias || a.ln_np <= 0 || !aligned16(a.ln_colsum))) return VZ_ERR_BAD_ARG;
+  if (a.ln_stats && a.ln_np <= 0) return VZ_ERR_BAD_ARG;
+  if (a.ln_stats && !a.ln_rms && (!a.ln_colsum || !a.bias || !aligned16(a.ln_colsum))) return VZ_ERR_BAD_ARG;
+  if (a.act < 0 || a.act > VZ_ACT_SWIGLU) return VZ_ERR_BAD_ARG;
+  if (a.act == VZ_ACT_SWIGLU && (a.N % 128 != 0 || a.row_mode != VZ_ROWS_PLAIN || a.force_simple || a.w_is_kn))
+    return VZ_ERR_UNSUPPORTED;
   if (a.stats_out && (a.stats_np <= 0 || a.out_f32 || batch > 1)) return VZ_ERR_BAD_ARG;
   // the epilogue addresses rows with 32-bit element offsets
   if ((double)(a.M + a.M / 2 + 2) * a.ldo >= 2147483647.0 || (a.residual && (double)(a.M + 2) * a.ldr >= 2147483647.0))

@@ -40,7 +40,7 @@ int gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, co
   g.batch = 1; g.out_f32 = 0;
   g.a_bstride = g.w_bstride = g.o_bstride = g.r_bstride = g.bias_bstride = 0;
   g.ln_stats = nullptr; g.ln_colsum = nullptr; g.ln_np = 0; g.ln_eps = 0.f; g.stats_out = nullptr; g.stats_np = 0;
-  g.sk_ws = st.sk_ws; g.sk_ws_bytes = st.sk_bytes; g.w_is_kn = 0;
+  g.sk_ws = st.sk_ws; g.sk_ws_bytes = st.sk_bytes; g.w_is_kn = 0; g.ln_rms = 0;
   return gemm_launch(g, st);
 }
 
@@ -56,7 +56,7 @@ int gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K,
   g.a_bstride = g.w_bstride = g.o_bstride = g.r_bstride = g.bias_bstride = 0;
   g.ln_stats = ln_stats; g.ln_colsum = ln_colsum; g.ln_np = ln_np; g.ln_eps = 1e-5f;
   g.stats_out = simple ? nullptr : stats_out; g.stats_np = stats_np;
-  g.sk_ws = st.sk_ws; g.sk_ws_bytes = st.sk_bytes; g.w_is_kn = 0;
+  g.sk_ws = st.sk_ws; g.sk_ws_bytes = st.sk_bytes; g.w_is_kn = 0; g.ln_rms = 0;
   VZ_TRY(gemm_launch(g, st));
   // the debug GEMM has no statistics epilogue: a row kernel produces the single partial instead
   if (simple && stats_out) VZ_TRY(row_stats_launch(out, ldo, M, N, stats_out, st));
@@ -74,7 +74,7 @@ int gemm_batched(const void* A, int lda, long long sa, const void* W, int ldw, l
   g.batch = batch; g.out_f32 = out_f32;
   g.a_bstride = sa; g.w_bstride = sw; g.o_bstride = so; g.r_bstride = 0; g.bias_bstride = sbias;
   g.ln_stats = nullptr; g.ln_colsum = nullptr; g.ln_np = 0; g.ln_eps = 0.f; g.stats_out = nullptr; g.stats_np = 0;
-  g.sk_ws = st.sk_ws; g.sk_ws_bytes = st.sk_bytes; g.w_is_kn = w_is_kn;
+  g.sk_ws = st.sk_ws; g.sk_ws_bytes = st.sk_bytes; g.w_is_kn = w_is_kn; g.ln_rms = 0;
   return gemm_launch(g, st);
 }
 

@@ -19,24 +19,27 @@ def gemm(A: torch.Tensor, W: torch.Tensor, *, M: int, N: int, K: int, lda: int, 
          bias: Optional[torch.Tensor] = None, act: int = 0, w_is_kn: bool = False, batch: int = 1,
          a_bstride: int = 0, w_bstride: int = 0, o_bstride: int = 0, bias_bstride: int = 0,
          out_f32: bool = False, ln_stats: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None,
-         ln_np: int = 0, ln_eps: float = 0.0) -> torch.Tensor:
+         ln_np: int = 0, ln_eps: float = 0.0, ln_rms: bool = False, residual: Optional[torch.Tensor] = None,
+         ldr: int = 0, stats_out: Optional[torch.Tensor] = None, stats_np: int = 0,
+         sk_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Raw call: pointers are the tensors' data_ptr() (views welcome), sizes / strides in ELEMENTS."""
     lib = _lib.load()
     g = _lib.GemmArgs()
     g.A, g.W, g.out = A.data_ptr(), W.data_ptr(), out.data_ptr()
     g.bias = bias.data_ptr() if bias is not None else None
-    g.residual = None
+    g.residual = residual.data_ptr() if residual is not None else None
     g.M, g.N, g.K = M, N, K
-    g.lda, g.ldw, g.ldo, g.ldr = lda, ldw, ldo, 0
+    g.lda, g.ldw, g.ldo, g.ldr = lda, ldw, ldo, ldr
     g.act, g.row_mode, g.rows_per, g.force_simple = act, 0, 0, 0
     g.batch, g.out_f32 = batch, 1 if out_f32 else 0
     g.a_bstride, g.w_bstride, g.o_bstride, g.r_bstride, g.bias_bstride = a_bstride, w_bstride, o_bstride, 0, bias_bstride
     g.ln_stats = ln_stats.data_ptr() if ln_stats is not None else None
     g.ln_colsum = ln_colsum.data_ptr() if ln_colsum is not None else None
-    g.stats_out = None
-    g.ln_np, g.ln_eps, g.stats_np = ln_np, ln_eps, 0
-    g.sk_ws, g.sk_ws_bytes = None, 0
+    g.stats_out = stats_out.data_ptr() if stats_out is not None else None
+    g.ln_np, g.ln_eps, g.stats_np = ln_np, ln_eps, stats_np
+    g.sk_ws, g.sk_ws_bytes = (sk_ws.data_ptr(), sk_ws.numel() * sk_ws.element_size()) if sk_ws is not None else (None, 0)
     g.w_is_kn = 1 if w_is_kn else 0
+    g.ln_rms = 1 if ln_rms else 0
     _lib.check(lib.vz_gemm_bf16(C.byref(g), _lib.stream_ptr()), f"vz_gemm_bf16 M={M} N={N} K={K} batch={batch} kn={w_is_kn}")
     return out
 

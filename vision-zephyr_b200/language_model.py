@@ -27,10 +27,57 @@ class VisZephyrB200Config(MistralConfig):
 
 
 class VisZephyrB200Model(VisZephyrB200MetaModel, MistralModel):
+    """HF MistralModel + the B200 mixin.  With `config.vz_native_prefill = True` a gradient-free forward that starts
+    a sequence (no cached tokens yet) runs the decoder stack natively on packed rows (mistral_prefill.py: RMSNorm and
+    SwiGLU fused into tcgen05 GEMMs, no pad rows) and fills the KV cache HF's decode steps continue from; every other
+    call -- training, decode steps, requests for attentions / hidden states -- is HF Mistral unchanged."""
     config_class = VisZephyrB200Config
 
     def __init__(self, config: MistralConfig):
         super().__init__(config)
+        self._vz_prefill = None
+        self._vz_prefill_key = None
+
+    def native_prefill(self):
+        """The packed-row prefill engine over this model's current weights (re-folded when they change)."""
+        from .mistral_prefill import MistralPrefillB200
+        key = tuple((p.data_ptr(), p._version) for p in self.layers.parameters())
+        if self._vz_prefill is None or self._vz_prefill_key != key:
+            self._vz_prefill = MistralPrefillB200(self)
+            self._vz_prefill_key = key
+        return self._vz_prefill
+
+    def _native_prefill_applies(self, inputs_embeds, attention_mask, past_key_values, kwargs) -> bool:
+        if not getattr(self.config, "vz_native_prefill", False) or torch.is_grad_enabled():
+            return False
+        if inputs_embeds is None or inputs_embeds.dim() != 3 or not inputs_embeds.is_cuda:
+            return False
+        if past_key_values is not None and past_key_values.get_seq_length() != 0:
+            return False
+        if attention_mask is not None and (attention_mask.dim() != 2 or attention_mask.shape[1] != inputs_embeds.shape[1]):
+            return False
+        return not (kwargs.get("output_attentions") or kwargs.get("output_hidden_states"))
+
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None,
+                inputs_embeds=None, use_cache=None, **kwargs):
+        if (input_ids is None) == (inputs_embeds is None):
+            raise ValueError("You must specify exactly one of input_ids or inputs_embeds")
+        if getattr(self.config, "vz_native_prefill", False) and not torch.is_grad_enabled():
+            embeds = inputs_embeds if inputs_embeds is not None else self.embed_tokens(input_ids)
+            if self._native_prefill_applies(embeds, attention_mask, past_key_values, kwargs):
+                from transformers import DynamicCache
+                from transformers.modeling_outputs import BaseModelOutputWithPast
+                use_cache = self.config.use_cache if use_cache is None else use_cache
+                if use_cache and past_key_values is None:
+                    past_key_values = DynamicCache(config=self.config)
+                hidden = self.native_prefill().prefill(embeds, attention_mask, position_ids,
+                                                       past_key_values if use_cache else None,
+                                                       row_sumsq=getattr(embeds, "vz_row_sumsq", None))
+                return BaseModelOutputWithPast(last_hidden_state=hidden,
+                                               past_key_values=past_key_values if use_cache else None)
+        return super().forward(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
+                               past_key_values=past_key_values, inputs_embeds=inputs_embeds, use_cache=use_cache,
+                               **kwargs)
 
 
 class VisZephyrB200ForCausalLM(MistralForCausalLM, VisZephyrB200MetaForCausalLM):
