@@ -206,8 +206,9 @@ def test_native_prefill_behind_the_splice_matches_hf_and_feeds_hf_decode(llm, go
     finally:
         cfg.vz_native_prefill = False
         cfg.vz_first_layer_stats = False
-    # the path + 2 layers x (4 GEMMs + rope) + table / gather / scatter kernels were this library's launches
-    assert launches1 - launches0 >= 237 + 2 * 5 + 3
+    # 2 layers x (4 GEMMs + rope) + table / gather / scatter kernels were this library's launches (the tower and the
+    # projector replay from CUDA graphs at this size and are not counted)
+    assert launches1 - launches0 >= 2 * 5 + 3
     a, b = got.logits[keep].float().cpu().numpy(), ref.logits[keep].float().cpu().numpy()
     assert cos_rows(a, b).min() >= 0.999
     assert abs(got.loss.item() - ref.loss.item()) <= 0.02 * abs(ref.loss.item())
