@@ -131,7 +131,7 @@ int vz_gemm_profile_read(long long* launches, double* total_ms, double* total_fl
 enum {
   VZ_PROF_GEMM = 0, VZ_PROF_VIT_ATTN = 1, VZ_PROF_FUSE = 2, VZ_PROF_PRE_H = 3, VZ_PROF_PRE_V = 4,
   VZ_PROF_PRE_FUSED = 5, VZ_PROF_SPLICE_SCATTER = 6, VZ_PROF_QATTN = 7, VZ_PROF_SOFTMAX = 8,
-  VZ_PROF_LAYERNORM = 9, VZ_PROF_TEXT_GATHER = 10, VZ_PROF_OTHER = 11, VZ_PROF_COUNT = 12
+  VZ_PROF_LAYERNORM = 9, VZ_PROF_TEXT_GATHER = 10, VZ_PROF_OTHER = 11, VZ_PROF_LLM_ATTN = 12, VZ_PROF_COUNT = 13
 };
 int vz_profile(int enable);
 int vz_profile_read(int tag, long long* launches, double* total_ms, double* total_work);
@@ -475,6 +475,17 @@ int vz_row_stats(const void* x, int ldx, int M, int D, float* stats, void* strea
  * row_bytes and both leading dimensions in BYTES, multiples of 16.                                            */
 int vz_rows_move(const void* src, long long lds_bytes, void* dst, long long ldd_bytes, const int32_t* map,
                  int n_rows, int row_bytes, int gather, void* stream);
+
+/* Causal grouped-query attention of the prefill on packed rows (tcgen05 / TMEM; head_dim 128): qkv bf16 [M, ld] =
+ * q heads | k heads | v heads per row (after vz_rope_apply), sample b = rows [cu[b], cu[b + 1]); out bf16 [M, ldo]
+ * (n_heads * 128 columns) = softmax(scale q k^T, keys 0 .. i of the same sample) v.  The work list comes from
+ * vz_attn_causal_items (HOST: lens_h[b] = rows of sample b -> int32 x 4 per (128-query tile, head), longest first;
+ * returns the item count, or the count needed if items_h is NULL / max_items too small; algo_flops = 4 * 128 *
+ * sum_b S_b (S_b + 1) / 2 * n_heads) and must be copied to the device by the caller.  Replaces the attention core of
+ * HF MistralAttention.forward / train/zephyr_flash_attn_monkey_patch.py:86-136 (flash_attn_varlen on unpadded rows). */
+int vz_attn_causal_items(const int32_t* lens_h, int B, int n_heads, int32_t* items_h, int max_items, double* algo_flops);
+int vz_attn_causal(const void* qkv, int ld, int M, void* out, int ldo, const int32_t* items, int n_items, int n_heads,
+                   int n_kv_heads, int head_dim, float scale, double algo_flops, void* stream);
 
 #ifdef __cplusplus
 }

@@ -219,3 +219,67 @@ def test_native_prefill_row_statistics_from_the_caller(mistral2):
         a = eng.prefill(x, mask, None, None).clone()
         b = eng.prefill(x, mask, None, None, row_sumsq=stats)
     assert cos_rows(a[mask.bool()].float().cpu().numpy(), b[mask.bool()].float().cpu().numpy()).min() >= 0.9999
+
+
+def _attn_reference(qkv, lens, nh, nkv, hd):
+    """fp32 causal GQA attention per sample (q head h reads kv head h // (nh / nkv), like HF repeat_kv)"""
+    out = torch.empty((qkv.shape[0], nh * hd), dtype=torch.float32, device=qkv.device)
+    row = 0
+    for n in lens:
+        blk = qkv[row: row + n].float()
+        q = blk[:, : nh * hd].reshape(n, nh, hd).transpose(0, 1)
+        k = blk[:, nh * hd: (nh + nkv) * hd].reshape(n, nkv, hd).transpose(0, 1).repeat_interleave(nh // nkv, 0)
+        v = blk[:, (nh + nkv) * hd:].reshape(n, nkv, hd).transpose(0, 1).repeat_interleave(nh // nkv, 0)
+        o = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True)
+        out[row: row + n] = o.transpose(0, 1).reshape(n, nh * hd)
+        row += n
+    return out
+
+
+@pytest.mark.parametrize("lens", [[1], [64], [65, 128, 129], [300, 37, 181, 1, 127, 256], [2140, 514, 1645]])
+def test_causal_gqa_attention_matches_sdpa(lens):
+    """vz_attn_causal on packed rows: tile / block boundary lengths, single-row samples, the longest config-5 sample"""
+    from vision_zephyr_b200 import _lib
+    lib = _lib.load()
+    nh, nkv, hd = 32, 8, 128
+    M = sum(lens)
+    gen = torch.Generator(device="cuda").manual_seed(M)
+    qkv = torch.randn((M, (nh + 2 * nkv) * hd), device="cuda", generator=gen).to(torch.bfloat16)
+    qkv[:, : nh * hd] *= 2.0           # sharper softmax: the running-maximum rescale is exercised
+    lens_h = np.asarray(lens, dtype=np.int32)
+    n = lib.vz_attn_causal_items(lens_h.ctypes.data, len(lens), nh, None, 0, None)
+    assert n == sum((s + 127) // 128 for s in lens) * nh
+    items_h = np.empty((n, 4), dtype=np.int32)
+    flops = C.c_double(0)
+    assert lib.vz_attn_causal_items(lens_h.ctypes.data, len(lens), nh, items_h.ctypes.data, n, C.byref(flops)) == n
+    assert flops.value == 4.0 * hd * sum(s * (s + 1) / 2 for s in lens) * nh
+    nkb = (items_h[:, 2] + 63) // 64
+    assert (np.diff(nkb) <= 0).all()                    # longest first
+    items = torch.from_numpy(items_h).cuda()
+    out = torch.full((M + 3, nh * hd), 7.0, dtype=torch.bfloat16, device="cuda")     # 3 guard rows behind the last sample
+    _lib.check(lib.vz_attn_causal(qkv.data_ptr(), qkv.shape[1], M, out.data_ptr(), nh * hd, items.data_ptr(), n, nh, nkv,
+                                  hd, hd ** -0.5, flops.value, _lib.stream_ptr()), "vz_attn_causal")
+    torch.cuda.synchronize()
+    ref = _attn_reference(qkv, lens, nh, nkv, hd)
+    got = out[:M].float()
+    assert torch.isfinite(got).all()
+    assert (out[M:] == 7.0).all()                       # nothing written past the last valid row
+    g2, r2 = got.reshape(M * nh, hd).cpu().numpy(), ref.reshape(M * nh, hd).cpu().numpy()
+    assert cos_rows(g2, r2).min() >= 0.999
+    assert np.abs(g2 - r2).max() <= 0.03 * np.abs(r2).max()
+
+
+def test_native_attention_agrees_with_flash_attn_in_the_stack(mistral2):
+    from vision_zephyr_b200.mistral_prefill import MistralPrefillB200
+    eng = MistralPrefillB200(mistral2)
+    assert eng.attn_impl == "native"
+    B, L, H = 2, 400, 4096
+    x = torch.randn((B, L, H), device="cuda").to(torch.bfloat16)
+    mask = torch.ones((B, L), dtype=torch.long, device="cuda")
+    mask[0, 333:] = 0
+    with torch.no_grad():
+        a = eng.prefill(x, mask, None, None).clone()
+        eng.attn_impl = "fa2"
+        b = eng.prefill(x, mask, None, None)
+    keep = mask.bool()
+    assert cos_rows(a[keep].float().cpu().numpy(), b[keep].float().cpu().numpy()).min() >= 0.9995

@@ -50,10 +50,15 @@ def main():
     v_v = qkv[:M, 5120:].view(M, 8, 128)
     a = torch.randn((M, 4096), device=dev).to(torch.bfloat16)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    items, n_items, attn_flops = eng.attention_items(LENS)
+    attn_out = ws["attn"]
     stages = {
         "qkv_gemm (rmsnorm fused)": (lambda: gemm(x, L.w_qkv, M=M, N=6144, K=H, lda=H, ldw=H, out=qkv, ldo=6144, ln_stats=stats0,
                                                   ln_np=1, ln_eps=1e-5, ln_rms=True, sk_ws=eng._sk), 2.0 * M * 6144 * H),
         "rope": (lambda: lib.vz_rope_apply(qkv.data_ptr(), 6144, M, 40, 128, cs.data_ptr(), st), 0.0),
+        "attention (vz_attn_causal, tcgen05)": (lambda: lib.vz_attn_causal(qkv.data_ptr(), 6144, M, attn_out.data_ptr(), 4096,
+                                                                        items.data_ptr(), n_items, 32, 8, 128, 128 ** -0.5,
+                                                                        attn_flops, st), sum(n * n for n in LENS) * 8192.0),
         "attention (flash-attn 2 varlen)": (lambda: flash_attn_varlen_func(q_v, k_v, v_v, cu, cu, max(LENS), max(LENS), causal=True),
                                             sum(n * n for n in LENS) * 8192.0 / 2 * 2),
         "o_proj (+residual +stats)": (lambda: gemm(a, L.w_o, M=M, N=H, K=H, lda=H, ldw=H, out=h_a, ldo=H, residual=x, ldr=H,
@@ -77,7 +82,7 @@ def main():
         ts.sort()
         ms = ts[len(ts) // 2]
         out["stages"][name] = {"us": ms * 1e3, "tflops": flops / (ms * 1e-3) / 1e12 if flops else None}
-    out["layer_sum_us"] = sum(v["us"] for v in out["stages"].values())
+    out["layer_sum_us"] = sum(v["us"] for k, v in out["stages"].items() if "flash-attn" not in k)
     with torch.no_grad():
         for _ in range(2):
             eng.forward_packed(x, pos, cu, max(LENS))

@@ -91,7 +91,7 @@ ROWS_PLAIN, ROWS_PATCH_EMBED, ROWS_RES_MOD = 0, 1, 2
 PRIM_LAYER, PRIM_RECT = 0, 1
 OUT_PATCHES_BF16, OUT_CHW_F32 = 0, 1
 MERGE_FLAT, MERGE_SPATIAL, MERGE_SPATIAL_UNPAD, MERGE_SINGLE_NEWLINE = 0, 1, 2, 3
-PROF_COUNT = 12
+PROF_COUNT = 13
 
 # every symbol include/vz_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
@@ -133,6 +133,8 @@ SYMBOLS = {
     "vz_rope_apply": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "vz_row_stats": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "vz_rows_move": (_i, [_vp, C.c_longlong, _vp, C.c_longlong, _vp, _i, _i, _i, _vp]),
+    "vz_attn_causal_items": (_i, [_vp, _i, _i, _vp, _i, _vp]),
+    "vz_attn_causal": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, C.c_float, C.c_double, _vp]),
 }
 
 _lock = threading.Lock()

@@ -1029,7 +1029,7 @@ extern "C" int vz_profile_read(int tag, long long* launches, double* total_ms, d
 extern "C" const char* vz_profile_tag_name(int tag) {
   static const char* names[VZ_PROF_COUNT] = {"gemm_bf16_tcgen05", "vit_attn_tc", "fuse", "preprocess_h", "preprocess_v",
                                              "preprocess_fused", "splice_scatter", "qattn", "softmax_rows", "layernorm",
-                                             "text_gather", "other"};
+                                             "text_gather", "other", "llm_attn_causal"};
   return (tag >= 0 && tag < VZ_PROF_COUNT) ? names[tag] : "?";
 }
 

@@ -9,21 +9,27 @@ on PACKED rows -- only the real tokens of every sample, in order -- and a decode
                                                (layer 0: handed over by the splice's scatter, vz_splice_scatter_rms;
                                                later layers: written by the previous down_proj epilogue)
     rope(q, k)                                 vz_rope_apply, in place on the packed q|k|v rows
-    a       = causal GQA attention             flash-attn 2 varlen (LIBRARY code, like cuBLAS would be; the one
-                                               stage of the layer that is not this repo's kernel -- 4 % of the FLOPs)
+    a       = causal GQA attention             vz_attn_causal: tcgen05 flash attention over the packed rows (S, P, O in
+                                               tensor memory, 128-query x 64-key blocks up to the diagonal, work items
+                                               sorted by length); VZ_LLM_ATTN=fa2 switches to flash-attn 2 varlen
+                                               (library code) as a cross-check
     h       = h + a Wo^T          (+ stats)    GEMM, residual and next RMSNorm's row statistics in the epilogue
     m       = silu(g) * u                      ONE GEMM over gate / up rows interleaved in blocks of 64: the SwiGLU
                                                product is taken in the epilogue, [M, 2 I] never exists
     h       = h + m Wd^T          (+ stats)    GEMM, as above
 
-i.e. four GEMM launches + one row kernel + the attention core per layer, no normalised copy of the hidden state,
+i.e. four GEMM launches + one row kernel + one attention launch per layer, no normalised copy of the hidden state,
 no pad rows.  The final RMSNorm, lm_head and the loss stay HF's (MistralForCausalLM.forward), fed with the padded
 last_hidden_state this module returns; the KV cache is filled for HF's decode steps.
 """
 from __future__ import annotations
 
+import ctypes as C
 import itertools
+import os
 from typing import List, Optional
+
+import numpy as np
 
 import torch
 
@@ -92,6 +98,9 @@ class MistralPrefillB200:
             raise ValueError("scaled rotary embeddings are not supported")
         self.final_norm = model.norm
         self._ws = {}
+        self.attn_impl = "fa2" if os.environ.get("VZ_LLM_ATTN", "") == "fa2" else "native"
+        if self.attn_impl == "native" and self.head_dim != 128:
+            raise ValueError("vz_attn_causal is built for head_dim 128 (set VZ_LLM_ATTN=fa2 for other geometries)")
         lib = _lib.load()
         self._sk = torch.empty(lib.vz_gemm_sk_workspace_bytes(), dtype=torch.uint8, device=dev)
 
@@ -105,19 +114,34 @@ class MistralPrefillB200:
             ws = dict(cap=cap,
                       qkv=torch.empty((cap, self.qkv_cols), dtype=bf, device=dev),
                       act=torch.empty((cap, self.inter), dtype=bf, device=dev),
+                      attn=torch.empty((cap, self.q_cols), dtype=bf, device=dev),
                       h=[torch.empty((cap, self.hidden), dtype=bf, device=dev) for _ in range(2)],
                       stats=torch.empty((cap, self.hidden // 64, 2), dtype=torch.float32, device=dev),
                       cs=torch.empty((cap, self.head_dim // 2, 2), dtype=torch.float32, device=dev))
             self._ws[key] = ws
         return ws
 
+    def attention_items(self, lens):
+        """device work list of vz_attn_causal for samples of `lens` rows: (items int32 [n, 4], n, algorithmic FLOPs)"""
+        lib = _lib.load()
+        lens_h = np.ascontiguousarray(lens, dtype=np.int32)
+        n = lib.vz_attn_causal_items(lens_h.ctypes.data, len(lens_h), self.n_heads, None, 0, None)
+        if n <= 0:
+            raise _lib.VzError(f"vz_attn_causal_items: {n}")
+        items_h = np.empty((n, 4), dtype=np.int32)
+        flops = C.c_double(0.0)
+        got = lib.vz_attn_causal_items(lens_h.ctypes.data, len(lens_h), self.n_heads, items_h.ctypes.data, n, C.byref(flops))
+        if got != n:
+            raise _lib.VzError(f"vz_attn_causal_items: {got} != {n}")
+        return _lib.h2d(items_h, self.device), n, flops.value
+
     def forward_packed(self, x: torch.Tensor, positions: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int,
-                       row_sumsq: Optional[torch.Tensor] = None, kv_sink=None) -> torch.Tensor:
-        """x bf16 [M, hidden] (packed real rows), positions int32 [M], cu_seqlens int32 [B + 1] (device).
+                       row_sumsq: Optional[torch.Tensor] = None, kv_sink=None, lens=None) -> torch.Tensor:
+        """x bf16 [M, hidden] (packed real rows), positions int32 [M], cu_seqlens int32 [B + 1] (device);
+        lens = the same lengths on the host (read back from cu_seqlens when not given).
         row_sumsq f32 [M, 2] = (anything, sum of squares) per row, or None (computed here).
         kv_sink(layer_idx, k [M, n_kv * hd] post-rope view, v view): called per layer before the buffers are reused.
         Returns the last decoder layer's output (BEFORE the final norm), bf16 [M, hidden] -- a workspace view."""
-        from flash_attn import flash_attn_varlen_func      # library attention core (see the module docstring)
         lib = _lib.load()
         st = _lib.stream_ptr()
         M, H = x.shape
@@ -140,6 +164,18 @@ class MistralPrefillB200:
         window = (-1, -1)
         if self.sliding_window is not None and max_seqlen > self.sliding_window:
             window = (int(self.sliding_window) - 1, 0)
+        native_attn = self.attn_impl == "native" and window == (-1, -1)
+        if native_attn:
+            if lens is None:
+                cu_h = cu_seqlens.cpu().tolist()
+                lens = [b - a for a, b in zip(cu_h[:-1], cu_h[1:])]
+            if sum(lens) != M:
+                raise ValueError("forward_packed: lens do not add up to the packed row count")
+            items, n_items, attn_flops = self.attention_items(lens)
+            attn_out = ws["attn"]
+            scale = float(self.head_dim) ** -0.5
+        else:
+            from flash_attn import flash_attn_varlen_func      # library attention (cross-check / sliding window)
         h = x
         q_v = qkv[:M, : self.q_cols].view(M, self.n_heads, self.head_dim)
         k_v = qkv[:M, self.q_cols: self.q_cols + self.kv_cols].view(M, self.n_kv, self.head_dim)
@@ -152,9 +188,14 @@ class MistralPrefillB200:
                                          cs.data_ptr(), st), "vz_rope_apply")
             if kv_sink is not None:
                 kv_sink(li, qkv[:M, self.q_cols: self.q_cols + self.kv_cols], qkv[:M, self.q_cols + self.kv_cols:])
-            a = flash_attn_varlen_func(q_v, k_v, v_v, cu_seqlens, cu_seqlens, max_seqlen, max_seqlen, causal=True,
-                                       window_size=window)
-            a = a.view(M, self.q_cols)
+            if native_attn:
+                _lib.check(lib.vz_attn_causal(qkv.data_ptr(), self.qkv_cols, M, attn_out.data_ptr(), self.q_cols,
+                                              items.data_ptr(), n_items, self.n_heads, self.n_kv, self.head_dim,
+                                              scale, attn_flops, st), "vz_attn_causal")
+                a = attn_out
+            else:
+                a = flash_attn_varlen_func(q_v, k_v, v_v, cu_seqlens, cu_seqlens, max_seqlen, max_seqlen, causal=True,
+                                           window_size=window).view(M, self.q_cols)
             # h_a = h + a Wo^T, statistics of h_a for the post-attention RMSNorm
             gemm(a, L.w_o, M=M, N=H, K=self.q_cols, lda=self.q_cols, ldw=self.q_cols, out=h_a, ldo=H,
                  residual=h, ldr=H, stats_out=S, stats_np=np_h, sk_ws=self._sk)
@@ -214,7 +255,8 @@ class MistralPrefillB200:
                                                 M, kvb, 0, st), "vz_rows_move(kv)")
                 past_key_values.update(k_pad.transpose(1, 2), v_pad.transpose(1, 2), li)
 
-        h = self.forward_packed(x, positions, cu, int(max(lens)), row_sumsq=rs, kv_sink=kv_sink)
+        h = self.forward_packed(x, positions, cu, int(max(lens)), row_sumsq=rs, kv_sink=kv_sink,
+                                lens=[int(n) for n in lens if n > 0])
         hn = self.final_norm(h).to(torch.bfloat16).contiguous()
         out = torch.zeros((B, L, H), dtype=torch.bfloat16, device=dev)
         _lib.check(lib.vz_rows_move(hn.data_ptr(), H * 2, out.data_ptr(), H * 2, idx.data_ptr(), M, H * 2, 0, st),
