@@ -387,7 +387,13 @@ def bench_c5(dev, lut, steps, llm_layers=32):
             n_g, ms_g, fl_g = prof["gemm_bf16_tcgen05"]
             native["gemm"] = {"launches": int(n_g), "ms": ms_g, "tflops": fl_g / (ms_g * 1e-3) / 1e12,
                               "frac_of_sustained_peak": fl_g / (ms_g * 1e-3) / 1e12 / pk.get("bf16_tflops_sustained", pk["bf16_tflops"])}
-            native["attention_core"] = "flash-attn 2 varlen (library)"
+            if "llm_attn_causal" in prof and prof["llm_attn_causal"][0]:
+                n_a, ms_a, fl_a = prof["llm_attn_causal"]
+                native["attention"] = {"kernel": "vz_attn_causal (tcgen05, S / P / O in tensor memory)", "launches": int(n_a),
+                                       "ms": ms_a, "us_per_layer": ms_a / n_a * 1e3,
+                                       "tflops_algorithmic": fl_a / (ms_a * 1e-3) / 1e12}
+            native["attention_core"] = model.get_model().native_prefill().attn_impl
+            native["other_ms"] = native["llm_only_ms"] - ms_g - (prof.get("llm_attn_causal", (0, 0.0, 0))[1])
     except Exception as e:
         native["error"] = f"{type(e).__name__}: {e}"[:300]
     finally:
