@@ -64,7 +64,12 @@ def run(name, M, N, K, act, res, reps=20, ln=False, stats=False, sk=False):
     print(f"{name:10s} M={M:6d} N={N:6d} K={K:5d} act={act} res={res}: {med * 1e3:8.1f} us  {2.0 * M * N * K / med / 1e9:7.1f} TFLOP/s")
 
 
-if os.environ.get("VZ_BENCH_LN") == "1":
+if os.environ.get("VZ_BENCH_ONLY"):
+    # one shape (an ncu target): VZ_BENCH_ONLY=o VZ_BENCH_STATS=1 VZ_BENCH_REPS=2
+    sh = [x for x in SHAPES if x[0] == os.environ["VZ_BENCH_ONLY"]][0]
+    run(*sh[:6], reps=int(os.environ.get("VZ_BENCH_REPS", "20")), stats=os.environ.get("VZ_BENCH_STATS") == "1",
+        ln=os.environ.get("VZ_BENCH_LNC") == "1")
+elif os.environ.get("VZ_BENCH_LN") == "1":
     for nm in ("qkv", "fc1"):
         sh = [x for x in SHAPES if x[0] == nm][0]
         run(*sh[:6]); run(*sh[:6], ln=True)

@@ -68,7 +68,10 @@ constexpr int GROUP_N = 8;    // n-blocks per rasterisation band (keeps the W ba
 
 // TWO = 2-CTA form (cta_group::2): a pair of SMs computes a 256 x BN tile, each CTA stages its own 128
 // A rows and HALF of the B tile, which cuts the shared-memory traffic per FLOP by a third.
-template <int BN, bool TWO = false>
+// (Measured and dropped: TMA stores for the residual epilogues too.  They need residual landing buffers distinct
+//  from the output staging, 8 KB per epilogue warp, i.e. one pipeline stage less in the 2-CTA form -- and five stages
+//  cost more than the stores save: out-proj 45.2 -> 49.2 us, fc2 119.7 -> 127.0 us.)
+template <int BN, bool TWO = false, bool RES = false>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (TWO ? BN / 2 : BN) * BK * 2;
@@ -76,7 +79,8 @@ struct Cfg {
   static constexpr int STAGES = TWO ? 6 : ((BN == 256) ? 4 : (BN == 192 ? 4 : 6));
   static constexpr int TMEM_COLS = (BN == 192) ? 512 : 2 * BN;  // two accumulator stages (power of two)
   static constexpr int BAR_BYTES = 256;
-  static constexpr int EPI_BYTES = kEpiWarps * EPI_STAGE_BYTES;
+  static constexpr int EPI_WARP_BYTES = EPI_STAGE_BYTES;
+  static constexpr int EPI_BYTES = kEpiWarps * EPI_WARP_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + align slack
 };
 
@@ -102,6 +106,7 @@ struct GemmDev {
   // stream-K tail (see WorkIter): the first dp_tiles tiles are walked whole, round-robin; the k-blocks of
   // the last sk_tiles tiles are cut into one contiguous range per worker
   int dp_tiles, sk_tiles;
+  int tma_out;             // 1 = output chunks leave through TMA stores (plain rows, bf16): tmC is valid
   float4* sk_ws;           // per (worker, CTA rank): one 128 x BN fp32 partial accumulator
   uint32_t* sk_flags;      // per (worker, CTA rank, epilogue warp): epoch of the partial it holds
   uint32_t sk_epoch;
@@ -185,8 +190,9 @@ __device__ __forceinline__ float act_apply(float x, int act) {
 template <int BN, int ACT, bool RES, bool LN, bool STATS, bool F32, bool TWO, bool BKN = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
-                         const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
-  using C = Cfg<BN, TWO>;
+                         const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                         const GemmDev p) {
+  using C = Cfg<BN, TWO, RES>;
   // 2-CTA form: `rank` is this CTA's position in its pair; tiles are 256 rows tall and the pair index
   // walks them.  1-CTA form: rank 0, every CTA is its own "pair".
   const uint32_t rank = TWO ? cluster_ctarank() : 0u;
@@ -212,6 +218,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_out) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -325,7 +332,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     const int e = warp - 4;
     const int q = e & 3;
     const int half = e >> 2;
-    uint8_t* stg = sEpi + e * EPI_STAGE_BYTES;
+    uint8_t* stg = sEpi + e * C::EPI_WARP_BYTES;
     // own-row addressing (lane = row) and cooperative addressing (4 lanes per row)
     const uint32_t own_off = (uint32_t)lane * 64u;
     const uint32_t own_sw = (uint32_t)((lane >> 1) & 3);
@@ -466,8 +473,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           }
         }
       };
-      // fused normalisation + bias of the 32 columns starting at col_
-      auto norm_bias = [&](int col_, float* v_) {
+      // fused normalisation + bias of the 32 columns starting at col_ (pre_ = the bias values if already in registers)
+      auto norm_bias = [&](int col_, float* v_, const float4* pre_) {
         if (LN && p.ln_rms) {
           // RMSNorm(x) W^T == rstd * (x W'^T) (gain folded into W')
 #pragma unroll
@@ -492,6 +499,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             v_[4 * i + 2] = fmaf(ln_rstd, fmaf(-ln_mu, cs.z, v_[4 * i + 2]), b.z);
             v_[4 * i + 3] = fmaf(ln_rstd, fmaf(-ln_mu, cs.w, v_[4 * i + 3]), b.w);
           }
+        } else if (pre_) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v_[4 * i + 0] += pre_[i].x; v_[4 * i + 1] += pre_[i].y; v_[4 * i + 2] += pre_[i].z; v_[4 * i + 3] += pre_[i].w;
+          }
         } else if (bias_b) {
           const float4* b4 = reinterpret_cast<const float4*>(bias_b + col_);
 #pragma unroll
@@ -510,7 +522,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         const int col0 = n_blk * BN + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         const int ocol0 = SWI ? n_blk * (BN / 2) + (c >> 2) * 64 + (c & 1) * 32 : col0;   // output column of the chunk
-        uint8_t* stg = sEpi + e * EPI_STAGE_BYTES + (cc & 1u) * 2048u;  // shadows the warp base on purpose
+        uint8_t* stg = sEpi + e * C::EPI_WARP_BYTES + (cc & 1u) * 2048u;  // shadows the warp base on purpose
+        uint8_t* stg_o = stg;                                             // output staging
+        // plain bias: fetched BEFORE the accumulator / residual waits (ncu: the load -> add dependency was the
+        // epilogue's largest single stall, and the epilogue is what bounds the K = 1024 GEMMs)
+        float4 bb[8];
+        const bool pre_bias = !LN && bias_b != nullptr;
+        if (pre_bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(bias_b + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bb[i] = __ldg(b4 + i);
+        }
         float v[32];
         {
           uint32_t r[32];
@@ -525,7 +547,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
         }
         add_partials(c, v, c == half);
-        norm_bias(col0, v);
+        norm_bias(col0, v, pre_bias ? bb : nullptr);
         if (SWI) {
           float u[32];
           {
@@ -536,7 +558,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             for (int i = 0; i < 32; ++i) u[i] = __uint_as_float(r[i]);
           }
           add_partials(c + 2, u, false);
-          norm_bias(col0 + 64, u);
+          norm_bias(col0 + 64, u, nullptr);
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = act_apply(v[i], ACT) * u[i];
         } else if (ACT != VZ_ACT_NONE) {
@@ -546,7 +568,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         if (F32) {
           // fp32 output (attention scores): 128 B per row, 8 chunks swizzled by row & 7; stores cover
           // 4 rows x 128 B per instruction
-          uint8_t* stg = sEpi + e * EPI_STAGE_BYTES;  // fp32 rows need the warp's whole 4 KB
+          uint8_t* stg = sEpi + e * C::EPI_WARP_BYTES;  // fp32 rows need the warp's whole 4 KB
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             *reinterpret_cast<float4*>(stg + lane * 128 + (((uint32_t)i ^ (uint32_t)(lane & 7)) << 4)) =
@@ -579,6 +601,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
           for (int i = 0; i < 32; ++i) { st1 += v[i]; st2 = fmaf(v[i], v[i], st2); }
         }
+        if (p.tma_out) {
+          // the staging half's previous tenant (two chunks ago) must have been read by its store
+          if (lane == 0) tma_store_wait_read1();
+          __syncwarp();
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 w;
@@ -586,13 +613,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
           w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
           w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-          *reinterpret_cast<uint4*>(stg + own_off + (((uint32_t)i ^ own_sw) << 4)) = w;
+          *reinterpret_cast<uint4*>(stg_o + own_off + (((uint32_t)i ^ own_sw) << 4)) = w;
+        }
+        if (p.tma_out) {
+          // 32 rows x 64 B in the TMA's 64-byte swizzle (chunk ^ ((row >> 1) & 3)): one bulk store per chunk, rows
+          // beyond M clipped by the tensor map
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmC, stg_o, ocol0, m_base, bz);
+            tma_store_commit();
+          }
+          continue;
         }
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int rr = 8 * i + co_r;
-          const uint4 w = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((co_j ^ ((rr >> 1) & 3)) << 4));
+          const uint4 w = *reinterpret_cast<const uint4*>(stg_o + rr * 64 + ((co_j ^ ((rr >> 1) & 3)) << 4));
           if (co_ok[i]) *reinterpret_cast<uint4*>(out_b + co_out[i] + ocol0) = w;
         }
         __syncwarp();  // staging tile is reused by the next chunk
@@ -609,6 +647,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         reinterpret_cast<float2*>(p.stats_out)[(size_t)(m_base + lane) * p.stats_np + n_blk * 2 + half] =
             make_float2(st1, st2);
     }
+    if (p.tma_out && lane == 0) tma_store_wait_read();   // shared memory must outlive the last stores' reads
   }
 
   tc_fence_before();
@@ -747,15 +786,60 @@ int make_tmap(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int
   return VZ_OK;
 }
 
+// Output map of the epilogue's TMA stores: bf16 [batch][rows][cols], box = 32 columns x 32 rows in the 64-byte swizzle
+// (the staging layout of an epilogue warp); rows beyond `rows` are clipped by the hardware.
+int make_tmap_out(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int batch, long long bstride) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return VZ_ERR_CUDA;
+  if (batch <= 1) { batch = 1; bstride = (long long)rows * ld; }
+  static const bool use_cache = []() { const char* e = getenv("VZ_TMAP_CACHE"); return !(e && e[0] == '0'); }();
+  thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  const TmapKey key{base, bstride, rows, cols, ld, -32, batch};
+  if (use_cache) {
+    auto it = cache.find(key);
+    if (it != cache.end()) { *tm = it->second; return VZ_OK; }
+  }
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)bstride * 2};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_ERROR_INVALID_CONTEXT && r != CUDA_ERROR_NOT_INITIALIZED) break;
+    cudaFree(nullptr);   // see make_tmap: bind the primary context, retry once
+  }
+  if (r != CUDA_SUCCESS) {
+    g_last_cuda_error = 100000 + (int)r;
+    return VZ_ERR_CUDA;
+  }
+  if (use_cache) {
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(key, *tm);
+  }
+  return VZ_OK;
+}
+
 template <int BN, int ACT, bool RES, bool LN, bool STATS, bool F32, bool TWO, bool BKN = false>
 int launch_tc(const vz_gemm_args& a, const GemmDev& p_in, int num_sms, cudaStream_t st) {
-  using C = Cfg<BN, TWO>;
-  CUtensorMap tmA, tmB;
+  using C = Cfg<BN, TWO, RES>;
+  CUtensorMap tmA, tmB, tmC;
   VZ_TRY(make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM, a.batch, a.a_bstride));
   if (BKN) VZ_TRY(make_tmap(&tmB, a.W, a.K, a.N, a.ldw, 64, a.batch, a.w_bstride));   // [K, N]: 64 x 64 boxes
   else VZ_TRY(make_tmap(&tmB, a.W, a.N, a.K, a.ldw, TWO ? BN / 2 : BN, a.batch, a.w_bstride));
   VZ_ENSURE_DYN_SMEM((gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO, BKN>), C::SMEM_BYTES);
   GemmDev p = p_in;
+  // output chunks through TMA stores: plain rows, bf16, no residual (whose landing buffers share the staging, see Cfg)
+  static const int tma_out_on = []() { const char* e = getenv("VZ_GEMM_TMA_OUT"); return e ? atoi(e) : 1; }();
+  p.tma_out = (tma_out_on && a.row_mode == VZ_ROWS_PLAIN && !F32 && !RES) ? 1 : 0;
+  if (p.tma_out) {
+    const int n_out = ACT == VZ_ACT_SWIGLU ? a.N / 2 : a.N;
+    VZ_TRY(make_tmap_out(&tmC, a.out, a.M, n_out, a.ldo, a.batch, a.o_bstride));
+  } else {
+    tmC = tmA;   // unused
+  }
   const long tiles = (long)p.num_m * p.num_n * p.batch;
   const int workers = TWO ? num_sms / 2 : num_sms;
   p.dp_tiles = (int)tiles;
@@ -793,10 +877,10 @@ int launch_tc(const vz_gemm_args& a, const GemmDev& p_in, int num_sms, cudaStrea
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VZ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO, BKN>, tmA, tmB, p));
+    VZ_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO, BKN>, tmA, tmB, tmC, p));
     count_launch();
   } else {
-    gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO, BKN><<<grid, kThreads, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+    gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO, BKN><<<grid, kThreads, C::SMEM_BYTES, st>>>(tmA, tmB, tmC, p);
     VZ_LAUNCH_CHECK();
   }
   return VZ_OK;
