@@ -439,7 +439,7 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       pend = true; pact = active; pq = qb; ph = h; pt = t; pl = stt.l;
     }
     if (pend) epilogue(pq, ph, pt, n - 1, pl, pact);
-    if (lane == 0) tma_store_wait_read();   // shared memory must outlive the last store's read
+    if (lane == 0) tma_store_wait_all();    // the last store has landed before this CTA exits
   }
   tc_fence_before();
   __syncthreads();

@@ -647,7 +647,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         reinterpret_cast<float2*>(p.stats_out)[(size_t)(m_base + lane) * p.stats_np + n_blk * 2 + half] =
             make_float2(st1, st2);
     }
-    if (p.tma_out && lane == 0) tma_store_wait_read();   // shared memory must outlive the last stores' reads
+    if (p.tma_out && lane == 0) tma_store_wait_all();    // the last stores have landed before this CTA exits
   }
 
   tc_fence_before();
