@@ -372,6 +372,8 @@ def bench_c5(dev, lut, steps, llm_layers=32):
             cosr = torch.nn.functional.cosine_similarity(a, b, dim=-1)
             native["parity_vs_hf"] = {"min_row_cosine": float(cosr.min()), "max_abs": float((a - b).abs().max()),
                                       "ref_abs_max": float(b.abs().max()), "rows": int(a.shape[0])}
+            # 32 random-init layers in bf16: HF's own bf16 run sits at 0.995 against fp32 (profiles/r2_prefill.md)
+            native["parity_ok"] = bool(cosr.min() >= 0.99)
             del ref_h, got_h, a, b
             l0 = lib.vz_kernel_launches()
             o3 = prefill_native()

@@ -24,7 +24,8 @@ def _rms(x, eps):
     return x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps)
 
 
-@pytest.mark.parametrize("M,K,I", [(100, 512, 256), (700, 1024, 1024), (3000, 512, 4096), (2500, 4096, 14336 // 7)])
+@pytest.mark.parametrize("M,K,I", [(100, 512, 256), (700, 1024, 1024), (3000, 512, 4096), (2500, 4096, 2048),
+                                   (8970, 4096, 14336)])        # the last one: config 5's gate | up GEMM at full size
 def test_gemm_rmsnorm_swiglu_matches_torch(M, K, I):
     from vision_zephyr_b200 import _lib
     from vision_zephyr_b200.gemm import gemm

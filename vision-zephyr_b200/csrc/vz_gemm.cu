@@ -339,6 +339,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     const int co_r = lane >> 2, co_j = lane & 3;
     uint32_t acc = 0, acc_phase = 0;
     uint32_t cc = 0;  // chunk counter: selects which half of the warp's staging area is current
+    uint32_t oc = 0;  // TMA stores issued by this warp: their staging halves alternate per STORE (the SwiGLU form skips
+                      // every other chunk, so the chunk counter would hand two consecutive stores the same half)
     WorkIter work(worker, n_workers, p.dp_tiles, p.sk_tiles, p.num_k);
     WorkItem it;
     // stream-K hand-over slots: element (row 32 q + lane, column 32 c + 4 j .. + 3) of the CTA's partial
@@ -523,7 +525,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         if (col0 >= p.N) break;  // warp-uniform
         const int ocol0 = SWI ? n_blk * (BN / 2) + (c >> 2) * 64 + (c & 1) * 32 : col0;   // output column of the chunk
         uint8_t* stg = sEpi + e * C::EPI_WARP_BYTES + (cc & 1u) * 2048u;  // shadows the warp base on purpose
-        uint8_t* stg_o = stg;                                             // output staging
+        uint8_t* stg_o = p.tma_out ? sEpi + e * C::EPI_WARP_BYTES + (oc & 1u) * 2048u : stg;   // output staging
         // plain bias: fetched BEFORE the accumulator / residual waits (ncu: the load -> add dependency was the
         // epilogue's largest single stall, and the epilogue is what bounds the K = 1024 GEMMs)
         float4 bb[8];
@@ -624,6 +626,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             tma_store_3d(&tmC, stg_o, ocol0, m_base, bz);
             tma_store_commit();
           }
+          ++oc;
           continue;
         }
         __syncwarp();
