@@ -64,7 +64,6 @@ constexpr int UMMA_K = 16;    // fixed for 16-bit inputs
 constexpr int kEpiWarps = 8;  // two warps per TMEM lane quarter, interleaved 32-column chunks
 constexpr int kThreads = 128 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-11 epilogue
 constexpr int EPI_STAGE_BYTES = 32 * 128;  // per epilogue warp: 32 rows x 32 values (bf16 or f32), chunk-swizzled
-constexpr int GROUP_N = 8;    // n-blocks per rasterisation band (keeps the W band + A strip in L2)
 
 // TWO = 2-CTA form (cta_group::2): a pair of SMs computes a 256 x BN tile, each CTA stages its own 128
 // A rows and HALF of the B tile, which cuts the shared-memory traffic per FLOP by a third.
@@ -107,6 +106,8 @@ struct GemmDev {
   // the last sk_tiles tiles are cut into one contiguous range per worker
   int dp_tiles, sk_tiles;
   int tma_out;             // 1 = output chunks leave through TMA stores (plain rows, bf16): tmC is valid
+  int group_n;             // n-blocks per rasterisation band: all m-tiles are walked per band, so A is re-read from
+                           // DRAM once per band while the band's W rows (group_n * BN * K * 2 bytes) stay in L2
   float4* sk_ws;           // per (worker, CTA rank): one 128 x BN fp32 partial accumulator
   uint32_t* sk_flags;      // per (worker, CTA rank, epilogue warp): epoch of the partial it holds
   uint32_t sk_epoch;
@@ -150,15 +151,15 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk, int& b) {
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group_n, int& m_blk, int& n_blk, int& b) {
   const int per_batch = num_m * num_n;
   b = tile / per_batch;
   tile -= b * per_batch;
-  const int per_band = num_m * GROUP_N;
+  const int per_band = num_m * group_n;
   const int band = tile / per_band;
   const int within = tile - band * per_band;
-  const int n0 = band * GROUP_N;
-  const int gsz = min(GROUP_N, num_n - n0);
+  const int n0 = band * group_n;
+  const int gsz = min(group_n, num_n - n0);
   m_blk = within / gsz;
   n_blk = n0 + (within - m_blk * gsz);
 }
@@ -249,7 +250,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       WorkItem it;
       while (work.next(it)) {
         int m_blk, n_blk, bz;
-        tile_coords(it.tile, p.num_m, p.num_n, m_blk, n_blk, bz);
+        tile_coords(it.tile, p.num_m, p.num_n, p.group_n, m_blk, n_blk, bz);
         for (int kb = it.kb0; kb < it.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
           if (TWO) {
@@ -349,7 +350,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     constexpr int NR = TWO ? 2 : 1;         // CTAs per worker: slot / flag index = worker * NR + rank < number of SMs
     while (work.next(it)) {
       int m_blk, n_blk, bz;
-      tile_coords(it.tile, p.num_m, p.num_n, m_blk, n_blk, bz);
+      tile_coords(it.tile, p.num_m, p.num_n, p.group_n, m_blk, n_blk, bz);
       if (it.kb0 > 0) {
         // ---- tail of a tile that an earlier worker finishes: dump the raw accumulator, raise the flag ----
         mbar_wait(&tfull_bar[acc], acc_phase, 400 + acc);
@@ -835,6 +836,19 @@ int launch_tc(const vz_gemm_args& a, const GemmDev& p_in, int num_sms, cudaStrea
   VZ_ENSURE_DYN_SMEM((gemm_bf16_tcgen05_kernel<BN, ACT, RES, LN, STATS, F32, TWO, BKN>), C::SMEM_BYTES);
   GemmDev p = p_in;
   // output chunks through TMA stores: plain rows, bf16, no residual (whose landing buffers share the staging, see Cfg)
+  // Band width of the tile walk, measured with ncu on the LLM's GEMMs (8 970 rows; DRAM MB read / us):
+  //   gate|up, K = 4096, 112 n-blocks: 6: 2094 / 1423, 8: 1613 / 1399, 12: 1288 / 1376, 16: 1061 / 1368, 20: 1191 / 1374,
+  //   28: 1892 / 1417 (operands: 308 MB); down, K = 14336, 16 n-blocks: 4: 1569 / 752, 8: 1159 / 693, 16: 1321 / 701.
+  // i.e. a band whose W rows take ~33 MB (a quarter of the L2), but never fewer than 8 n-blocks; bands evened out.
+  static const int group_env = []() { const char* e = getenv("VZ_GEMM_GROUP_N"); return e ? atoi(e) : 0; }();
+  {
+    const long per_nblk = (long)BN * a.K * 2;
+    long g = (33L << 20) / (per_nblk > 0 ? per_nblk : 1);
+    g = g < 8 ? 8 : (g > 32 ? 32 : g);
+    const long nb = (p.num_n + g - 1) / g;
+    g = (p.num_n + nb - 1) / nb;
+    p.group_n = group_env > 0 ? group_env : (int)(g < 1 ? 1 : g);
+  }
   static const int tma_out_on = []() { const char* e = getenv("VZ_GEMM_TMA_OUT"); return e ? atoi(e) : 1; }();
   p.tma_out = (tma_out_on && a.row_mode == VZ_ROWS_PLAIN && !F32 && !RES) ? 1 : 0;
   if (p.tma_out) {
