@@ -237,7 +237,8 @@ def _attn_reference(qkv, lens, nh, nkv, hd):
     return out
 
 
-@pytest.mark.parametrize("lens", [[1], [64], [65, 128, 129], [300, 37, 181, 1, 127, 256], [2140, 514, 1645]])
+@pytest.mark.parametrize("lens", [[1], [64], [65, 128, 129], [300, 37, 181, 1, 127, 256], [2140, 514, 1645],
+                                  [5, 40, 17] * 24, [4100]])
 def test_causal_gqa_attention_matches_sdpa(lens):
     """vz_attn_causal on packed rows: tile / block boundary lengths, single-row samples, the longest config-5 sample"""
     from vision_zephyr_b200 import _lib
