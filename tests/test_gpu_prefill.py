@@ -285,3 +285,64 @@ def test_native_attention_agrees_with_flash_attn_in_the_stack(mistral2):
         b = eng.prefill(x, mask, None, None)
     keep = mask.bool()
     assert cos_rows(a[keep].float().cpu().numpy(), b[keep].float().cpu().numpy()).min() >= 0.9995
+
+
+def test_sliding_window_shorter_than_the_prompt_takes_the_windowed_core():
+    """Mistral's sliding window (config.sliding_window; Zephyr ships 4096, longer than any 2048-token prompt): when a
+    sample is longer than the window the engine hands the attention to flash-attn's windowed varlen call, and the
+    result follows HF's sliding-window mask."""
+    from transformers import MistralConfig, MistralModel
+    from vision_zephyr_b200.mistral_prefill import MistralPrefillB200
+    cfg = MistralConfig(hidden_size=4096, intermediate_size=1024, num_hidden_layers=1, num_attention_heads=32,
+                        num_key_value_heads=8, vocab_size=100, rms_norm_eps=1e-5, rope_theta=10000.0, sliding_window=48,
+                        attn_implementation="sdpa")
+    torch.manual_seed(5)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device("cuda"):
+            m = MistralModel(cfg)
+    finally:
+        torch.set_default_dtype(old)
+    m.eval().requires_grad_(False)
+    B, L = 2, 160
+    x = torch.randn((B, L, 4096), device="cuda").to(torch.bfloat16)
+    mask = torch.ones((B, L), dtype=torch.long, device="cuda")
+    mask[1, 100:] = 0
+    with torch.no_grad():
+        ref = m(inputs_embeds=x, attention_mask=mask, use_cache=False).last_hidden_state
+        got = MistralPrefillB200(m).prefill(x, mask, None, None)
+    keep = mask.bool()
+    assert cos_rows(got[keep].float().cpu().numpy(), ref[keep].float().cpu().numpy()).min() >= 0.999
+
+
+def test_engine_refolds_when_the_weights_change():
+    """VisZephyrB200Model.native_prefill() keys its folded weights on (pointer, version) of every decoder parameter"""
+    from vision_zephyr_b200.language_model import VisZephyrB200Model, random_mistral_config
+    cfg = random_mistral_config(num_hidden_layers=1, intermediate_size=512, vocab_size=64)
+    # the LLM part alone: no vision modules are built without mm_vision_tower
+    cfg.mm_vision_tower = None
+    torch.manual_seed(2)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device("cuda"):
+            from transformers import MistralModel
+            m = MistralModel(cfg)
+    finally:
+        torch.set_default_dtype(old)
+    m.eval().requires_grad_(False)
+    m.__class__ = type("Patched", (MistralModel,), {"native_prefill": VisZephyrB200Model.native_prefill})
+    m._vz_prefill, m._vz_prefill_key = None, None
+    e1 = m.native_prefill()
+    assert m.native_prefill() is e1                      # unchanged weights: same engine
+    x = torch.randn((1, 40, 4096), device="cuda").to(torch.bfloat16)
+    with torch.no_grad():
+        a = e1.prefill(x, None, None, None).clone()
+        m.layers[0].mlp.down_proj.weight.mul_(0.5)       # in-place update bumps the version
+        e2 = m.native_prefill()
+        assert e2 is not e1
+        b = e2.prefill(x, None, None, None)
+        ref = m(inputs_embeds=x, use_cache=False).last_hidden_state
+    assert not torch.equal(a, b)
+    assert cos_rows(b[0].float().cpu().numpy(), ref[0].float().cpu().numpy()).min() >= 0.999
