@@ -82,7 +82,6 @@ int gather_rows_launch(const void* in, void* out, int M, int row_bytes, const in
                        int rows_per, cudaStream_t st);
 int softmax_rows_launch(const float* s, void* p, int rows, int n, float scale, cudaStream_t st);
 int vit_attn_tc_launch(const void* qkv, void* out, int T, cudaStream_t st);
-int vit_attn_tc2_launch(const void* qkv, void* out, int T, cudaStream_t st);
 int encode_tmap_2d_bf16(CUtensorMap* tm, const void* base, long long rows, int cols, int ld, int box_cols, int box_rows);
 int encode_tmap_3d_bf16(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows, int batch, long long bstride);
 int qattn_launch(int mode, const void* q, int q_rs, int q_zrows, const void* k0, const void* v0,

@@ -156,17 +156,13 @@ QfWs qf_layout(void* base, int T, int n_samples, int text_rows) {
 
 using namespace vz;
 
-// impl: 1 = the tcgen05 kernel with one softmax thread per query row (vz_attn_tc.cu), 2 = the split-row form
-// (vz_attn_tc2.cu: two threads per row, each with its own maximum / sum / accumulator), -1 = the default
-// (VZ_ATTN_IMPL=1|2 overrides).  (impl 0 used to select the first, mma.sync implementation; that kernel now lives
-// in libvz_b200_testonly.so as a cross-check for the tests and is not reachable from this library.)
+// impl: 1 or -1 = the tcgen05 kernel.  (impl 0 used to select the first, mma.sync implementation; that kernel now
+// lives in libvz_b200_testonly.so as a cross-check for the tests and is not reachable from this library.  A split-row
+// form -- two softmax threads per query row -- was impl 2 in commit 7f1ed23: correct, 7 % slower, removed.)
 extern "C" int vz_vit_attention(const void* qkv, void* out, int T, int impl, void* stream) {
   if (!qkv || !out || T <= 0) return VZ_ERR_BAD_ARG;
   if (!aligned16(qkv) || !aligned16(out)) return VZ_ERR_BAD_ARG;
-  if (impl == 0 || impl > 2) return VZ_ERR_UNSUPPORTED;
-  static const int def_impl = []() { const char* e = getenv("VZ_ATTN_IMPL"); const int v = e ? atoi(e) : 0; return (v == 1 || v == 2) ? v : 1; }();
-  if (impl < 0) impl = def_impl;
-  if (impl == 2) return vit_attn_tc2_launch(qkv, out, T, reinterpret_cast<cudaStream_t>(stream));
+  if (impl == 0 || impl > 1) return VZ_ERR_UNSUPPORTED;
   return vit_attn_tc_launch(qkv, out, T, reinterpret_cast<cudaStream_t>(stream));
 }
 
