@@ -864,14 +864,17 @@ int launch_tc(const vz_gemm_args& a, const GemmDev& p_in, int num_sms, cudaStrea
   p.sk_ws = nullptr; p.sk_flags = nullptr; p.sk_epoch = 0;
   // Stream-K tail: when the tile count is not a multiple of the worker count, the last (partial) round
   // leaves most SMs idle; instead the k-blocks of the last full round + the remainder are split evenly.
-  // Worth it when the balanced schedule beats the rounded one by more than the hand-over (~6 k-blocks).
+  // Worth it when the balanced schedule beats the rounded one by more than the hand-over.  Measured on single-tile
+  // problems (tools/gemm_small.py): the hand-over costs ~6.7 us = ~22 k-blocks, not the 6 assumed in round 1 -- the
+  // ViT out-proj of ONE tile (40 tiles of 16 k-blocks) ran 18.5 us split over 148 SMs against 15.3 us as whole tiles.
+  // (Also measured: loading the next worker's partial while the current one is added does not shorten it.)
   static const int sk_on = []() { const char* e = getenv("VZ_GEMM_SK"); return e ? atoi(e) : 1; }();
   const size_t sk_need = kSkFlagBytes + (size_t)num_sms * BM * BN * sizeof(float);
   if (sk_on && a.sk_ws && a.sk_ws_bytes >= sk_need && aligned16(a.sk_ws) && tiles % workers != 0 && p.num_k >= 8 &&
       tiles * p.num_k >= workers) {
     const long full = tiles / workers;
     const double t_dp = (double)(full + 1) * p.num_k;
-    const double t_sk = (double)tiles * p.num_k / workers + 6.0;
+    const double t_sk = (double)tiles * p.num_k / workers + 22.0;
     if (t_sk < 0.96 * t_dp) {
       p.sk_tiles = full == 0 ? (int)tiles : (int)(workers + tiles % workers);
       p.dp_tiles = (int)tiles - p.sk_tiles;
