@@ -991,6 +991,10 @@ int pick_tile_n(int M, int N, int batch, int num_sms) {
   //  so 192 is only reachable through VZ_GEMM_BN)
   (void)cost256; (void)cost192;
   if (N % 256 == 0 && tiles256 >= num_sms) bn = 256;
+  // small problems: when 128-wide tiles need a second, mostly empty round and 192-wide ones fit in one (the ViT fc1 of
+  // ONE tile: 160 vs 110 tiles on 148 SMs), the wider tile wins
+  const long tiles128 = num_m * ((N + 127) / 128) * batch;
+  if (bn == 128 && N >= 192 && tiles128 > num_sms && tiles192 <= num_sms) bn = 192;
   if (forced_bn == 256 && N % 256 == 0) bn = 256;
   if (forced_bn == 192 && N >= 192) bn = 192;
   if (forced_bn == 128) bn = 128;
@@ -1074,7 +1078,8 @@ int gemm_launch(const vz_gemm_args& a, cudaStream_t st) {
   // not a multiple of 256 or the problem has fewer 256-wide tiles than SMs.  The persistent grid works
   // in rounds of num_sms tiles; for mid-sized problems (the Q-Former's M = 32*T rows) 128x192 tiles
   // need fewer, cheaper rounds.  (VZ_GEMM_BN=256|192|128 overrides, for experiments.)
-  const int bn = pick_tile_n(a.M, a.N, batch, num_sms);
+  int bn = pick_tile_n(a.M, a.N, batch, num_sms);
+  if (bn == 192 && a.w_is_kn) bn = 128;   // the [K, N] operand form has no 192-wide instantiation
   if (bn == 256) {
     p.num_n = a.N / 256;
     // 2-CTA (cta_group::2) form for the large problems: 256-row pair tiles, a third less smem traffic
