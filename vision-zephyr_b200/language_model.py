@@ -2,8 +2,9 @@
 
 This is what INTEGRATION.md section 1 produces when applied to the reference's
   VisZephyrConfig / VisZephyrModel / VisZephyrForCausalLM   vis_zephyr/model/language_model/vis_zephyr.py:19-170
-i.e. the SAME class statements with the B200 mixins as bases.  The LLM body itself stays HF Mistral
-(out of scope); only the hand-over is here: forward / generate call
+i.e. the SAME class statements with the B200 mixins as bases.  The LLM body is HF Mistral, except that a
+sequence-starting, gradient-free forward can run its decoder stack natively on packed rows (mistral_prefill.py,
+config.vz_native_prefill); the hand-over is here: forward / generate call
 prepare_inputs_labels_for_multimodal and pass the 6-tuple on (vis_zephyr.py:76-98, :124-142), and
 generation re-attaches `images` / `images_size` to the step inputs (:144-168).
 Used by tests/test_gpu_llm.py, bench.py's c5_prefill_b8 workload and tools/; save_mm_projector is the
@@ -54,8 +55,9 @@ class VisZephyrB200Model(VisZephyrB200MetaModel, MistralModel):
             return False
         if past_key_values is not None and past_key_values.get_seq_length() != 0:
             return False
-        if attention_mask is not None and (attention_mask.dim() != 2 or attention_mask.shape[1] != inputs_embeds.shape[1]):
-            return False
+        if attention_mask is not None and (not isinstance(attention_mask, torch.Tensor) or attention_mask.dim() != 2
+                                           or attention_mask.shape[1] != inputs_embeds.shape[1]):
+            return False              # pre-built 4-D masks / mask dicts: HF's own path
         return not (kwargs.get("output_attentions") or kwargs.get("output_hidden_states"))
 
     def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None,
