@@ -40,3 +40,23 @@ d = anyres.slot_descriptor(0, 5, 576, "spatial_unpad", "anyres", (1000, 900), st
 print("merge rows", arch.merge_rows(feat, torch.zeros(4096, device="cuda", dtype=torch.bfloat16), [d])[0].shape)
 torch.cuda.synchronize()
 print("sanitize smoke done")
+
+# the prefill behind the splice: one decoder layer, ragged left-padded batch, KV cache filled
+from transformers import DynamicCache, MistralConfig, MistralModel
+from vision_zephyr_b200.mistral_prefill import MistralPrefillB200
+cfg = MistralConfig(hidden_size=4096, intermediate_size=1024, num_hidden_layers=1, num_attention_heads=32,
+                    num_key_value_heads=8, vocab_size=64, rms_norm_eps=1e-5, sliding_window=None)
+_old = torch.get_default_dtype()
+torch.set_default_dtype(torch.bfloat16)
+with torch.device("cuda"):
+    llm = MistralModel(cfg)
+torch.set_default_dtype(_old)
+llm.eval().requires_grad_(False)
+x = torch.randn((3, 140, 4096), device="cuda").to(torch.bfloat16)
+m = torch.zeros((3, 140), dtype=torch.long, device="cuda")
+for b, n in enumerate((140, 1, 77)):
+    m[b, 140 - n:] = 1
+with torch.no_grad():
+    cache = DynamicCache(config=cfg)
+    h = MistralPrefillB200(llm).prefill(x, m, None, cache)
+print("native prefill", tuple(h.shape), "cache", tuple(cache.layers[0].keys.shape), bool(torch.isfinite(h.float()).all()))
