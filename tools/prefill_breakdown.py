@@ -54,7 +54,7 @@ def main():
     attn_out = ws["attn"]
     stages = {
         "qkv_gemm (rmsnorm fused)": (lambda: gemm(x, L.w_qkv, M=M, N=6144, K=H, lda=H, ldw=H, out=qkv, ldo=6144, ln_stats=stats0,
-                                                  ln_np=1, ln_eps=1e-5, ln_rms=True, sk_ws=eng._sk), 2.0 * M * 6144 * H),
+                                                  ln_np=1, ln_eps=1e-5, ln_rms=True, sk_ws=ws["sk"]), 2.0 * M * 6144 * H),
         "rope": (lambda: lib.vz_rope_apply(qkv.data_ptr(), 6144, M, 40, 128, cs.data_ptr(), st), 0.0),
         "attention (vz_attn_causal, tcgen05)": (lambda: lib.vz_attn_causal(qkv.data_ptr(), 6144, M, attn_out.data_ptr(), 4096,
                                                                         items.data_ptr(), n_items, 32, 8, 128, 128 ** -0.5,
@@ -62,11 +62,11 @@ def main():
         "attention (flash-attn 2 varlen)": (lambda: flash_attn_varlen_func(q_v, k_v, v_v, cu, cu, max(LENS), max(LENS), causal=True),
                                             sum(n * n for n in LENS) * 8192.0 / 2 * 2),
         "o_proj (+residual +stats)": (lambda: gemm(a, L.w_o, M=M, N=H, K=H, lda=H, ldw=H, out=h_a, ldo=H, residual=x, ldr=H,
-                                                   stats_out=S, stats_np=np_h, sk_ws=eng._sk), 2.0 * M * H * H),
+                                                   stats_out=S, stats_np=np_h, sk_ws=ws["sk"]), 2.0 * M * H * H),
         "gate_up (rmsnorm + swiglu fused)": (lambda: gemm(h_a, L.w_gu, M=M, N=2 * I, K=H, lda=H, ldw=H, out=act, ldo=I, act=ACT_SWIGLU,
-                                                          ln_stats=S, ln_np=np_h, ln_eps=1e-5, ln_rms=True, sk_ws=eng._sk), 4.0 * M * I * H),
+                                                          ln_stats=S, ln_np=np_h, ln_eps=1e-5, ln_rms=True, sk_ws=ws["sk"]), 4.0 * M * I * H),
         "down_proj (+residual +stats)": (lambda: gemm(act, L.w_d, M=M, N=H, K=I, lda=I, ldw=I, out=h_b, ldo=H, residual=h_a, ldr=H,
-                                                      stats_out=S, stats_np=np_h, sk_ws=eng._sk), 2.0 * M * I * H),
+                                                      stats_out=S, stats_np=np_h, sk_ws=ws["sk"]), 2.0 * M * I * H),
     }
     out = {"rows": M, "lens": LENS, "stages": {}}
     for name, (fn, flops) in stages.items():

@@ -101,8 +101,7 @@ class MistralPrefillB200:
         self.attn_impl = "fa2" if os.environ.get("VZ_LLM_ATTN", "") == "fa2" else "native"
         if self.attn_impl == "native" and self.head_dim != 128:
             raise ValueError("vz_attn_causal is built for head_dim 128 (set VZ_LLM_ATTN=fa2 for other geometries)")
-        lib = _lib.load()
-        self._sk = torch.empty(lib.vz_gemm_sk_workspace_bytes(), dtype=torch.uint8, device=dev)
+        _lib.load()
 
     # ------------------------------------------------------------------------------------------
     def _buffers(self, M: int):
@@ -117,7 +116,9 @@ class MistralPrefillB200:
                       attn=torch.empty((cap, self.q_cols), dtype=bf, device=dev),
                       h=[torch.empty((cap, self.hidden), dtype=bf, device=dev) for _ in range(2)],
                       stats=torch.empty((cap, self.hidden // 64, 2), dtype=torch.float32, device=dev),
-                      cs=torch.empty((cap, self.head_dim // 2, 2), dtype=torch.float32, device=dev))
+                      cs=torch.empty((cap, self.head_dim // 2, 2), dtype=torch.float32, device=dev),
+                      # stream-K scratch of the GEMMs: exclusive to one stream at a time (vz_b200.h), so per stream too
+                      sk=torch.empty(_lib.load().vz_gemm_sk_workspace_bytes(), dtype=torch.uint8, device=dev))
             self._ws[key] = ws
         return ws
 
@@ -148,7 +149,7 @@ class MistralPrefillB200:
         if H != self.hidden or x.dtype != torch.bfloat16 or not x.is_contiguous():
             raise ValueError("forward_packed: x must be contiguous bf16 [M, hidden]")
         ws = self._buffers(M)
-        qkv, act, (h_a, h_b), S, cs = ws["qkv"], ws["act"], ws["h"], ws["stats"], ws["cs"]
+        qkv, act, (h_a, h_b), S, cs, sk = ws["qkv"], ws["act"], ws["h"], ws["stats"], ws["cs"], ws["sk"]
         # partial row statistics per output row of a [M, hidden] GEMM; every launch is ordered on one stream, so ONE
         # buffer serves all producers (a consumer has finished before the next producer starts)
         np_h = lib.vz_gemm_stats_partials(M, H)
@@ -183,7 +184,7 @@ class MistralPrefillB200:
         for li, L in enumerate(self.layers):
             # q | k | v = rmsnorm(h) W'^T
             gemm(h, L.w_qkv, M=M, N=self.qkv_cols, K=H, lda=H, ldw=H, out=qkv, ldo=self.qkv_cols,
-                 ln_stats=stats, ln_np=np_in, ln_eps=self.eps, ln_rms=True, sk_ws=self._sk)
+                 ln_stats=stats, ln_np=np_in, ln_eps=self.eps, ln_rms=True, sk_ws=sk)
             _lib.check(lib.vz_rope_apply(qkv.data_ptr(), self.qkv_cols, M, self.n_heads + self.n_kv, self.head_dim,
                                          cs.data_ptr(), st), "vz_rope_apply")
             if kv_sink is not None:
@@ -198,13 +199,13 @@ class MistralPrefillB200:
                                            window_size=window).view(M, self.q_cols)
             # h_a = h + a Wo^T, statistics of h_a for the post-attention RMSNorm
             gemm(a, L.w_o, M=M, N=H, K=self.q_cols, lda=self.q_cols, ldw=self.q_cols, out=h_a, ldo=H,
-                 residual=h, ldr=H, stats_out=S, stats_np=np_h, sk_ws=self._sk)
+                 residual=h, ldr=H, stats_out=S, stats_np=np_h, sk_ws=sk)
             # m = silu(rmsnorm(h_a) Wg'^T) * (rmsnorm(h_a) Wu'^T)
             gemm(h_a, L.w_gu, M=M, N=2 * self.inter, K=H, lda=H, ldw=H, out=act, ldo=self.inter, act=ACT_SWIGLU,
-                 ln_stats=S, ln_np=np_h, ln_eps=self.eps, ln_rms=True, sk_ws=self._sk)
+                 ln_stats=S, ln_np=np_h, ln_eps=self.eps, ln_rms=True, sk_ws=sk)
             # h_b = h_a + m Wd^T, statistics of h_b for the next layer's input RMSNorm
             gemm(act, L.w_d, M=M, N=H, K=self.inter, lda=self.inter, ldw=self.inter, out=h_b, ldo=H,
-                 residual=h_a, ldr=H, stats_out=S, stats_np=np_h, sk_ws=self._sk)
+                 residual=h_a, ldr=H, stats_out=S, stats_np=np_h, sk_ws=sk)
             h, stats, np_in = h_b, S, np_h
         return h[:M]
 
