@@ -43,9 +43,9 @@ IMAGES_PER_GPU, TILES_PER_IMAGE, SEQ = 8, 5, 64
 METRIC = "anyres images/sec (ViT-L/14-336 + Q-Former)"
 WEIGHT_BYTES = 2 * (303_507_456 - 1024 * 768 - 2 * 1024 + 1_678_428_160)   # bf16 CLIP (no projection head) + Q-Former
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full
-# capture of this same command (mean over the four ViT GEMM shapes: 249.9, 293.4, 207.5, 117.0 MB)
-TRAFFIC_PER_LAUNCH = 2.17e8
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel: ncu over the 178 GEMM launches of
+# one step of this same command (profiles/r2_gemm_traffic.md: 22.77 GB read + 8.31 GB written; algorithmic ~27.6 GB)
+TRAFFIC_PER_LAUNCH = 1.746e8
 
 
 def peaks():
@@ -813,9 +813,9 @@ def main():
         "clocks": clocks,
         "roofline": {"kernel": "gemm_bf16_tcgen05_kernel", "bound": "tensor", "achieved": gemm_tflops, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf if peak_tf else None,
-                     # dram__bytes_read+write per launch, ncu --set full, mean over the four ViT GEMM shapes
-                     # (profiles/r1_v9_final.md); algorithmic bytes of the same launches: 219 MB
-                     "traffic": TRAFFIC_PER_LAUNCH, "traffic_source": "profiles/r1_v9_final.md",
+                     # dram__bytes_read+write per launch, ncu, mean over the step's 178 GEMM launches
+                     # (profiles/r2_gemm_traffic.md); algorithmic bytes of the same launches: ~155 MB per launch
+                     "traffic": TRAFFIC_PER_LAUNCH, "traffic_source": "profiles/r2_gemm_traffic.md",
                      "peak_source": f"{pk_kind} bf16_tflops_sustained", "launches": int(n_g),
                      "gemm_ms_per_step": g_ms / args.steps,
                      "measured_in": "second pass of the same K steps with CUDA events around every kernel launch",
