@@ -270,3 +270,34 @@ def test_gate_up_interleave_and_cpu_forward_stays_hf():
     m = MistralModel(cfg).eval()
     with pytest.raises(vz._lib.VzError):
         MistralPrefillB200(m)             # CPU weights: loud failure, no fallback inside the engine
+
+
+def test_attn_causal_work_list_is_built_on_the_host():
+    """vz_attn_causal_items is pure host code: (128-query tile, head) items of every sample, longest first."""
+    import ctypes as C
+    from vision_zephyr_b200 import _lib
+    lib = _lib.load()
+    lens = np.asarray([300, 0, 37, 129, 1], dtype=np.int32)
+    nh = 4
+    tiles = [(s + 127) // 128 for s in lens]
+    n = lib.vz_attn_causal_items(lens.ctypes.data, len(lens), nh, None, 0, None)
+    assert n == sum(tiles) * nh
+    items = np.empty((n, 4), dtype=np.int32)
+    flops = C.c_double(0)
+    assert lib.vz_attn_causal_items(lens.ctypes.data, len(lens), nh, items.ctypes.data, n, C.byref(flops)) == n
+    assert flops.value == 4.0 * 128 * sum(int(s) * (int(s) + 1) / 2 for s in lens) * nh
+    assert lib.vz_attn_causal_items(lens.ctypes.data, len(lens), nh, items.ctypes.data, n - 1, None) == n   # too small: count only
+    starts = np.concatenate([[0], np.cumsum(lens)])
+    seen = set()
+    for q_row0, kv_row0, n_keys, hq in items:
+        h, qt = hq & 0xff, hq >> 8
+        b = int(np.searchsorted(starts, kv_row0, side="right") - 1)
+        while lens[b] == 0:
+            b += 1                                        # an empty sample shares its start row with the next one
+        assert starts[b] == kv_row0 and q_row0 == kv_row0 + qt * 128 and 0 <= h < nh
+        assert n_keys == min((qt + 1) * 128, lens[b])
+        seen.add((b, qt, h))
+    assert len(seen) == n                                 # every (sample, tile, head) exactly once
+    nkb = (items[:, 2] + 63) // 64
+    assert (np.diff(nkb) <= 0).all()                      # longest first
+    assert lib.vz_attn_causal_items(lens.ctypes.data, len(lens), 300, None, 0, None) < 0      # heads must fit 8 bits
