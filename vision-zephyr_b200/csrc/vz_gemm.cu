@@ -870,11 +870,18 @@ int launch_tc(const vz_gemm_args& a, const GemmDev& p_in, int num_sms, cudaStrea
   // (Also measured: loading the next worker's partial while the current one is added does not shorten it.)
   static const int sk_on = []() { const char* e = getenv("VZ_GEMM_SK"); return e ? atoi(e) : 1; }();
   const size_t sk_need = kSkFlagBytes + (size_t)num_sms * BM * BN * sizeof(float);
+  int sk_workers = workers;
   if (sk_on && a.sk_ws && a.sk_ws_bytes >= sk_need && aligned16(a.sk_ws) && tiles % workers != 0 && p.num_k >= 8 &&
       tiles * p.num_k >= workers) {
     const long full = tiles / workers;
+    // fewer tiles than workers: at most three workers per tile -- the finishing worker adds its partners' partial tiles
+    // one after the other (the single-tile cross-attention scores, 10 tiles of 80 k-blocks, were cut into ~15 pieces
+    // each: 35 us per launch).  Single-image call with a cap of 2 / 3 / 4 / 6 / 8 / none: 3.22 / 3.11 / 3.15 / 3.25 /
+    // 3.27 / 3.41 ms (VZ_GEMM_SK_MAXSPLIT, 0 = no cap).
+    static const int max_split = []() { const char* e = getenv("VZ_GEMM_SK_MAXSPLIT"); return e ? atoi(e) : 3; }();
+    if (full == 0 && max_split > 0 && tiles * max_split < sk_workers) sk_workers = (int)(tiles * max_split);
     const double t_dp = (double)(full + 1) * p.num_k;
-    const double t_sk = (double)tiles * p.num_k / workers + 22.0;
+    const double t_sk = (double)tiles * p.num_k / sk_workers + 22.0;
     if (t_sk < 0.96 * t_dp) {
       p.sk_tiles = full == 0 ? (int)tiles : (int)(workers + tiles % workers);
       p.dp_tiles = (int)tiles - p.sk_tiles;
@@ -884,7 +891,7 @@ int launch_tc(const vz_gemm_args& a, const GemmDev& p_in, int num_sms, cudaStrea
       if (p.sk_epoch == 0) p.sk_epoch = g_sk_epoch.fetch_add(1, std::memory_order_relaxed) + 1;
     }
   }
-  const int grid = (p.sk_tiles > 0 ? workers : (tiles < workers ? (int)tiles : workers)) * (TWO ? 2 : 1);
+  const int grid = (p.sk_tiles > 0 ? sk_workers : (tiles < workers ? (int)tiles : workers)) * (TWO ? 2 : 1);
   ProfScope prof(VZ_PROF_GEMM, 2.0 * a.M * (double)a.N * a.K * p.batch, st);
   if (TWO) {
     cudaLaunchConfig_t cfg = {};
